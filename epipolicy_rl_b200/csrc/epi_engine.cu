@@ -1,0 +1,835 @@
+// epi_engine.cu — host side of libepi_b200.so: EpiDesc -> DevPlan compiler, state management, C-ABI.
+//
+// Replaces: the per-day work of Epidemic.get_next_state / step / reset
+// (core/epidemic.py:82-116) and the sparse/dense helpers of epipolicy/matrix/* that only exist to
+// feed it. Static construction (make_static, the parsers) stays in the reference; its output
+// arrives here as an EpiDesc.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/epi_b200.h"
+#include "epi_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Unsupported { std::string msg; };
+struct Invalid { std::string msg; };
+struct CudaFail { std::string msg; };
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) throw CudaFail{std::string(#call) + ": " + cudaGetErrorString(e_)};     \
+  } while (0)
+
+template <class T>
+std::vector<T> vec(const T* p, size_t n) { return std::vector<T>(p, p + n); }
+
+}  // namespace
+
+struct epi_engine {
+  int device = 0, precision = 0, N = 0;
+  EpiDesc d{};                      // scalars only are valid after create
+  DevPlan plan{};
+  DevState S{}, init{};
+  std::vector<void*> allocs;
+  char *big_scratch = nullptr, *small_scratch = nullptr;
+  int cta_mode = 0, threads = 128, wpb = 4, grid = 1;
+  size_t smem_bytes = 0, scratch_bytes = 0;
+  int64_t launches = 0;
+  // host-buffer path
+  float* h_act = nullptr; float* d_act = nullptr;
+  void* h_obs = nullptr; void* d_obs = nullptr;
+  double* h_rew = nullptr; double* d_rew = nullptr;
+  uint8_t* h_done = nullptr; uint8_t* d_done = nullptr;
+  cudaStream_t stream = nullptr;
+  mutable std::string err;
+  double* dbg_attempts = nullptr;   // [N,64,2], allocated on first use of state selector 9
+  std::vector<int> acc_flat_host;   // [n_acc]
+  size_t real_size() const { return precision == EPI_FP64 ? 8 : 4; }
+
+  template <class T>
+  T* up(const std::vector<T>& v) {
+    T* p = nullptr;
+    size_t n = v.size() ? v.size() : 1;
+    CK(cudaMalloc(&p, n * sizeof(T)));
+    allocs.push_back(p);
+    if (v.size()) CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return p;
+  }
+  template <class T>
+  T* dalloc(size_t n, bool zero = true) {
+    T* p = nullptr;
+    CK(cudaMalloc(&p, (n ? n : 1) * sizeof(T)));
+    allocs.push_back(p);
+    if (zero) CK(cudaMemset(p, 0, (n ? n : 1) * sizeof(T)));
+    return p;
+  }
+};
+
+namespace {
+
+int64_t align16(int64_t x) { return (x + 15) & ~int64_t(15); }
+
+// ------------------------------------------------------------------------------------------
+// EpiDesc -> DevPlan
+// ------------------------------------------------------------------------------------------
+void build_plan(epi_engine* h, const EpiDesc& d) {
+  DevPlan& P = h->plan;
+  const int C = d.C, L = d.L, G = d.G, F = d.F, PP = d.P, I = d.I, LG = L * G;
+  if (C < 1 || L < 1 || G < 1 || F < 1 || I < 0) throw Invalid{"bad dimensions"};
+  if (G > 32 || F > 32) throw Unsupported{"more than 32 groups or facilities"};
+  P.C = C; P.L = L; P.G = G; P.F = F; P.P = PP; P.I = I; P.A = d.A; P.NCP = d.NCP; P.LG = LG; P.CLG = C * LG;
+  P.nnz = d.nnz; P.E = d.E; P.horizon = d.horizon; P.n_op = d.NOP; P.n_expr = d.NEXPR; P.n_sel = d.NSEL;
+  P.n_flat = (3 + C) * C * LG + I * L;
+
+  auto list = [&](int id) { return vec(d.list_data + d.list_off[id], (size_t)(d.list_off[id + 1] - d.list_off[id])); };
+  auto mask = [&](int id, int n) {
+    std::vector<uint8_t> m(n, 0);
+    for (int v : list(id)) { if (v < 0 || v >= n) throw Invalid{"list entry out of range"}; m[v] = 1; }
+    return m;
+  };
+
+  // ---- op -> program, expression -> owner
+  std::vector<int> op_prog(d.NOP, -1), expr_itv(d.NEXPR, 0), expr_prog(d.NEXPR, -1);
+  for (int p = 0; p < d.NPROG; p++)
+    for (int o = d.prog_off[p]; o < d.prog_off[p + 1]; o++) op_prog[o] = p;
+  for (int o = 0; o < d.NOP; o++) {
+    int e = d.op_expr[o];
+    if (e < 0 || e >= d.NEXPR) throw Invalid{"op_expr out of range"};
+    expr_itv[e] = d.op_itv[o];
+    expr_prog[e] = op_prog[o];
+  }
+  for (int e = 0; e < d.NEXPR; e++) {
+    int depth = 0, mx = 0;
+    for (int k = d.expr_off[e]; k < d.expr_off[e + 1]; k++) {
+      int op = d.tok_op[k];
+      depth += op <= 2 ? 1 : (op == 7 ? 0 : -1);
+      mx = depth > mx ? depth : mx;
+    }
+    if (mx > 16 || depth != 1) throw Unsupported{"expression too deep or malformed"};
+  }
+
+  // ---- locale classes: identical default tables and identical op coverage
+  std::vector<int> lclass(L), rep;
+  {
+    std::map<std::string, int> seen;
+    for (int l = 0; l < L; l++) {
+      std::string key;
+      for (int p = 0; p < PP; p++) key.append((const char*)(d.mp0 + ((size_t)p * L + l) * F * G), sizeof(float) * F * G);
+      key.append((const char*)(d.ft0 + (size_t)l * F * G), sizeof(float) * F * G);
+      key.append((const char*)(d.fi0 + (size_t)l * F * G * G), sizeof(float) * F * G * G);
+      for (int o = 0; o < d.NOP; o++) {
+        int k = d.op_kind[o];
+        if (k == EPI_OP_PARAM_MUL) key.push_back((char)mask(d.op_arg[8 * o + 1], L)[l]);
+        else if (k == EPI_OP_FI_MUL || k == EPI_OP_FT_MUL) key.push_back((char)mask(d.op_arg[8 * o + 0], L)[l]);
+      }
+      auto it = seen.find(key);
+      if (it == seen.end()) { it = seen.emplace(key, (int)rep.size()).first; rep.push_back(l); }
+      lclass[l] = it->second;
+    }
+  }
+  const int n_lc = (int)rep.size();
+  P.n_lc = n_lc;
+
+  // ---- multiplier classes
+  std::vector<int> mp_cls((size_t)n_lc * PP * F * G, 0), ft_cls((size_t)n_lc * F * G, 0), fi_cls((size_t)n_lc * F * G * G, 0);
+  std::vector<float> mp0((size_t)n_lc * PP * F * G), ft0((size_t)n_lc * F * G), fi0((size_t)n_lc * F * G * G);
+  std::map<std::vector<int>, int> cls_id;
+  std::vector<std::vector<int>> cls_list;
+  cls_id[{}] = 0; cls_list.push_back({});
+  auto get_cls = [&](const std::vector<int>& ops) {
+    auto it = cls_id.find(ops);
+    if (it == cls_id.end()) { it = cls_id.emplace(ops, (int)cls_list.size()).first; cls_list.push_back(ops); }
+    return it->second;
+  };
+  int has_ft_ops = 0;
+  {
+    // per op masks
+    struct OpM { int kind; std::vector<uint8_t> a, l, f, g, g2; };
+    std::vector<OpM> om(d.NOP);
+    for (int o = 0; o < d.NOP; o++) {
+      const int32_t* a = d.op_arg + 8 * o;
+      om[o].kind = d.op_kind[o];
+      if (om[o].kind == EPI_OP_PARAM_MUL) { om[o].a = mask(a[0], PP); om[o].l = mask(a[1], L); om[o].f = mask(a[2], F); om[o].g = mask(a[3], G); }
+      else if (om[o].kind == EPI_OP_FI_MUL) { om[o].l = mask(a[0], L); om[o].f = mask(a[1], F); om[o].g = mask(a[2], G); om[o].g2 = mask(a[3], G); }
+      else if (om[o].kind == EPI_OP_FT_MUL) { om[o].l = mask(a[0], L); om[o].f = mask(a[1], F); om[o].g = mask(a[2], G); has_ft_ops = 1; }
+      else if (om[o].kind == EPI_OP_MOB_MUL) throw Unsupported{"mobility multipliers (sim.apply with locale-from/locale-to) with a non-empty selection"};
+    }
+    for (int lc = 0; lc < n_lc; lc++) {
+      int l = rep[lc];
+      for (int p = 0; p < PP; p++) for (int f = 0; f < F; f++) for (int g = 0; g < G; g++) {
+        std::vector<int> ops;
+        for (int o = 0; o < d.NOP; o++)
+          if (om[o].kind == EPI_OP_PARAM_MUL && om[o].a[p] && om[o].l[l] && om[o].f[f] && om[o].g[g]) ops.push_back(o);
+        size_t idx = (((size_t)lc * PP + p) * F + f) * G + g;
+        mp_cls[idx] = get_cls(ops);
+        mp0[idx] = d.mp0[(((size_t)p * L + l) * F + f) * G + g];
+      }
+      for (int f = 0; f < F; f++) for (int g = 0; g < G; g++) {
+        std::vector<int> ops;
+        for (int o = 0; o < d.NOP; o++)
+          if (om[o].kind == EPI_OP_FT_MUL && om[o].l[l] && om[o].f[f] && om[o].g[g]) ops.push_back(o);
+        size_t idx = ((size_t)lc * F + f) * G + g;
+        ft_cls[idx] = get_cls(ops);
+        ft0[idx] = d.ft0[((size_t)l * F + f) * G + g];
+        for (int g2 = 0; g2 < G; g2++) {
+          std::vector<int> ops2;
+          for (int o = 0; o < d.NOP; o++)
+            if (om[o].kind == EPI_OP_FI_MUL && om[o].l[l] && om[o].f[f] && om[o].g[g] && om[o].g2[g2]) ops2.push_back(o);
+          fi_cls[idx * G + g2] = get_cls(ops2);
+          fi0[idx * G + g2] = d.fi0[(((size_t)l * F + f) * G + g) * G + g2];
+        }
+      }
+    }
+  }
+  P.has_ft_ops = has_ft_ops;
+  P.n_cls = (int)cls_list.size();
+  std::vector<int> cls_off{0}, cls_op;
+  for (auto& v : cls_list) { cls_op.insert(cls_op.end(), v.begin(), v.end()); cls_off.push_back((int)cls_op.size()); }
+
+  // ---- default (normalised) facility_timespent and the constant FOI-denominator kernel
+  std::vector<float> tden((size_t)n_lc * F * G * G);
+  std::vector<double> tden64((size_t)n_lc * F * G * G);
+  for (int lc = 0; lc < n_lc; lc++) {
+    std::vector<float> ftn((size_t)F * G);
+    for (int g = 0; g < G; g++) {
+      float s = 0.0f;
+      for (int f = 0; f < F; f++) s += ft0[((size_t)lc * F + f) * G + g];
+      for (int f = 0; f < F; f++) ftn[(size_t)f * G + g] = s > 1e-15f ? ft0[((size_t)lc * F + f) * G + g] / s : (f == 0 ? 1.0f : 0.0f);
+    }
+    for (int v = 0; v < F; v++) for (int u0 = 0; u0 < G; u0++) for (int u = 0; u < G; u++) {
+      size_t base = ((size_t)lc * F + v) * G;
+      double t64 = (double)ftn[(size_t)v * G + u] * (double)fi0[(base + u0) * G + u] * (double)fi0[(base + u) * G + u0];
+      tden64[(base + u0) * G + u] = t64;
+      tden[(base + u0) * G + u] = (float)t64;
+    }
+  }
+
+  // ---- constant combined mobility (no mobility ops): get_normalized_matrix (matrix/coo.py:173-188)
+  // with all multipliers 1, then compute_combined_mobility (core_optimize.py:69-92) in f32
+  std::vector<float> mx_csr((size_t)G * d.nnz, 0.0f), mx_csc((size_t)G * d.nnz, 0.0f);
+  {
+    std::vector<std::vector<float>> red(d.M);
+    for (int m = 0; m < d.M; m++) {
+      const int32_t* ip = d.mode_indptr + (size_t)m * (L + 1);
+      int nnz_m = d.mode_off[m + 1] - d.mode_off[m];
+      red[m].assign((size_t)G * nnz_m, 0.0f);
+      for (int g = 0; g < G; g++) {
+        const float* org = d.mode_origin + (size_t)G * d.mode_off[m] + (size_t)g * nnz_m;
+        const int32_t* ix = d.mode_indices + d.mode_off[m];
+        for (int r = 0; r < L; r++) {
+          double osum = 0;
+          for (int k = ip[r]; k < ip[r + 1]; k++) osum += org[k];
+          for (int k = ip[r]; k < ip[r + 1]; k++)
+            red[m][(size_t)g * nnz_m + k] = osum > 1e-15 ? (float)((double)org[k] / osum * osum) : (ix[k] == r ? (float)osum : 0.0f);
+        }
+      }
+    }
+    std::vector<int> cptr(d.csc_indptr, d.csc_indptr + L + 1), mi(d.M);
+    for (int r = 0; r < L; r++) {
+      for (int m = 0; m < d.M; m++) mi[m] = d.mode_indptr[(size_t)m * (L + 1) + r];
+      for (int k = d.csr_indptr[r]; k < d.csr_indptr[r + 1]; k++) {
+        int c = d.csr_indices[k];
+        int dest = cptr[c]++;
+        for (int m = 0; m < d.M; m++) {
+          const int32_t* ip = d.mode_indptr + (size_t)m * (L + 1);
+          const int32_t* ix = d.mode_indices + d.mode_off[m];
+          int nnz_m = d.mode_off[m + 1] - d.mode_off[m];
+          if (mi[m] < ip[r + 1] && c == ix[mi[m]]) {
+            for (int g = 0; g < G; g++) mx_csr[(size_t)g * d.nnz + k] += d.mode_bias[m] * red[m][(size_t)g * nnz_m + mi[m]];
+            mi[m]++;
+          }
+        }
+        for (int g = 0; g < G; g++) mx_csc[(size_t)g * d.nnz + dest] = mx_csr[(size_t)g * d.nnz + k];
+      }
+    }
+  }
+
+  // ---- selects
+  std::vector<uint8_t> sel_c((size_t)d.NSEL * C), sel_l((size_t)d.NSEL * L), sel_g((size_t)d.NSEL * G);
+  std::vector<int> sel_mode(d.NSEL), chg_slot(C, -1);
+  int n_chg = 0;
+  for (int s = 0; s < d.NSEL; s++) {
+    auto mc = mask(d.sel_arg[4 * s + 0], C), ml = mask(d.sel_arg[4 * s + 1], L), mg = mask(d.sel_arg[4 * s + 2], G);
+    std::copy(mc.begin(), mc.end(), sel_c.begin() + (size_t)s * C);
+    std::copy(ml.begin(), ml.end(), sel_l.begin() + (size_t)s * L);
+    std::copy(mg.begin(), mg.end(), sel_g.begin() + (size_t)s * G);
+    sel_mode[s] = d.sel_arg[4 * s + 3];
+    if (sel_mode[s] == EPI_SEL_CHANGE)
+      for (int c = 0; c < C; c++) if (mc[c] && chg_slot[c] < 0) chg_slot[c] = n_chg++;
+  }
+  P.n_chg = n_chg;
+
+  // ---- MOVE ops -> slots
+  std::vector<int> mv_op, mv_c1_off{0}, mv_c1, mv_c2_off{0}, mv_c2, slot_of_pair((size_t)C * C, -1);
+  std::vector<uint8_t> mv_g, mv_l1;
+  std::vector<std::pair<int, int>> slots;
+  for (int o = 0; o < d.NOP; o++) {
+    if (d.op_kind[o] != EPI_OP_MOVE) continue;
+    const int32_t* a = d.op_arg + 8 * o;
+    auto c1 = list(a[0]), c2 = list(a[3]);
+    auto l1 = mask(a[1], L), g1 = mask(a[2], G), l2 = mask(a[4], L), g2 = mask(a[5], G);
+    for (int x : c1) for (int y : c2) if (x == y) throw Unsupported{"sim.move between locales within one compartment"};
+    for (int l = 0; l < L; l++) if (l1[l] && !l2[l]) throw Unsupported{"sim.move across locales"};
+    mv_op.push_back(o);
+    for (int g = 0; g < G; g++) mv_g.push_back(g1[g] && g2[g]);
+    mv_l1.insert(mv_l1.end(), l1.begin(), l1.end());
+    mv_c1.insert(mv_c1.end(), c1.begin(), c1.end()); mv_c1_off.push_back((int)mv_c1.size());
+    mv_c2.insert(mv_c2.end(), c2.begin(), c2.end()); mv_c2_off.push_back((int)mv_c2.size());
+    for (int x : c1) for (int y : c2)
+      if (slot_of_pair[(size_t)x * C + y] < 0) { slot_of_pair[(size_t)x * C + y] = (int)slots.size(); slots.push_back({x, y}); }
+  }
+  const int n_slot = (int)slots.size();
+  if (n_slot > EPI_MAX_SLOTS) throw Unsupported{"more than 8 distinct move (c1,c2) pairs"};
+  for (int a = 0; a < n_slot; a++) for (int b = 0; b < n_slot; b++) {
+    if (a != b && slots[a].first == slots[b].first) throw Unsupported{"two moves out of one compartment (order-dependent clamp)"};
+    if (slots[a].second == slots[b].first) throw Unsupported{"a move target that is another move's source (order-dependent clamp)"};
+  }
+  P.n_slot = n_slot; P.n_mv_op = (int)mv_op.size();
+  std::vector<uint8_t> slot_cover((size_t)n_slot * LG, 0);
+  for (size_t mo = 0; mo < mv_op.size(); mo++)
+    for (int q1 = mv_c1_off[mo]; q1 < mv_c1_off[mo + 1]; q1++) for (int q2 = mv_c2_off[mo]; q2 < mv_c2_off[mo + 1]; q2++) {
+      int sl = slot_of_pair[(size_t)mv_c1[q1] * C + mv_c2[q2]];
+      for (int l = 0; l < L; l++) for (int g = 0; g < G; g++)
+        if (mv_l1[mo * L + l] && mv_g[mo * G + g]) slot_cover[(size_t)sl * LG + l * G + g] = 1;
+    }
+  for (int s = 0; s < n_slot; s++) { P.slot_c1[s] = slots[s].first; P.slot_c2[s] = slots[s].second; }
+
+  // ---- ADD ops
+  std::vector<int> add_op, add_parts;
+  std::vector<uint8_t> add_i, add_l;
+  for (int o = 0; o < d.NOP; o++) {
+    if (d.op_kind[o] != EPI_OP_ADD) continue;
+    const int32_t* a = d.op_arg + 8 * o;
+    auto mi = mask(a[0], I), ml = mask(a[1], L);
+    add_op.push_back(o);
+    add_parts.push_back((int)(list(a[0]).size() * list(a[1]).size()));
+    add_i.insert(add_i.end(), mi.begin(), mi.end());
+    add_l.insert(add_l.end(), ml.begin(), ml.end());
+  }
+  P.n_add_op = (int)add_op.size();
+
+  // ---- control-parameter expansion (epipolicy_environment.py:24-31,:40-47)
+  std::vector<int> cp_src(d.NCP, -1);
+  std::vector<float> cp_fixed(d.NCP, 0.0f);
+  std::vector<uint8_t> init_active(I);
+  int n_act = 0;
+  for (int i = 0; i < I; i++) {
+    init_active[i] = (uint8_t)(d.init_active[i] != 0);
+    for (int k = d.itv_cp_off[i]; k < d.itv_cp_off[i + 1]; k++) {
+      if (d.itv_is_cost[i]) cp_fixed[k] = d.cp_default[k];
+      else if (d.cp_min[k] == d.cp_max[k]) cp_fixed[k] = d.cp_min[k];
+      else cp_src[k] = n_act++;
+    }
+  }
+  if (n_act != d.A) throw Invalid{"EpiDesc.A does not match the number of free control parameters"};
+
+  // ---- regular edge programs
+  std::vector<int> ep_off{0}, ep;
+  for (int e = 0; e < d.E; e++) {
+    ep.push_back(d.edge_numer_off[e + 1] - d.edge_numer_off[e]);
+    for (int k = d.edge_numer_off[e]; k < d.edge_numer_off[e + 1]; k++) ep.push_back(d.fac[k]);
+    ep.push_back(d.edge_den_off[e + 1] - d.edge_den_off[e]);
+    for (int s = d.edge_den_off[e]; s < d.edge_den_off[e + 1]; s++) {
+      ep.push_back(s);
+      ep.push_back(d.sum_fac_off[s + 1] - d.sum_fac_off[s]);
+      for (int k = d.sum_fac_off[s]; k < d.sum_fac_off[s + 1]; k++) ep.push_back(d.fac[k]);
+    }
+    ep_off.push_back((int)ep.size());
+  }
+
+  // ---- infectious groups: edges with the same susceptible side and proportional scatter are one
+  // weighted force-of-infection problem (everything downstream of the FOI numerator is linear in X[c2])
+  struct Grp { int c0, p0; std::vector<int> np, dp; int ref_edge; std::vector<int> c2; std::vector<double> w; };
+  std::vector<Grp> grps;
+  for (int e = 0; e < d.IE; e++) {
+    std::vector<int> np = vec(d.ie_np + d.ie_np_off[e], (size_t)(d.ie_np_off[e + 1] - d.ie_np_off[e]));
+    std::vector<int> dp = vec(d.ie_dp + d.ie_dp_off[e], (size_t)(d.ie_dp_off[e + 1] - d.ie_dp_off[e]));
+    int s0 = d.sc_off[d.E + e], s1 = d.sc_off[d.E + e + 1];
+    bool placed = false;
+    for (auto& g : grps) {
+      if (g.c0 != d.ie_c0[e] || g.p0 != d.ie_p0[e] || g.np != np || g.dp != dp) continue;
+      int r0 = d.sc_off[d.E + g.ref_edge], r1 = d.sc_off[d.E + g.ref_edge + 1];
+      if (r1 - r0 != s1 - s0 || s1 == s0 || d.sc_coef[r0] == 0.0f) continue;
+      double ratio = (double)d.sc_coef[s0] / (double)d.sc_coef[r0];
+      bool ok = true;
+      for (int k = 0; k < s1 - s0 && ok; k++) {
+        ok = d.sc_kind[s0 + k] == d.sc_kind[r0 + k] && d.sc_a[s0 + k] == d.sc_a[r0 + k] && d.sc_b[s0 + k] == d.sc_b[r0 + k] &&
+             fabs((double)d.sc_coef[s0 + k] - ratio * (double)d.sc_coef[r0 + k]) <= 1e-13 * fabs((double)d.sc_coef[s0 + k]);
+      }
+      if (!ok) continue;
+      g.c2.push_back(d.ie_c2[e]); g.w.push_back(ratio); placed = true;
+      break;
+    }
+    if (!placed) grps.push_back(Grp{d.ie_c0[e], d.ie_p0[e], np, dp, e, {d.ie_c2[e]}, {1.0}});
+  }
+  const int NG = (int)grps.size();
+  if (NG > EPI_MAX_NG) throw Unsupported{"more than 8 infectious-edge groups"};
+  P.NG = NG; P.NSRC = d.E + NG + n_slot;
+  std::vector<int> ig_c0, ig_p0, ig_np_off{0}, ig_np, ig_dp_off{0}, ig_dp, ig_w_off{0}, ig_w_c2;
+  std::vector<double> ig_w;
+  for (auto& g : grps) {
+    ig_c0.push_back(g.c0); ig_p0.push_back(g.p0);
+    ig_np.insert(ig_np.end(), g.np.begin(), g.np.end()); ig_np_off.push_back((int)ig_np.size());
+    ig_dp.insert(ig_dp.end(), g.dp.begin(), g.dp.end()); ig_dp_off.push_back((int)ig_dp.size());
+    ig_w_c2.insert(ig_w_c2.end(), g.c2.begin(), g.c2.end()); ig_w.insert(ig_w.end(), g.w.begin(), g.w.end());
+    ig_w_off.push_back((int)ig_w.size());
+  }
+
+  // ---- gather lists
+  std::vector<std::vector<std::pair<int, float>>> xg(C);
+  std::map<int, int> acc_of_flat;  // flat row (in LG units) -> acc id
+  std::vector<std::vector<std::pair<int, float>>> ag;
+  std::vector<int> acc_flat;
+  auto acc_id = [&](int flat_row) {
+    auto it = acc_of_flat.find(flat_row);
+    if (it == acc_of_flat.end()) { it = acc_of_flat.emplace(flat_row, (int)ag.size()).first; ag.emplace_back(); acc_flat.push_back(flat_row); }
+    return it->second;
+  };
+  auto add_scatter = [&](int src, int s0, int s1) {
+    for (int k = s0; k < s1; k++) {
+      float coef = d.sc_coef[k];
+      int a = d.sc_a[k], b = d.sc_b[k];
+      if (a < 0 || a >= C) throw Invalid{"scatter compartment out of range"};
+      switch (d.sc_kind[k]) {
+        case EPI_SC_COMP: xg[a].push_back({src, coef}); break;
+        case EPI_SC_GAIN: ag[acc_id(C + a)].push_back({src, coef}); break;
+        case EPI_SC_LOST: ag[acc_id(2 * C + a)].push_back({src, coef}); break;
+        default: ag[acc_id(3 * C + a * C + b)].push_back({src, coef}); break;
+      }
+    }
+  };
+  for (int e = 0; e < d.E; e++) add_scatter(e, d.sc_off[e], d.sc_off[e + 1]);
+  for (int k = 0; k < NG; k++) add_scatter(d.E + k, d.sc_off[d.E + grps[k].ref_edge], d.sc_off[d.E + grps[k].ref_edge + 1]);
+  for (int s = 0; s < n_slot; s++) ag[acc_id(3 * C + slots[s].first * C + slots[s].second)].push_back({d.E + NG + s, 1.0f});
+  P.n_acc = (int)ag.size();
+  h->acc_flat_host = acc_flat;
+  std::vector<int> xg_off{0}, xg_src, ag_off{0}, ag_src;
+  std::vector<float> xg_coef, ag_coef;
+  for (auto& v : xg) { for (auto& pr : v) { xg_src.push_back(pr.first); xg_coef.push_back(pr.second); } xg_off.push_back((int)xg_src.size()); }
+  for (auto& v : ag) { for (auto& pr : v) { ag_src.push_back(pr.first); ag_coef.push_back(pr.second); } ag_off.push_back((int)ag_src.size()); }
+
+  // ---- workspace layout
+  const int64_t rs = (int64_t)h->real_size();
+  {
+    int64_t o = 0;
+    auto take = [&](int64_t bytes) { int64_t r = o; o = align16(o + bytes); return r; };
+    P.o_mult_y = take(4 * (int64_t)P.n_cls); P.o_mult_d = take(4 * (int64_t)P.n_cls);
+    P.o_cpv = take(4 * (int64_t)d.NCP); P.o_act = take(I);
+    P.o_expr = take(8 * (int64_t)d.NEXPR); P.o_sel = take(8 * (int64_t)d.NSEL);
+    P.o_mpt0 = take(4 * (int64_t)n_lc * PP * G); P.o_coefS = take(rs * (int64_t)NG * n_lc * F * G);
+    P.o_Tnum = take(4 * (int64_t)n_lc * F * G * G); P.o_Tden = take(has_ft_ops ? rs * (int64_t)n_lc * F * G * G : 0);
+    P.o_fi_y = take(4 * (int64_t)n_lc * F * G * G); P.o_fi_gap = take(4 * (int64_t)n_lc * F * G * G);
+    P.o_ft_y = take(4 * (int64_t)n_lc * F * G); P.o_ft_gap = take(4 * (int64_t)n_lc * F * G);
+    P.small_bytes = o;
+    o = 0;
+    const int64_t CLG = P.CLG, nA = (int64_t)P.n_acc * LG;
+    P.o_X = take(8 * CLG); P.o_ys = take(rs * CLG); P.o_K = take(rs * 7 * CLG);
+    P.o_accY = take(rs * nA); P.o_accB = take(rs * nA); P.o_accE = take(rs * nA); P.o_accF = take(rs * nA); P.o_accF2 = take(rs * nA);
+    P.o_flows = take(rs * (int64_t)P.NSRC * LG);
+    P.o_alive = take(rs * LG); P.o_Xw = take(rs * (int64_t)NG * LG); P.o_Ag = take(rs * LG); P.o_Wg = take(rs * (int64_t)NG * LG);
+    P.o_s = take(rs * (int64_t)NG * LG); P.o_r = take(rs * (int64_t)NG * LG);
+    P.o_mvY = take(4 * (int64_t)n_slot * LG); P.o_mvD = take(4 * (int64_t)n_slot * LG);
+    P.o_cost = take(8 * (int64_t)I * L); P.o_crY = take(8 * (int64_t)I * L); P.o_crD = take(8 * (int64_t)I * L);
+    P.has_src64 = (rs == 4 && n_slot > 0) ? 1 : 0;
+    P.o_ysS = take(P.has_src64 ? 8 * (int64_t)n_slot * LG : 0); P.o_KS = take(P.has_src64 ? 8 * 7 * (int64_t)n_slot * LG : 0);
+    P.big_bytes = o;
+  }
+
+  // ---- upload
+  std::vector<uint8_t> dummy8(1, 0);
+  P.alive_coef = h->up(vec(d.alive_coef, C)); P.X0 = h->up(vec(d.X0, (size_t)C * LG)); P.lclass = h->up(lclass);
+  P.mp0 = h->up(mp0); P.ft0 = h->up(ft0); P.fi0 = h->up(fi0); P.mp_cls = h->up(mp_cls); P.ft_cls = h->up(ft_cls); P.fi_cls = h->up(fi_cls);
+  P.Tden_const = h->up(tden); P.Tden_const64 = h->up(tden64); P.mx_csr = h->up(mx_csr); P.mx_csc = h->up(mx_csc);
+  P.csr_indptr = h->up(vec(d.csr_indptr, L + 1)); P.csr_indices = h->up(vec(d.csr_indices, d.nnz));
+  P.csc_indptr = h->up(vec(d.csc_indptr, L + 1)); P.csc_indices = h->up(vec(d.csc_indices, d.nnz));
+  P.cls_off = h->up(cls_off); P.cls_op = h->up(cls_op);
+  P.op_kind = h->up(vec(d.op_kind, d.NOP)); P.op_itv = h->up(vec(d.op_itv, d.NOP)); P.op_expr = h->up(vec(d.op_expr, d.NOP));
+  P.op_prog = h->up(op_prog); P.prog_step = h->up(vec(d.prog_step, I)); P.prog_init = h->up(vec(d.prog_init, I));
+  P.expr_off = h->up(vec(d.expr_off, d.NEXPR + 1)); P.tok_op = h->up(vec(d.tok_op, d.NTOK)); P.tok_arg = h->up(vec(d.tok_arg, d.NTOK));
+  P.tok_f32 = h->up(vec(d.tok_f32, d.NTOK)); P.tok_val = h->up(vec(d.tok_val, d.NTOK));
+  P.expr_itv = h->up(expr_itv); P.expr_prog = h->up(expr_prog);
+  P.sel_c = h->up(sel_c); P.sel_l = h->up(sel_l); P.sel_g = h->up(sel_g); P.sel_mode = h->up(sel_mode); P.chg_slot_of_comp = h->up(chg_slot);
+  P.mv_op = h->up(mv_op); P.mv_g = h->up(mv_g); P.mv_l1 = h->up(mv_l1); P.mv_c1_off = h->up(mv_c1_off); P.mv_c1 = h->up(mv_c1);
+  P.mv_c2_off = h->up(mv_c2_off); P.mv_c2 = h->up(mv_c2); P.slot_of_pair = h->up(slot_of_pair); P.slot_cover = h->up(slot_cover);
+  P.add_op = h->up(add_op); P.add_i = h->up(add_i); P.add_l = h->up(add_l); P.add_parts = h->up(add_parts);
+  P.cp_src = h->up(cp_src); P.cp_fixed = h->up(cp_fixed); P.init_cpv = h->up(vec(d.init_cpv, d.NCP)); P.init_active = h->up(init_active);
+  P.ep_off = h->up(ep_off); P.ep = h->up(ep); P.ep_coef = h->up(vec(d.sum_coef, d.NS));
+  P.ig_c0 = h->up(ig_c0); P.ig_p0 = h->up(ig_p0); P.ig_np_off = h->up(ig_np_off); P.ig_np = h->up(ig_np);
+  P.ig_dp_off = h->up(ig_dp_off); P.ig_dp = h->up(ig_dp); P.ig_w_off = h->up(ig_w_off); P.ig_w_c2 = h->up(ig_w_c2); P.ig_w = h->up(ig_w);
+  P.xg_off = h->up(xg_off); P.xg_src = h->up(xg_src); P.xg_coef = h->up(xg_coef);
+  P.ag_off = h->up(ag_off); P.ag_src = h->up(ag_src); P.ag_coef = h->up(ag_coef); P.acc_flat = h->up(acc_flat);
+}
+
+void alloc_state(epi_engine* h, DevState& S, int N) {
+  const DevPlan& P = h->plan;
+  size_t rs = h->real_size(), LG = P.LG;
+  S.X = h->dalloc<double>((size_t)N * P.CLG);
+  S.acc = h->dalloc<char>((size_t)N * P.n_acc * LG * rs);
+  S.cost = h->dalloc<double>((size_t)N * P.I * P.L);
+  S.crY = h->dalloc<double>((size_t)N * P.I * P.L);
+  S.mvY = h->dalloc<float>((size_t)N * P.n_slot * LG);
+  S.Xprev = h->dalloc<double>((size_t)N * P.n_chg * LG);
+  S.multY = h->dalloc<float>((size_t)N * P.n_cls);
+  S.meta = h->dalloc<int>((size_t)N * 8);
+  S.last_err = h->dalloc<double>((size_t)N);
+}
+
+void choose_launch(epi_engine* h) {
+  DevPlan& P = h->plan;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, h->device));
+  const int64_t smem_max = (int64_t)prop.sharedMemPerBlockOptin - 1024;  // leave room for static smem
+  const int sms = prop.multiProcessorCount;
+  int64_t per_env = P.small_bytes + P.big_bytes;
+  if (per_env * 8 <= (int64_t)prop.sharedMemPerMultiprocessor - 8 * 1024 || per_env <= 28 * 1024) {
+    // WARP teams: the whole working set of an env in shared memory
+    h->cta_mode = 0;
+    P.small_in_smem = P.big_in_smem = 1;
+    int wpb = 4;
+    while (wpb > 1 && per_env * wpb > smem_max) wpb >>= 1;
+    h->wpb = wpb; h->threads = 32 * wpb;
+    h->smem_bytes = (size_t)(per_env * wpb);
+    int ctas_per_sm = (int)((prop.sharedMemPerMultiprocessor - 1024) / (h->smem_bytes + 1024));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    if (ctas_per_sm * wpb > 48) ctas_per_sm = 48 / wpb;
+    int want = (h->N + wpb - 1) / wpb;
+    int cap = sms * ctas_per_sm;
+    h->grid = want < cap ? want : cap;
+    h->scratch_bytes = 0;
+  } else {
+    h->cta_mode = 1;
+    P.small_in_smem = P.small_bytes <= 96 * 1024;
+    P.big_in_smem = P.small_in_smem && (P.small_bytes + P.big_bytes <= smem_max);
+    h->threads = P.LG >= 2048 ? 512 : 256;
+    h->wpb = 1;
+    h->smem_bytes = (size_t)((P.small_in_smem ? P.small_bytes : 0) + (P.big_in_smem ? P.big_bytes : 0));
+    int ctas_per_sm = (int)((prop.sharedMemPerMultiprocessor - 1024) / (h->smem_bytes + 2048));
+    int by_threads = 1536 / h->threads;
+    if (ctas_per_sm > by_threads) ctas_per_sm = by_threads;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    int cap = sms * ctas_per_sm;
+    h->grid = h->N < cap ? h->N : cap;
+    int64_t per_team = (P.big_in_smem ? 0 : P.big_bytes) + (P.small_in_smem ? 0 : P.small_bytes);
+    h->scratch_bytes = (size_t)per_team * h->grid;
+    if (!P.big_in_smem) h->big_scratch = h->dalloc<char>((size_t)P.big_bytes * h->grid, false);
+    if (!P.small_in_smem) h->small_scratch = h->dalloc<char>((size_t)P.small_bytes * h->grid, false);
+  }
+}
+
+template <class real, bool CTA>
+void launch_t(epi_engine* h, const DevState& S, const epi::StepArgs& a, int grid, cudaStream_t st) {
+#ifdef EPI_HOST_EMU
+  (void)grid; (void)st;
+  epi::step_emulated<real, CTA>(h->plan, S, a);
+#else
+  auto kern = epi::step_kernel<real, CTA>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  kern<<<grid, h->threads, h->smem_bytes, st>>>(h->plan, S, a);
+  CK(cudaGetLastError());
+#endif
+  h->launches++;
+}
+
+void launch(epi_engine* h, const DevState& S, epi::StepArgs a, cudaStream_t st) {
+  a.big_scratch = h->big_scratch;
+  a.small_scratch = h->small_scratch;
+  a.dbg_attempts = (a.N == h->N) ? h->dbg_attempts : nullptr;
+  int grid = h->grid;
+  if (a.N < h->N) grid = 1;
+  if (h->precision == EPI_FP64) {
+    if (h->cta_mode) launch_t<double, true>(h, S, a, grid, st); else launch_t<double, false>(h, S, a, grid, st);
+  } else {
+    if (h->cta_mode) launch_t<float, true>(h, S, a, grid, st); else launch_t<float, false>(h, S, a, grid, st);
+  }
+}
+
+void do_reset(epi_engine* h, const uint8_t* mask, void* obs_out, cudaStream_t st) {
+  int grid = h->N < 4096 ? h->N : 4096;
+#ifdef EPI_HOST_EMU
+  (void)grid; (void)st;
+  if (h->precision == EPI_FP64) epi::reset_kernel<double>(h->plan, h->S, h->init, mask, h->N, obs_out);
+  else epi::reset_kernel<float>(h->plan, h->S, h->init, mask, h->N, obs_out);
+#else
+  if (h->precision == EPI_FP64) epi::reset_kernel<double><<<grid, 128, 0, st>>>(h->plan, h->S, h->init, mask, h->N, obs_out);
+  else epi::reset_kernel<float><<<grid, 128, 0, st>>>(h->plan, h->S, h->init, mask, h->N, obs_out);
+#endif
+  CK(cudaGetLastError());
+  h->launches++;
+}
+
+template <class F>
+int guarded(const epi_engine* h, F&& f) {
+  try {
+    f();
+    return EPI_OK;
+  } catch (const Unsupported& e) {
+    (h ? h->err : g_create_error) = "unsupported: " + e.msg;
+    return EPI_E_UNSUPPORTED;
+  } catch (const Invalid& e) {
+    (h ? h->err : g_create_error) = "invalid: " + e.msg;
+    return EPI_E_INVALID;
+  } catch (const CudaFail& e) {
+    (h ? h->err : g_create_error) = "cuda: " + e.msg;
+    return EPI_E_CUDA;
+  } catch (const std::bad_alloc&) {
+    (h ? h->err : g_create_error) = "out of host memory";
+    return EPI_E_NOMEM;
+  } catch (...) {
+    (h ? h->err : g_create_error) = "unknown failure";
+    return EPI_E_INVALID;
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int epi_create(const EpiDesc* desc, int n_envs, int device, int precision, epi_t** out) {
+  if (!desc || !out || n_envs < 1 || (precision != EPI_FP64 && precision != EPI_FP32)) {
+    g_create_error = "invalid: null descriptor/out pointer, n_envs < 1 or unknown precision";
+    return EPI_E_INVALID;
+  }
+  epi_engine* h = new epi_engine();
+  h->device = device; h->precision = precision; h->N = n_envs;
+  int rc = guarded(nullptr, [&] {
+    CK(cudaSetDevice(device));
+    h->d = *desc;
+    build_plan(h, *desc);
+    choose_launch(h);
+    alloc_state(h, h->S, n_envs);
+    alloc_state(h, h->init, 1);
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    // make_setting (core/epidemic.py:77-80): execute the schedule's day-0 action on the default state,
+    // keep the resulting parameters as "yesterday" of every fresh episode
+    {
+      DevState tmp = h->init;
+      std::vector<double> x0 = vec(desc->X0, (size_t)h->plan.CLG);
+      CK(cudaMemcpy(tmp.X, x0.data(), x0.size() * 8, cudaMemcpyHostToDevice));
+      std::vector<float> ones(h->plan.n_cls, 1.0f);
+      CK(cudaMemcpy(tmp.multY, ones.data(), ones.size() * 4, cudaMemcpyHostToDevice));
+      {
+        // the previous state of the default state is itself ('change' selects give 0, epidemic.py:96-99)
+        std::vector<int> chg(h->plan.C);
+        CK(cudaMemcpy(chg.data(), h->plan.chg_slot_of_comp, sizeof(int) * h->plan.C, cudaMemcpyDeviceToHost));
+        size_t LG = h->plan.LG;
+        for (int c = 0; c < h->plan.C; c++)
+          if (chg[c] >= 0) CK(cudaMemcpy(tmp.Xprev + (size_t)chg[c] * LG, tmp.X + (size_t)c * LG, LG * 8, cudaMemcpyDeviceToDevice));
+      }
+      epi::StepArgs a{};
+      a.variant = 1; a.n_days = 0; a.init_only = 1; a.N = 1;
+      launch(h, h->init, a, h->stream);
+      CK(cudaStreamSynchronize(h->stream));
+    }
+    do_reset(h, nullptr, nullptr, h->stream);
+    CK(cudaStreamSynchronize(h->stream));
+  });
+  if (rc != EPI_OK) {
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    *out = nullptr;
+    return rc;
+  }
+  *out = h;
+  return EPI_OK;
+}
+
+void epi_destroy(epi_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->h_act) cudaFreeHost(h->h_act);
+  if (h->h_obs) cudaFreeHost(h->h_obs);
+  if (h->h_rew) cudaFreeHost(h->h_rew);
+  if (h->h_done) cudaFreeHost(h->h_done);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* epi_last_error(const epi_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int epi_info(const epi_t* h, EpiInfo* o) {
+  if (!h || !o) return EPI_E_INVALID;
+  const DevPlan& P = h->plan;
+  memset(o, 0, sizeof(*o));
+  o->n_envs = h->N; o->precision = h->precision; o->device = h->device; o->obs_dim = P.CLG; o->action_dim = P.A;
+  o->ncp = P.NCP; o->n_itv = P.I; o->horizon = P.horizon; o->n_flat = P.n_flat; o->n_acc = P.n_acc; o->n_slot = P.n_slot;
+  o->n_lc = P.n_lc; o->n_groups_inf = P.NG; o->n_cls = P.n_cls; o->team_kind = h->cta_mode; o->threads = h->threads;
+  o->grid = h->grid; o->envs_per_cta = h->cta_mode ? 1 : h->wpb; o->smem_bytes = (int64_t)h->smem_bytes;
+  o->small_bytes = P.small_bytes; o->big_bytes = P.big_bytes; o->scratch_bytes = (int64_t)h->scratch_bytes;
+  int64_t rs = (int64_t)h->real_size();
+  o->state_bytes_per_env = 8 * (P.CLG + (int64_t)P.n_chg * P.LG) + rs * (int64_t)P.n_acc * P.LG + 16 * (int64_t)P.I * P.L +
+                           4 * ((int64_t)P.n_slot * P.LG + P.n_cls) + 32 + 8;
+  return EPI_OK;
+}
+
+int epi_reset(epi_t* h, const uint8_t* mask_dev, void* obs_out_dev, void* cuda_stream) {
+  if (!h) return EPI_E_INVALID;
+  return guarded(h, [&] {
+    CK(cudaSetDevice(h->device));
+    do_reset(h, mask_dev, obs_out_dev, (cudaStream_t)cuda_stream);
+  });
+}
+
+int epi_step(epi_t* h, const float* actions_dev, int n_days, void* obs_out_dev, double* reward_out_dev,
+             uint8_t* done_out_dev, void* cuda_stream) {
+  if (!h) return EPI_E_INVALID;
+  return guarded(h, [&] {
+    if (!actions_dev && h->plan.A > 0) throw Invalid{"actions_dev is NULL"};
+    if (n_days < 1) throw Invalid{"n_days < 1"};
+    CK(cudaSetDevice(h->device));
+    epi::StepArgs a{};
+    a.actions = actions_dev; a.variant = 0; a.n_days = n_days; a.N = h->N;
+    a.obs_out = obs_out_dev; a.reward_out = reward_out_dev; a.done_out = done_out_dev;
+    launch(h, h->S, a, (cudaStream_t)cuda_stream);
+  });
+}
+
+int epi_step_plan(epi_t* h, const float* cpv_dev, const uint8_t* active_dev, int schedule_programs, int n_days,
+                  void* obs_out_dev, double* reward_out_dev, uint8_t* done_out_dev, void* cuda_stream) {
+  if (!h) return EPI_E_INVALID;
+  return guarded(h, [&] {
+    if (!cpv_dev) throw Invalid{"cpv_dev is NULL"};
+    if (n_days < 1) throw Invalid{"n_days < 1"};
+    CK(cudaSetDevice(h->device));
+    epi::StepArgs a{};
+    a.cpv = cpv_dev; a.active = active_dev; a.variant = schedule_programs ? 1 : 0; a.n_days = n_days; a.N = h->N;
+    a.obs_out = obs_out_dev; a.reward_out = reward_out_dev; a.done_out = done_out_dev;
+    launch(h, h->S, a, (cudaStream_t)cuda_stream);
+  });
+}
+
+int epi_step_host(epi_t* h, const float* actions_host, int n_days, void* obs_out_host, double* reward_out_host,
+                  uint8_t* done_out_host) {
+  if (!h) return EPI_E_INVALID;
+  return guarded(h, [&] {
+    if (!actions_host && h->plan.A > 0) throw Invalid{"actions_host is NULL"};
+    if (n_days < 1) throw Invalid{"n_days < 1"};
+    CK(cudaSetDevice(h->device));
+    const size_t N = h->N, A = h->plan.A ? h->plan.A : 1, rs = h->real_size(), CLG = h->plan.CLG;
+    if (!h->h_act) {
+      CK(cudaMallocHost(&h->h_act, N * A * 4)); h->d_act = h->dalloc<float>(N * A);
+      CK(cudaMallocHost(&h->h_obs, N * CLG * rs)); h->d_obs = h->dalloc<char>(N * CLG * rs);
+      CK(cudaMallocHost(&h->h_rew, N * 8)); h->d_rew = h->dalloc<double>(N);
+      CK(cudaMallocHost(&h->h_done, N)); h->d_done = h->dalloc<uint8_t>(N);
+    }
+    if (h->plan.A > 0) {
+      memcpy(h->h_act, actions_host, N * h->plan.A * 4);
+      CK(cudaMemcpyAsync(h->d_act, h->h_act, N * h->plan.A * 4, cudaMemcpyHostToDevice, h->stream));
+    }
+    epi::StepArgs a{};
+    a.actions = h->d_act; a.variant = 0; a.n_days = n_days; a.N = h->N;
+    a.obs_out = obs_out_host ? h->d_obs : nullptr; a.reward_out = h->d_rew; a.done_out = h->d_done;
+    launch(h, h->S, a, h->stream);
+    if (obs_out_host) CK(cudaMemcpyAsync(h->h_obs, h->d_obs, N * CLG * rs, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_rew, h->d_rew, N * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_done, h->d_done, N, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (obs_out_host) memcpy(obs_out_host, h->h_obs, N * CLG * rs);
+    if (reward_out_host) memcpy(reward_out_host, h->h_rew, N * 8);
+    if (done_out_host) memcpy(done_out_host, h->h_done, N);
+  });
+}
+
+int epi_get_state(epi_t* h, int what, void* out, size_t bytes) {
+  if (!h || !out) return EPI_E_INVALID;
+  return guarded(h, [&] {
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    const DevPlan& P = h->plan;
+    const size_t N = h->N, rs = h->real_size(), LG = P.LG, nC = (size_t)P.I * P.L;
+    auto need = [&](size_t n) { if (bytes != n) throw Invalid{"buffer size mismatch: expected " + std::to_string(n) + " bytes"}; };
+    switch (what) {
+      case 0: need(N * P.CLG * 8); CK(cudaMemcpy(out, h->S.X, bytes, cudaMemcpyDeviceToHost)); break;
+      case 1: need(N * nC * 8); CK(cudaMemcpy(out, h->S.cost, bytes, cudaMemcpyDeviceToHost)); break;
+      case 2: {
+        need(N * 4);
+        std::vector<int> m(N * 8);
+        CK(cudaMemcpy(m.data(), h->S.meta, N * 32, cudaMemcpyDeviceToHost));
+        for (size_t e = 0; e < N; e++) ((int32_t*)out)[e] = m[e * 8];
+      } break;
+      case 3: {  // the reference's flat observable (obj/observable.py:24-25), structural zeros included
+        need(N * (size_t)P.n_flat * 8);
+        std::vector<double> X(N * P.CLG);
+        std::vector<char> acc(N * P.n_acc * LG * rs);
+        std::vector<double> cost(N * nC);
+        CK(cudaMemcpy(X.data(), h->S.X, X.size() * 8, cudaMemcpyDeviceToHost));
+        if (!acc.empty()) CK(cudaMemcpy(acc.data(), h->S.acc, acc.size(), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(cost.data(), h->S.cost, cost.size() * 8, cudaMemcpyDeviceToHost));
+        double* o = (double*)out;
+        memset(o, 0, bytes);
+        auto rd = [&](const std::vector<char>& v, size_t i) { return rs == 8 ? ((const double*)v.data())[i] : (double)((const float*)v.data())[i]; };
+        for (size_t e = 0; e < N; e++) {
+          double* f = o + e * (size_t)P.n_flat;
+          for (size_t i = 0; i < (size_t)P.CLG; i++) f[i] = X[e * P.CLG + i];
+          for (int a = 0; a < P.n_acc; a++)
+            for (size_t i = 0; i < LG; i++) f[(size_t)h->acc_flat_host[a] * LG + i] = rd(acc, (e * P.n_acc + a) * LG + i);
+          for (size_t i = 0; i < nC; i++) f[(size_t)(3 + P.C) * P.CLG + i] = cost[e * nC + i];
+        }
+      } break;
+      case 4: {
+        need(N * 16);
+        std::vector<int> m(N * 8);
+        CK(cudaMemcpy(m.data(), h->S.meta, N * 32, cudaMemcpyDeviceToHost));
+        for (size_t e = 0; e < N; e++) {
+          int32_t* t = (int32_t*)out + e * 4;
+          t[0] = m[e * 8 + 3]; t[1] = m[e * 8 + 4]; t[2] = m[e * 8 + 5]; t[3] = m[e * 8 + 2];
+        }
+      } break;
+      case 5: need(N * 8); CK(cudaMemcpy(out, h->S.last_err, bytes, cudaMemcpyDeviceToHost)); break;
+      case 6: need(N * nC * 8); CK(cudaMemcpy(out, h->S.crY, bytes, cudaMemcpyDeviceToHost)); break;
+      case 7: need(N * P.n_cls * 4); CK(cudaMemcpy(out, h->S.multY, bytes, cudaMemcpyDeviceToHost)); break;
+      case 8: need(N * P.n_slot * LG * 4); if (bytes) CK(cudaMemcpy(out, h->S.mvY, bytes, cudaMemcpyDeviceToHost)); break;
+      case 9: {  // (h, error_norm) per attempted RK step of the last day; recording starts at the first query
+        need(N * 128 * 8);
+        if (!h->dbg_attempts) h->dbg_attempts = h->dalloc<double>(N * 128);
+        CK(cudaMemcpy(out, h->dbg_attempts, bytes, cudaMemcpyDeviceToHost));
+      } break;
+      default: throw Invalid{"unknown state selector"};
+    }
+  });
+}
+
+int epi_set_state(epi_t* h, int what, const void* in, size_t bytes) {
+  if (!h || !in) return EPI_E_INVALID;
+  return guarded(h, [&] {
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    const DevPlan& P = h->plan;
+    const size_t N = h->N, rs = h->real_size(), nC = (size_t)P.I * P.L;
+    auto need = [&](size_t n) { if (bytes != n) throw Invalid{"buffer size mismatch: expected " + std::to_string(n) + " bytes"}; };
+    switch (what) {
+      case 0: need(N * P.CLG * 8); CK(cudaMemcpy(h->S.X, in, bytes, cudaMemcpyHostToDevice)); break;
+      case 1: need(N * nC * 8); CK(cudaMemcpy(h->S.cost, in, bytes, cudaMemcpyHostToDevice)); break;
+      case 2: {
+        need(N * 4);
+        std::vector<int> m(N * 8);
+        CK(cudaMemcpy(m.data(), h->S.meta, N * 32, cudaMemcpyDeviceToHost));
+        for (size_t e = 0; e < N; e++) m[e * 8] = ((const int32_t*)in)[e];
+        CK(cudaMemcpy(h->S.meta, m.data(), N * 32, cudaMemcpyHostToDevice));
+      } break;
+      case 6: need(N * nC * 8); CK(cudaMemcpy(h->S.crY, in, bytes, cudaMemcpyHostToDevice)); break;
+      case 7: need(N * P.n_cls * 4); CK(cudaMemcpy(h->S.multY, in, bytes, cudaMemcpyHostToDevice)); break;
+      case 8: need(N * P.n_slot * (size_t)P.LG * 4); if (bytes) CK(cudaMemcpy(h->S.mvY, in, bytes, cudaMemcpyHostToDevice)); break;
+      default: throw Invalid{"state selector not settable"};
+    }
+  });
+}
+
+int64_t epi_launch_count(const epi_t* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

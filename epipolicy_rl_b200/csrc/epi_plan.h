@@ -1,0 +1,113 @@
+// epi_plan.h — the device-side "compiled scenario" shared by the host builder and the kernels.
+//
+// A DevPlan is built once per engine from an EpiDesc (include/epi_desc.h). It holds
+//   * the reference's static tables, de-duplicated by LOCALE CLASS (locales whose default
+//     parameters, facility matrices and op coverage are identical share one table row; the
+//     shipped scenarios and the synthetic 1000-locale scenario all collapse to ONE class),
+//   * multiplier classes: for every parameter / facility cell the ordered list of PARAM_MUL /
+//     FI_MUL / FT_MUL ops that touch it (core/executor.py:116-164), so "apply the action" is a
+//     handful of per-env scalars instead of a dense [P,L,F,G] delta tensor,
+//   * infectious edges grouped by (susceptible compartment, transmission parameter, extra
+//     parameters): the 16 COVID edges become 2 weighted force-of-infection problems
+//     (core_optimize.py:98-163 recomputes the whole FOI matrix per edge),
+//   * scatter maps turned into gather lists (no atomics),
+//   * the per-env workspace layout (offsets) for the RK45 stages.
+#pragma once
+#include <stdint.h>
+
+#define EPI_MAX_SLOTS 8
+#define EPI_MAX_SEL 32
+
+struct DevPlan {
+  // ---- dimensions
+  int C, L, G, F, P, I, A, NCP, LG, CLG, nnz, n_lc;
+  int E;      // regular edges
+  int NG;     // infectious groups
+  int NSRC;   // E + NG + n_slot : rows of the flows buffer
+  int n_acc;  // cumulative accumulators with a non-zero derivative (pairs / gain / lost)
+  int n_slot; // move slots (distinct (c1,c2) of MOVE ops)
+  int n_chg;  // compartments referenced by value-mode 'change' selects
+  int n_sel, n_expr, n_cls, n_op;
+  int n_flat; // length of the reference's flat ODE state (error-norm denominator)
+  int horizon;
+  int has_ft_ops; // FT_MUL ops present -> T_den depends on the env
+  // ---- static tables (device pointers)
+  const double* alive_coef;  // [C]
+  const double* X0;          // [CLG]
+  const int* lclass;         // [L]
+  const float* mp0;          // [n_lc,P,F,G]
+  const float* ft0;          // [n_lc,F,G] raw default
+  const float* fi0;          // [n_lc,F,G,G] raw default
+  const int* mp_cls;         // [n_lc,P,F,G] multiplier class (0 = identity)
+  const int* ft_cls;         // [n_lc,F,G]
+  const int* fi_cls;         // [n_lc,F,G,G]
+  const float* Tden_const;   // [n_lc,F,G,G] ft*fi0*fi0^T with the default (normalised) ft, when !has_ft_ops
+  const double* Tden_const64;
+  const float* mx_csr;       // [G,nnz] combined mobility on the union pattern (core_optimize.py:69-92)
+  const float* mx_csc;       // [G,nnz]
+  const int *csr_indptr, *csr_indices, *csc_indptr, *csc_indices;
+  // ---- multiplier classes
+  const int* cls_off;        // [n_cls+1]
+  const int* cls_op;         // op ids in execution order
+  // ---- ops / programs / expressions (EpiDesc arrays, uploaded verbatim)
+  const int *op_kind, *op_itv, *op_expr, *op_prog; // op_prog: program the op belongs to
+  const int *prog_step, *prog_init;                // [I]
+  const int *expr_off, *tok_op, *tok_arg, *tok_f32;
+  const double* tok_val;
+  const int* expr_itv;       // [n_expr] intervention owning the expression
+  const int* expr_prog;      // [n_expr]
+  // selects: byte masks
+  const uint8_t *sel_c, *sel_l, *sel_g; // [n_sel,C] [n_sel,L] [n_sel,G]
+  const int* sel_mode;                  // [n_sel]
+  const int* chg_slot_of_comp;          // [C] index into Xprev rows or -1
+  // MOVE ops (case "different compartment, same locale", executor.py:201-212)
+  int n_mv_op;
+  const int* mv_op;                     // [n_mv_op] op id
+  const uint8_t *mv_g, *mv_l1;          // [n_mv_op,G] (groups in both selections) [n_mv_op,L]
+  const int *mv_c1_off, *mv_c1, *mv_c2_off, *mv_c2; // per MOVE op compartment lists
+  const int* slot_of_pair;              // [C*C] slot id or -1
+  int slot_c1[EPI_MAX_SLOTS], slot_c2[EPI_MAX_SLOTS];
+  const uint8_t* slot_cover;            // [n_slot,LG]
+  // ADD ops
+  int n_add_op;
+  const int* add_op;                    // [n_add_op]
+  const uint8_t *add_i, *add_l;         // [n_add_op,I] [n_add_op,L]
+  const int* add_parts;                 // [n_add_op]
+  // control-parameter expansion (epipolicy_environment.py:40-47)
+  const int* cp_src;                    // [NCP] action index or -1
+  const float* cp_fixed;                // [NCP] value when cp_src < 0
+  const float* init_cpv;                // [NCP]
+  const uint8_t* init_active;           // [I]
+  // ---- regular edges: interpreted programs
+  const int* ep_off;                    // [E+1]
+  const int* ep;                        // nNumer, facs..., nSummant, {coef_idx, nFac, facs...}
+  const float* ep_coef;
+  // ---- infectious groups
+  const int *ig_c0, *ig_p0, *ig_np_off, *ig_np, *ig_dp_off, *ig_dp, *ig_w_off, *ig_w_c2;
+  const double* ig_w;
+  // ---- gather lists
+  const int *xg_off, *xg_src; const float* xg_coef;    // [C+1]
+  const int *ag_off, *ag_src; const float* ag_coef;    // [n_acc+1]
+  const int* acc_flat;                                  // [n_acc] offset/LG in the reference flat layout
+  // ---- workspace layout (element offsets; see build_layout)
+  int small_in_smem, big_in_smem;
+  int64_t small_bytes, big_bytes;
+  int64_t o_mult_y, o_mult_d, o_cpv, o_act, o_expr, o_sel, o_mpt0, o_coefS, o_Tnum, o_Tden, o_fi_y, o_fi_gap,
+      o_ft_y, o_ft_gap;                                  // small region (bytes)
+  int64_t o_X, o_ys, o_K, o_accY, o_accB, o_accE, o_accF, o_accF2, o_flows, o_alive, o_Xw, o_Ag, o_Wg, o_s, o_r,
+      o_mvY, o_mvD, o_cost, o_crY, o_crD, o_ysS, o_KS;   // big region (bytes)
+  int has_src64;  // fp32 mode with move slots: the slots' source compartments are carried in double
+};
+
+// persistent per-env state in HBM (all [N, ...] arrays)
+struct DevState {
+  double* X;        // [N,CLG]            current_comp (double in both precision modes)
+  void* acc;        // real [N,n_acc*LG]  live cumulative_move / gain / lost components
+  double* cost;     // [N,I*L]            cumulative_cost
+  double* crY;      // [N,I*L]            yesterday's cost rate
+  float* mvY;       // [N,n_slot*LG]      yesterday's move table
+  double* Xprev;    // [N,n_chg*LG]       previous state's compartments used by 'change' selects
+  float* multY;     // [N,n_cls]          yesterday's class multipliers
+  int* meta;        // [N,8]: t, ex_y bits, status, nfev, nsteps, nrej, (2 spare)
+  double* last_err; // [N]
+};

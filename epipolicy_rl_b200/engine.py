@@ -1,0 +1,134 @@
+"""BatchedEpidemic — host-side mirror of the reference's `Epidemic` (core/epidemic.py:34-116) for N
+independent instances of one scenario, driving libepi_b200.so through its C-ABI. PyTorch is used only
+for device buffers and streams."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+from .desc import EpiDesc
+
+PERIOD = 7  # epipolicy_environment.py:1
+
+
+class BatchedEpidemic:
+    """N copies of one scenario on one GPU.
+
+    precision: "fp64" = parity mode (mirrors the reference's float32/float64 roundings, 1e-9),
+               "fp32" = throughput mode (state and stages in float32, 1e-4).
+    """
+
+    def __init__(self, desc: EpiDesc, n_envs: int, device: int | str | torch.device = 0, precision: str = "fp64"):
+        self.L = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedEpidemic needs a CUDA device (no CPU fallback)")
+        dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        if dev.type != "cuda":
+            raise ValueError("device must be a CUDA device")
+        self.device = dev
+        self.desc = desc
+        self.n_envs = int(n_envs)
+        self.precision = {"fp64": _lib.EPI_FP64, "fp32": _lib.EPI_FP32}[precision]
+        self.dtype = torch.float64 if precision == "fp64" else torch.float32
+        self.np_dtype = np.float64 if precision == "fp64" else np.float32
+        self._c = desc.as_c()
+        h = ctypes.c_void_p()
+        rc = self.L.epi_create(ctypes.byref(self._c), self.n_envs, dev.index or 0, self.precision, ctypes.byref(h))
+        if rc != 0:
+            raise _lib.EpiError(rc, self.L.epi_last_error(None).decode())
+        self._h = h
+        self.info = _lib.EpiInfo()
+        self._ck(self.L.epi_info(self._h, ctypes.byref(self.info)))
+        self.obs_dim, self.action_dim = self.info.obs_dim, self.info.action_dim
+        with torch.cuda.device(dev):
+            self.obs = torch.empty((self.n_envs, self.obs_dim), dtype=self.dtype, device=dev)
+            self.reward = torch.zeros(self.n_envs, dtype=torch.float64, device=dev)
+            self.done = torch.zeros(self.n_envs, dtype=torch.uint8, device=dev)
+        self.reset()
+
+    # ---------------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            raise _lib.EpiError(rc, self.L.epi_last_error(self._h).decode())
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.L.epi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    # ---------------------------------------------------------------------------------
+    def reset(self, mask: torch.Tensor | None = None) -> torch.Tensor:
+        """Epidemic.reset (epidemic.py:104-106) for all envs, or those where mask != 0."""
+        m = None
+        if mask is not None:
+            m = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        self._ck(self.L.epi_reset(self._h, m.data_ptr() if m is not None else None, self.obs.data_ptr(), self._stream()))
+        return self.obs
+
+    def step(self, actions: torch.Tensor, n_days: int = PERIOD):
+        """EpiEnv.step for the batch: actions [N, A] float32 in [0, 1] on the device.
+        Returns (obs [N, C*L*G], reward [N] float64, done [N] uint8) — views of engine-owned tensors."""
+        a = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        if a.shape != (self.n_envs, self.action_dim):
+            raise ValueError(f"actions must have shape {(self.n_envs, self.action_dim)}, got {tuple(a.shape)}")
+        self._ck(self.L.epi_step(self._h, a.data_ptr(), int(n_days), self.obs.data_ptr(), self.reward.data_ptr(),
+                                 self.done.data_ptr(), self._stream()))
+        return self.obs, self.reward, self.done
+
+    def step_plan(self, cpv: torch.Tensor, active: torch.Tensor | None, schedule_programs: bool = True, n_days: int = 1):
+        """Epidemic.step with explicit Acts (full control-parameter vectors + active flags)."""
+        c = cpv.to(device=self.device, dtype=torch.float32).contiguous()
+        a = None if active is None else active.to(device=self.device, dtype=torch.uint8).contiguous()
+        self._ck(self.L.epi_step_plan(self._h, c.data_ptr(), a.data_ptr() if a is not None else None,
+                                      1 if schedule_programs else 0, int(n_days), self.obs.data_ptr(),
+                                      self.reward.data_ptr(), self.done.data_ptr(), self._stream()))
+        return self.obs, self.reward, self.done
+
+    def step_host(self, actions: np.ndarray, n_days: int = PERIOD):
+        """The same step through host (numpy) buffers: H2D, launch, D2H inside the call."""
+        a = np.ascontiguousarray(actions, np.float32)
+        if a.shape != (self.n_envs, self.action_dim):
+            raise ValueError(f"actions must have shape {(self.n_envs, self.action_dim)}")
+        if not hasattr(self, "_h_obs"):
+            self._h_obs = np.empty((self.n_envs, self.obs_dim), self.np_dtype)
+            self._h_rew = np.empty(self.n_envs, np.float64)
+            self._h_done = np.empty(self.n_envs, np.uint8)
+        self._ck(self.L.epi_step_host(self._h, a.ctypes.data, int(n_days), self._h_obs.ctypes.data,
+                                      self._h_rew.ctypes.data, self._h_done.ctypes.data))
+        return self._h_obs, self._h_rew, self._h_done
+
+    # ---------------------------------------------------------------------------------
+    def get_state(self, what: str) -> np.ndarray:
+        d, N = self.desc, self.n_envs
+        spec = {
+            "X": (0, (N, d.C, d.L, d.G), np.float64), "cost": (1, (N, d.I, d.L), np.float64),
+            "day": (2, (N,), np.int32), "flat": (3, (N, d.n_flat), np.float64), "trace": (4, (N, 4), np.int32),
+            "last_err": (5, (N,), np.float64), "cost_rate": (6, (N, d.I, d.L), np.float64),
+            "mult": (7, (N, self.info.n_cls), np.float32), "moves": (8, (N, self.info.n_slot, d.L, d.G), np.float32),
+            "attempts": (9, (N, 64, 2), np.float64),
+        }[what]
+        out = np.empty(spec[1], spec[2])
+        self._ck(self.L.epi_get_state(self._h, spec[0], out.ctypes.data, out.nbytes))
+        return out
+
+    def set_state(self, what: str, value: np.ndarray) -> None:
+        code, dt = {"X": (0, np.float64), "cost": (1, np.float64), "day": (2, np.int32), "cost_rate": (6, np.float64),
+                    "mult": (7, np.float32), "moves": (8, np.float32)}[what]
+        v = np.ascontiguousarray(value, dt)
+        self._ck(self.L.epi_set_state(self._h, code, v.ctypes.data, v.nbytes))
+
+    @property
+    def launches(self) -> int:
+        return int(self.L.epi_launch_count(self._h))

@@ -1,0 +1,94 @@
+/* epi_b200.h — C-ABI of the B200-native batched epidemic step (libepi_b200.so).
+ *
+ * The reference (Nikunj-Gupta/Epipolicy_RL) has no FFI for this path: the seam is the Python
+ * method call `Epidemic.get_next_state / Epidemic.step / Epidemic.reset`
+ * (epipolicy/core/epidemic.py:82-116) driven by `EpiEnv.step / reset`
+ * (epipolicy_environment.py:39-66). These entry points are what a ctypes binding placed at that
+ * seam would call (INTEGRATION.md shows the binding). Plain pointers and sizes only.
+ *
+ * Conventions: every function returns 0 on success, a negative EPI_E_* code on failure and never
+ * throws; `epi_last_error(h)` (or `epi_last_error(NULL)` after a failed epi_create) gives the text.
+ * One handle = one CUDA device; calls on a handle are serialised by the caller; work is
+ * stream-ordered on the `cuda_stream` argument (a `cudaStream_t` cast to void*, NULL = default).
+ * "device" pointers are CUDA device memory owned by the caller (e.g. torch tensors).
+ */
+#ifndef EPI_B200_H
+#define EPI_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#include "epi_desc.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct epi_engine epi_t;
+
+enum { EPI_OK = 0, EPI_E_INVALID = -1, EPI_E_UNSUPPORTED = -2, EPI_E_CUDA = -3, EPI_E_NOMEM = -4 };
+enum { EPI_FP64 = 0, EPI_FP32 = 1 }; /* fp64 parity mode (1e-9) / fp32 throughput mode (1e-4) */
+
+typedef struct EpiInfo {
+  int32_t n_envs, precision, device;
+  int32_t obs_dim;     /* C*L*G, observation = current_comp.flatten() in [C,L,G] order */
+  int32_t action_dim;  /* A */
+  int32_t ncp, n_itv;  /* NCP, I */
+  int32_t horizon;
+  int32_t n_flat;      /* length of the reference's flat ODE state */
+  int32_t n_acc, n_slot, n_lc, n_groups_inf, n_cls;
+  int32_t team_kind;   /* 0 = warp per env, 1 = CTA per env */
+  int32_t threads, grid, envs_per_cta;
+  int64_t smem_bytes, small_bytes, big_bytes, scratch_bytes, state_bytes_per_env;
+} EpiInfo;
+
+/* Epidemic.__init__ + make_setting (core/epidemic.py:36-80) for n_envs independent instances of one
+ * scenario on CUDA device `device`. `desc` holds host pointers and is copied. */
+int epi_create(const EpiDesc* desc, int n_envs, int device, int precision, epi_t** out);
+void epi_destroy(epi_t* h);
+const char* epi_last_error(const epi_t* h);
+int epi_info(const epi_t* h, EpiInfo* out);
+
+/* Epidemic.reset (core/epidemic.py:104-106) for the envs whose mask byte is non-zero (mask NULL = all).
+ * obs_out: device [n_envs, obs_dim] of the handle's real type (double for EPI_FP64, float for EPI_FP32) or NULL. */
+int epi_reset(epi_t* h, const uint8_t* mask_dev, void* obs_out_dev, void* cuda_stream);
+
+/* EpiEnv.step (epipolicy_environment.py:39-62) for the batch: `actions_dev` float32 [n_envs, action_dim]
+ * in [0,1]; n_days simulated days with the same action fused in one launch (the reference's PERIOD = 7);
+ * stops early for an env that reaches the horizon. Outputs (each may be NULL):
+ *   obs_out_dev    real   [n_envs, obs_dim]
+ *   reward_out_dev double [n_envs]   sum over the days of -sum(delta cumulative_cost) (epidemic.py:115)
+ *   done_out_dev   uint8  [n_envs]   day counter >= horizon (no auto-reset, like the reference) */
+int epi_step(epi_t* h, const float* actions_dev, int n_days, void* obs_out_dev, double* reward_out_dev,
+             uint8_t* done_out_dev, void* cuda_stream);
+
+/* Epidemic.step (core/epidemic.py:108-116) with an explicit action list, as Epidemic.run uses it with
+ * the scenario's schedule (:125-128): full control-parameter vectors `cpv_dev` float32 [n_envs, ncp] and
+ * `active_dev` uint8 [n_envs, n_itv] (1 = the intervention has an Act today). `schedule_programs` = 1
+ * resolves locale selectors as the schedule's day-0 Acts do, 0 as locale_regex '*'. */
+int epi_step_plan(epi_t* h, const float* cpv_dev, const uint8_t* active_dev, int schedule_programs, int n_days,
+                  void* obs_out_dev, double* reward_out_dev, uint8_t* done_out_dev, void* cuda_stream);
+
+/* The same step through HOST buffers (what a CPU-side caller such as SB3's DummyVecEnv sees):
+ * pinned staging, H2D of the actions, the fused launch, D2H of obs/reward/done, then a stream sync. */
+int epi_step_host(epi_t* h, const float* actions_host, int n_days, void* obs_out_host, double* reward_out_host,
+                  uint8_t* done_out_host);
+
+/* State access for checkpoint/resume and parity injection. `what`:
+ *   0 X [n_envs, obs_dim] double        1 cumulative_cost [n_envs, I*L] double
+ *   2 day counter [n_envs] int32        3 reference-layout flat observable [n_envs, n_flat] double (get only)
+ *   4 trace [n_envs, 4] int32: nfev, accepted steps, rejected steps, status of the last simulated day
+ *   5 last error norm [n_envs] double   6 yesterday's cost rate [n_envs, I*L] double
+ *   7 yesterday's class multipliers [n_envs, n_cls] float    8 yesterday's move table [n_envs, n_slot*L*G] float
+ *   9 (h, error_norm) of each attempted RK45 step of the last day [n_envs, 64, 2] double (get only; recording
+ *     starts with the first query)
+ * Host buffers; sizes are checked. */
+int epi_get_state(epi_t* h, int what, void* out_host, size_t bytes);
+int epi_set_state(epi_t* h, int what, const void* in_host, size_t bytes);
+
+/* number of kernel launches issued by this handle so far (bench bookkeeping) */
+int64_t epi_launch_count(const epi_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EPI_B200_H */

@@ -68,6 +68,8 @@ typedef struct Oracle {
   int nfev, nsteps, nrej, status;
   double last_err;
   int last_nfev_total;
+  double attempts[128]; /* (h, err) of each attempted RK step of the last day */
+  int n_attempts;
 } Oracle;
 
 /* ------------------------------------------------------------------ utilities */
@@ -548,7 +550,7 @@ static void rk45_day(Oracle* o) {
   double* y = o->y;
   double* f = o->K[0];
   double t = 0.0;
-  o->nfev = 0; o->nsteps = 0; o->nrej = 0; o->status = 0; o->last_err = 0;
+  o->nfev = 0; o->nsteps = 0; o->nrej = 0; o->status = 0; o->last_err = 0; o->n_attempts = 0;
   rhs(o, t, y, f);
   /* select_initial_step (common.py:68-134), order = 4 */
   double h_abs;
@@ -606,6 +608,7 @@ static void rk45_day(Oracle* o) {
       }
       double err = rms(o->ytmp, n);
       o->last_err = err;
+      if (o->n_attempts < 64) { o->attempts[2 * o->n_attempts] = h; o->attempts[2 * o->n_attempts + 1] = err; o->n_attempts++; }
       if (err < 1) {
         double factor = err == 0 ? 10.0 : fmin(10.0, 0.9 * pow(err, -0.2));
         if (rejected) factor = fmin(1.0, factor);
@@ -759,6 +762,10 @@ int oracle_day(const Oracle* o) { return o->t; }
 void oracle_get_trace(const Oracle* o, int32_t* out4, double* last_err) {
   out4[0] = o->nfev; out4[1] = o->nsteps; out4[2] = o->nrej; out4[3] = o->status;
   if (last_err) *last_err = o->last_err;
+}
+int oracle_get_attempts(const Oracle* o, double* out, int cap) {
+  for (int i = 0; i < o->n_attempts && i < cap; i++) { out[2 * i] = o->attempts[2 * i]; out[2 * i + 1] = o->attempts[2 * i + 1]; }
+  return o->n_attempts;
 }
 /* which: 0 = yesterday (state.unobs), 1 = initial */
 void oracle_get_param(const Oracle* o, int which, float* mp, float* ft, float* fi, float* mob, double* cost) {

@@ -47,6 +47,7 @@ def lib():
         L.oracle_day.argtypes = [P]
         L.oracle_get_trace.argtypes = [P, P, P]
         L.oracle_get_param.argtypes = [P, ctypes.c_int, P, P, P, P, P]
+        L.oracle_get_attempts.argtypes = [P, P, ctypes.c_int]
         L.oracle_get_moves.argtypes = [P, ctypes.c_int, P, ctypes.c_int]
         L.oracle_rollout.restype = ctypes.c_double
         L.oracle_rollout.argtypes = [ctypes.POINTER(CEpiDesc), P, ctypes.c_int, ctypes.c_int, ctypes.c_int, P]
@@ -102,6 +103,13 @@ class Oracle:
         e = ctypes.c_double()
         lib().oracle_get_trace(self._h, _p(t), ctypes.byref(e))
         return dict(nfev=int(t[0]), nsteps=int(t[1]), nrej=int(t[2]), status=int(t[3]), last_err=e.value)
+
+    @property
+    def attempts(self):
+        """(h, error_norm) of every attempted RK45 step of the last simulated day"""
+        a = np.zeros((64, 2))
+        n = lib().oracle_get_attempts(self._h, _p(a), 64)
+        return a[:n]
 
     def params(self, which=0):
         d = self.desc

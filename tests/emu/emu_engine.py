@@ -1,0 +1,76 @@
+"""numpy-buffer driver of the HOST EMULATION build (tests only) — same C-ABI calls as
+epipolicy_rl_b200.engine.BatchedEpidemic, with host arrays standing in for device tensors."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from build_emu import build  # noqa: E402
+
+from epipolicy_rl_b200 import lib as _lib  # noqa: E402
+
+_L = None
+
+
+def emu_lib():
+    global _L
+    if _L is None:
+        _L = _lib.bind(ctypes.CDLL(build()))
+    return _L
+
+
+class EmuEngine:
+    def __init__(self, desc, n_envs, precision="fp64"):
+        self.L, self.desc, self.n_envs = emu_lib(), desc, n_envs
+        self.np_dtype = np.float64 if precision == "fp64" else np.float32
+        self._c = desc.as_c()
+        h = ctypes.c_void_p()
+        rc = self.L.epi_create(ctypes.byref(self._c), n_envs, 0, 0 if precision == "fp64" else 1, ctypes.byref(h))
+        if rc != 0:
+            raise _lib.EpiError(rc, self.L.epi_last_error(None).decode())
+        self._h = h
+        self.info = _lib.EpiInfo()
+        self.L.epi_info(self._h, ctypes.byref(self.info))
+        self.obs = np.zeros((n_envs, self.info.obs_dim), self.np_dtype)
+        self.reward = np.zeros(n_envs)
+        self.done = np.zeros(n_envs, np.uint8)
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise _lib.EpiError(rc, self.L.epi_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            self.L.epi_destroy(self._h)
+            self._h = None
+
+    def reset(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        self._ck(self.L.epi_reset(self._h, m.ctypes.data if m is not None else None, self.obs.ctypes.data, None))
+        return self.obs
+
+    def step(self, actions, n_days=7):
+        a = np.ascontiguousarray(actions, np.float32)
+        self._ck(self.L.epi_step(self._h, a.ctypes.data, n_days, self.obs.ctypes.data, self.reward.ctypes.data,
+                                 self.done.ctypes.data, None))
+        return self.obs, self.reward, self.done
+
+    def step_plan(self, cpv, active, schedule_programs=True, n_days=1):
+        c = np.ascontiguousarray(cpv, np.float32)
+        a = None if active is None else np.ascontiguousarray(active, np.uint8)
+        self._ck(self.L.epi_step_plan(self._h, c.ctypes.data, a.ctypes.data if a is not None else None,
+                                      1 if schedule_programs else 0, n_days, self.obs.ctypes.data,
+                                      self.reward.ctypes.data, self.done.ctypes.data, None))
+        return self.obs, self.reward, self.done
+
+    def get_state(self, what):
+        d, N = self.desc, self.n_envs
+        spec = {"X": (0, (N, d.C, d.L, d.G), np.float64), "cost": (1, (N, d.I, d.L), np.float64),
+                "day": (2, (N,), np.int32), "flat": (3, (N, d.n_flat), np.float64), "trace": (4, (N, 4), np.int32),
+                "last_err": (5, (N,), np.float64), "attempts": (9, (N, 64, 2), np.float64)}[what]
+        out = np.empty(spec[1], spec[2])
+        self._ck(self.L.epi_get_state(self._h, spec[0], out.ctypes.data, out.nbytes))
+        return out

@@ -1,0 +1,93 @@
+"""The product's own sources (EpiDesc -> DevPlan compiler, day prologue, RK45 controller, RHS, C-ABI)
+compiled for the HOST with a one-thread team (tests/emu) and checked against the reference's golden
+trajectories. No GPU needed; the `-m gpu` tests repeat these checks on the real kernels."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+from conftest import SCENARIOS  # noqa: E402
+from emu_engine import EmuEngine  # noqa: E402
+from helpers import cost_err, load, x_err  # noqa: E402
+
+TOL = {"fp64": 1e-9, "fp32": 1e-4}
+
+
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_env_plans_per_day_vs_reference(name, prec):
+    d, z = load(name)
+    eng = EmuEngine(d, 2, prec)
+    acts = np.stack([z["rnd_actions"], z["lax_actions"]], 1)
+    X = np.stack([z["rnd_X"], z["lax_X"]], 1)
+    C = np.stack([z["rnd_cost"], z["lax_cost"]], 1)
+    nf = np.stack([z["rnd_nfev"], z["lax_nfev"]], 1)
+    day, worst, worst_c, mism, rew = 0, 0.0, 0.0, 0, np.zeros((len(acts), 2))
+    for w, a in enumerate(acts):
+        for _ in range(7):
+            if day >= d.horizon:
+                break
+            _, r, done = eng.step(a, 1)
+            rew[w] += r
+            worst = max(worst, x_err(eng.get_state("X"), X[day], d))
+            worst_c = max(worst_c, cost_err(eng.get_state("cost"), C[day]))
+            mism += int(np.any(eng.get_state("trace")[:, 0] != nf[day]))
+            day += 1
+    ref_rew = np.stack([z["rnd_rewards"], z["lax_rewards"]], 1)
+    rerr = float(np.max(np.abs(rew - ref_rew) / np.abs(ref_rew)))
+    print(f"{name} {prec}: X {worst:.2e} cost {worst_c:.2e} reward {rerr:.2e} nfev-mismatch days {mism}")
+    assert day == d.horizon and bool(done.all())
+    assert worst <= TOL[prec] and worst_c <= TOL[prec] and rerr <= TOL[prec]
+    if prec == "fp64":
+        assert mism == 0
+    eng.close()
+
+
+@pytest.mark.parametrize("name", SCENARIOS + ["warmup_scenario"])
+def test_schedule_plan_vs_reference(name):
+    d, z = load(name)
+    eng = EmuEngine(d, 1, "fp64")
+    X, C = z["sched_X"], z["sched_cost"]
+    tot = 0.0
+    for day in range(len(X)):
+        _, r, _ = eng.step_plan(z["sched_plan_cpv"][day][None], z["sched_plan_active"][day][None].astype(np.uint8), True, 1)
+        tot += float(r[0])
+        assert x_err(eng.get_state("X"), X[day], d) <= 1e-9, day
+        assert cost_err(eng.get_state("cost"), C[day]) <= 1e-9, day
+        assert int(eng.get_state("trace")[0, 0]) == int(z["sched_nfev"][day])
+    assert abs(tot - z["sched_rewards"].sum()) <= 1e-9 * abs(tot)
+    eng.close()
+
+
+def test_known_answer_and_fused_week():
+    d, _ = load("warmup_scenario")
+    eng = EmuEngine(d, 1, "fp64")
+    cpv = d.cp_default.copy()
+    cpv[:3] = [0.2, 10, 10]
+    _, r, _ = eng.step_plan(cpv[None], None, False, 1)
+    assert abs(float(r[0]) - (-4566.504778395923)) <= 1e-9 * 4566.5
+    eng.close()
+    d, _ = load("COVID_B")
+    a = np.random.default_rng(3).uniform(0, 1, (3, d.A)).astype(np.float32)
+    e1, e7 = EmuEngine(d, 3, "fp64"), EmuEngine(d, 3, "fp64")
+    r1 = np.zeros(3)
+    for _ in range(7):
+        r1 += e1.step(a, 1)[1]
+    _, r7, _ = e7.step(a, 7)
+    assert np.array_equal(e1.get_state("X"), e7.get_state("X")) and np.allclose(r1, r7, rtol=1e-13)
+
+
+def test_unsupported_programs_are_refused_not_approximated():
+    """A mobility multiplier with a non-empty selection is outside the compiled op algebra of the
+    CUDA path: epi_create must fail with EPI_E_UNSUPPORTED."""
+    from epipolicy_rl_b200 import lib
+    from epipolicy_rl_b200.desc import OP_MOB_MUL
+    d, _ = load("COVID_C")
+    k = d.arrays["op_kind"].copy()
+    k[np.where(k == 1)[0][0]] = OP_MOB_MUL
+    d.arrays["op_kind"] = k
+    with pytest.raises(lib.EpiError) as ei:
+        EmuEngine(d, 1, "fp64")
+    assert ei.value.code == -2

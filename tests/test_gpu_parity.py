@@ -1,0 +1,206 @@
+"""Parity of the CUDA path (through the C-ABI) against the reference's own trajectories
+(tests/golden) and against the CPU oracle. Tolerances are BASELINE.json's: 1e-9 relative in the
+fp64 parity mode, 1e-4 in the fp32 throughput mode (metric: SURVEY.md §8d, absolute floor 1e-6*pop)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import SCENARIOS
+from helpers import cost_err, expand_actions, load, x_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp64": 1e-9, "fp32": 1e-4}
+
+
+def _engine(desc, n, prec):
+    from epipolicy_rl_b200.engine import BatchedEpidemic
+    return BatchedEpidemic(desc, n, device=0, precision=prec)
+
+
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_env_plans_per_day_vs_reference(name, prec):
+    """rnd and lax weekly plans of the golden file, both stepped day by day in one batch of 2 envs."""
+    d, z = load(name)
+    eng = _engine(d, 2, prec)
+    acts = np.stack([z["rnd_actions"], z["lax_actions"]], 1)  # [53, 2, A]
+    X = np.stack([z["rnd_X"], z["lax_X"]], 1)
+    C = np.stack([z["rnd_cost"], z["lax_cost"]], 1)
+    nf = np.stack([z["rnd_nfev"], z["lax_nfev"]], 1)
+    day, worst, worst_c, nfev_mismatch, rew = 0, 0.0, 0.0, 0, np.zeros((len(acts), 2))
+    for w, a in enumerate(acts):
+        at = torch.from_numpy(a).cuda()
+        for _ in range(7):
+            if day >= d.horizon:
+                break
+            _, r, done = eng.step(at, 1)
+            rew[w] += r.cpu().numpy()
+            worst = max(worst, x_err(eng.get_state("X"), X[day], d))
+            worst_c = max(worst_c, cost_err(eng.get_state("cost"), C[day]))
+            nfev_mismatch += int(np.any(eng.get_state("trace")[:, 0] != nf[day]))
+            day += 1
+    assert day == d.horizon and bool(done.all())
+    ref_rew = np.stack([z["rnd_rewards"], z["lax_rewards"]], 1)
+    rerr = float(np.max(np.abs(rew - ref_rew) / np.abs(ref_rew)))
+    print(f"{name} {prec}: X {worst:.2e} cost {worst_c:.2e} reward {rerr:.2e} nfev-mismatch days {nfev_mismatch}")
+    assert worst <= TOL[prec] and worst_c <= TOL[prec] and rerr <= TOL[prec]
+    assert np.all(np.sign(rew) == np.sign(ref_rew))
+    if prec == "fp64":
+        assert nfev_mismatch == 0  # identical RK45 accept/reject sequence
+    eng.close()
+
+
+@pytest.mark.parametrize("name", SCENARIOS + ["warmup_scenario"])
+def test_schedule_plan_vs_reference(name):
+    """BASELINE.json configs[0] (SIR_A fixed plan) and the same for every scenario: the scenario's own
+    schedule through daily Epidemic.step."""
+    d, z = load(name)
+    eng = _engine(d, 1, "fp64")
+    X, C = z["sched_X"], z["sched_cost"]
+    tot = 0.0
+    for day in range(len(X)):
+        cpv = torch.from_numpy(z["sched_plan_cpv"][day][None]).cuda()
+        act = torch.from_numpy(z["sched_plan_active"][day][None].astype(np.uint8)).cuda()
+        _, r, _ = eng.step_plan(cpv, act, True, 1)
+        tot += float(r[0])
+        assert x_err(eng.get_state("X"), X[day], d) <= 1e-9, day
+        assert cost_err(eng.get_state("cost"), C[day]) <= 1e-9, day
+        assert int(eng.get_state("trace")[0, 0]) == int(z["sched_nfev"][day])
+    assert abs(tot - z["sched_rewards"].sum()) <= 1e-9 * abs(tot)
+    if name == "SIR_A":
+        assert abs(tot - (-188953003.74567512)) <= 1e-9 * abs(tot)  # SURVEY.md Appendix C anchor
+    eng.close()
+
+
+def test_known_answer_user_ipynb():
+    d, _ = load("warmup_scenario")
+    eng = _engine(d, 1, "fp64")
+    cpv = d.cp_default.copy()
+    cpv[:3] = [0.2, 10, 10]
+    _, r, _ = eng.step_plan(torch.from_numpy(cpv[None]).cuda(), None, False, 1)
+    assert abs(float(r[0]) - (-4566.504778395923)) <= 1e-9 * 4566.5
+    eng.close()
+
+
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+def test_sirv_b_1024_envs_vs_oracle(prec):
+    """BASELINE.json configs[1]: SIRV_B, 1024 envs, env e uses default_rng(1000+e).uniform(0,1,(53,4))."""
+    from oracle.oracle import rollout
+    d, z = load("SIRV_B")
+    n = 1024
+    acts = np.stack([np.random.default_rng(1000 + e).uniform(0, 1, (53, d.A)).astype(np.float32) for e in range(n)])
+    eng = _engine(d, n, prec)
+    rew = np.zeros(n)
+    for s in range(53):
+        obs, r, done = eng.step(torch.from_numpy(acts[:, s]).cuda(), 7)
+        rew += r.cpu().numpy()
+    total, fin = rollout(d, acts)
+    e = x_err(obs.double().cpu().numpy(), fin, d)
+    print(f"SIRV_B x1024 {prec}: final X err {e:.2e}, reward-sum err {abs(rew.sum() - total) / abs(total):.2e}")
+    assert e <= TOL[prec]
+    assert abs(rew.sum() - total) <= TOL[prec] * abs(total)
+    # and the 16 envs the reference itself ran
+    assert x_err(obs[:16].double().cpu().numpy(), z["batch_X"][:, -1], d) <= TOL[prec]
+    assert np.max(np.abs(rew[:16] - z["batch_rewards"].sum(1)) / np.abs(z["batch_rewards"].sum(1))) <= TOL[prec]
+    assert bool(done.all())
+    eng.close()
+
+
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+def test_covid_c_batch_vs_oracle(prec):
+    """BASELINE.json configs[2] spot check: 64 of the 4096 COVID_C envs against the oracle."""
+    from oracle.oracle import rollout
+    d, _ = load("COVID_C")
+    n, steps = 4096, 8
+    g = torch.Generator().manual_seed(1234)
+    acts = torch.rand((steps, n, d.A), generator=g)
+    eng = _engine(d, n, prec)
+    rew = np.zeros(n)
+    for s in range(steps):
+        obs, r, _ = eng.step(acts[s].cuda(), 7)
+        rew += r.cpu().numpy()
+    idx = np.arange(0, n, 64)
+    total, fin = rollout(d, acts[:, idx].permute(1, 0, 2).numpy())
+    e = x_err(obs[idx].double().cpu().numpy(), fin, d)
+    print(f"COVID_C x4096 {prec}: X err on 64 envs {e:.2e}")
+    assert e <= TOL[prec]
+    assert abs(rew[idx].sum() - total) <= TOL[prec] * abs(total)
+    eng.close()
+
+
+def test_fused_week_equals_seven_days_and_host_path():
+    d, _ = load("COVID_B")
+    a = torch.rand((16, d.A), generator=torch.Generator().manual_seed(3))
+    e1, e7, eh = _engine(d, 16, "fp64"), _engine(d, 16, "fp64"), _engine(d, 16, "fp64")
+    r1 = np.zeros(16)
+    for _ in range(7):
+        _, r, _ = e1.step(a.cuda(), 1)
+        r1 += r.cpu().numpy()
+    o7, r7, _ = e7.step(a.cuda(), 7)
+    oh, rh, dh = eh.step_host(a.numpy(), 7)
+    assert np.array_equal(e1.get_state("X"), e7.get_state("X"))  # same arithmetic, bit-identical
+    assert np.allclose(r1, r7.cpu().numpy(), rtol=1e-13)
+    assert np.array_equal(oh, o7.cpu().numpy()) and np.array_equal(rh, r7.cpu().numpy()) and not dh.any()
+    for e in (e1, e7, eh):
+        e.close()
+
+
+def test_reset_mask_done_and_state_roundtrip():
+    d, _ = load("SIRV_A")
+    eng = _engine(d, 8, "fp64")
+    a = torch.full((8, d.A), 0.3).cuda()
+    x0 = eng.get_state("X").copy()
+    for _ in range(3):
+        eng.step(a, 7)
+    assert np.all(eng.get_state("day") == 21)
+    mask = torch.tensor([1, 0, 0, 1, 0, 0, 0, 0], dtype=torch.uint8)
+    eng.reset(mask)
+    day = eng.get_state("day")
+    assert list(day) == [0, 21, 21, 0, 21, 21, 21, 21]
+    X = eng.get_state("X")
+    assert np.array_equal(X[0], x0[0]) and not np.array_equal(X[1], x0[1])
+    # a reset env replays exactly the same trajectory
+    eng2 = _engine(d, 8, "fp64")
+    eng.step(a, 7)
+    eng2.step(a, 7)
+    assert np.array_equal(eng.get_state("X")[0], eng2.get_state("X")[0])
+    # done: horizon reached, stepping continues afterwards like the reference (no auto-reset)
+    eng2.set_state("day", np.full(8, d.horizon - 3, np.int32))
+    _, _, done = eng2.step(a, 7)
+    assert bool(done.all()) and np.all(eng2.get_state("day") == d.horizon)
+    _, _, done = eng2.step(a, 7)
+    assert bool(done.all()) and np.all(eng2.get_state("day") == d.horizon + 1)
+    # flat observable in the reference's layout has the right length and carries X and cost
+    flat = eng.get_state("flat")
+    assert flat.shape == (8, d.n_flat)
+    assert np.array_equal(flat[:, : d.C * d.L * d.G].reshape(X.shape), eng.get_state("X"))
+    eng.close()
+    eng2.close()
+
+
+def test_error_paths():
+    from epipolicy_rl_b200 import lib
+    d, _ = load("SIR_A")
+    eng = _engine(d, 4, "fp64")
+    with pytest.raises(ValueError):
+        eng.step(torch.zeros((3, d.A)).cuda())
+    with pytest.raises(lib.EpiError):
+        eng.step(torch.zeros((4, d.A)).cuda(), 0)
+    with pytest.raises(lib.EpiError):
+        eng._ck(eng.L.epi_get_state(eng._h, 0, np.zeros(1).ctypes.data, 8))
+    eng.close()
+
+
+def test_single_env_twin_matches_reference_weekly():
+    """EpiEnv twin: float64 numpy obs, python float reward, bool done — checked on the reference's rnd plan."""
+    from epipolicy_rl_b200.env import EpiEnv
+    d, z = load("COVID_A")
+    env = EpiEnv(d)
+    obs = env.reset()
+    assert obs.dtype == np.float64 and obs.shape == (d.C * d.L * d.G,)
+    assert env.action_space.shape == (2,) and env.act_domain.shape == (6, 2)
+    for w in range(10):
+        obs, r, done, info = env.step(z["rnd_actions"][w])
+        assert x_err(obs, z["rnd_obs_weekly"][w], d) <= 1e-9
+        assert abs(r - z["rnd_rewards"][w]) <= 1e-9 * abs(r) and done is False and info == {}

@@ -1,0 +1,83 @@
+"""The CPU oracle against outputs of the unmodified reference (tests/golden, made by tools/gen_golden.py).
+This is what pins the oracle (the reference ships no tests of its own)."""
+import numpy as np
+import pytest
+
+from conftest import SCENARIOS
+from helpers import cost_err, load, x_err
+from oracle.oracle import Oracle, rollout
+
+
+@pytest.mark.parametrize("name", SCENARIOS + ["warmup_scenario"])
+def test_initial_parameter_literal(name):
+    d, z = load(name)
+    p = Oracle(d).params(1)
+    for k in ("mp", "ft", "fi", "mob"):
+        assert np.array_equal(p[k], z[f"init_{k}"].reshape(p[k].shape)), k  # float32 tables: bit-exact
+    assert np.allclose(p["cost"], z["init_cost"], rtol=1e-12, atol=0)
+    assert np.array_equal(p["moves"], z["init_moves"].reshape(p["moves"].shape))
+
+
+@pytest.mark.parametrize("name", SCENARIOS)
+@pytest.mark.parametrize("plan", ["rnd", "lax"])
+def test_env_plans_per_day(name, plan):
+    d, z = load(name)
+    o = Oracle(d)
+    X, C, acts = z[f"{plan}_X"], z[f"{plan}_cost"], z[f"{plan}_actions"]
+    day, nfev, rew = 0, [], []
+    for a in acts:
+        tot = 0.0
+        for _ in range(7):
+            if day >= d.horizon:
+                break
+            _, r, _ = o.step(a, 1)
+            tot += r
+            assert x_err(o.X, X[day], d) <= 1e-11, (day,)
+            assert cost_err(o.cost, C[day]) <= 1e-11, (day,)
+            if day < 10:  # the day's dest parameters (float32 tables bit-exact)
+                p = o.params(0)
+                for k in ("mp", "ft", "fi", "mob"):
+                    assert np.array_equal(p[k], z[f"{plan}_p_{k}"][day].reshape(p[k].shape)), (day, k)
+                assert np.array_equal(p["moves"], z[f"{plan}_p_moves{day}"].reshape(p["moves"].shape)), day
+                assert np.allclose(p["cost"], z[f"{plan}_p_cost"][day], rtol=1e-11, atol=1e-6)
+            nfev.append(o.trace["nfev"])
+            day += 1
+        rew.append(tot)
+    assert np.array_equal(np.array(nfev), z[f"{plan}_nfev"])  # identical RK45 step sequence
+    assert np.allclose(rew, z[f"{plan}_rewards"], rtol=1e-11)
+
+
+@pytest.mark.parametrize("name", SCENARIOS + ["warmup_scenario"])
+def test_schedule_plan(name):
+    d, z = load(name)
+    o = Oracle(d)
+    X, C = z["sched_X"], z["sched_cost"]
+    rew, nfev = [], []
+    for day in range(len(X)):
+        rew.append(o.day_step(z["sched_plan_cpv"][day], z["sched_plan_active"][day], init_programs=True))
+        assert x_err(o.X, X[day], d) <= 1e-11
+        assert cost_err(o.cost, C[day]) <= 1e-11
+        nfev.append(o.trace["nfev"])
+    assert np.array_equal(np.array(nfev), z["sched_nfev"])
+    assert np.allclose(rew, z["sched_rewards"], rtol=1e-10, atol=1e-6)
+
+
+def test_known_answer_user_ipynb():
+    """user.ipynb:82 — epi.step([construct_act(0,[0.2,10,10])]) on the warm-up scenario."""
+    d, z = load("warmup_scenario")
+    o = Oracle(d)
+    cpv = d.cp_default.copy()
+    cpv[:3] = [0.2, 10, 10]
+    r = o.day_step(cpv, np.ones(d.I, np.int32))
+    assert abs(r - (-4566.504778395923)) <= 1e-9
+    assert abs(float(z["known_answer_reward"][0]) - (-4566.504778395923)) == 0.0
+
+
+def test_sirv_b_batch_subset():
+    """BASELINE.json configs[1]: env e uses default_rng(1000+e).uniform(0,1,(53,4))."""
+    d, z = load("SIRV_B")
+    n = z["batch_X"].shape[0]
+    acts = np.stack([np.random.default_rng(1000 + e).uniform(0, 1, (53, d.A)).astype(np.float32) for e in range(n)])
+    total, fin = rollout(d, acts)
+    assert x_err(fin, z["batch_X"][:, -1], d) <= 1e-11
+    assert abs(total - z["batch_rewards"].sum()) <= 1e-11 * abs(total)
