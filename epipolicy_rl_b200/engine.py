@@ -68,6 +68,15 @@ class BatchedEpidemic:
         except Exception:  # noqa: BLE001
             pass
 
+    def bind_outputs(self, obs: torch.Tensor, reward: torch.Tensor, done: torch.Tensor) -> None:
+        """Let the kernel epilogue write obs / reward / done into caller-owned device buffers (e.g. the
+        send buffer of the learner all-gather, dist.py)."""
+        assert obs.shape == (self.n_envs, self.obs_dim) and obs.dtype == self.dtype and obs.is_contiguous()
+        assert reward.shape == (self.n_envs,) and reward.dtype == torch.float64
+        assert done.shape == (self.n_envs,) and done.dtype == torch.uint8
+        obs.copy_(self.obs); reward.copy_(self.reward); done.copy_(self.done)
+        self.obs, self.reward, self.done = obs, reward, done
+
     # ---------------------------------------------------------------------------------
     def reset(self, mask: torch.Tensor | None = None) -> torch.Tensor:
         """Epidemic.reset (epidemic.py:104-106) for all envs, or those where mask != 0."""
