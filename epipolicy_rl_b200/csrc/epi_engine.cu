@@ -8,13 +8,18 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
+
+#include <dlfcn.h>
 
 #include <map>
+#include <sstream>
 #include <string>
 #include <vector>
 
 #include "../../include/epi_b200.h"
 #include "epi_kernels.cuh"
+#include "epi_cell.cuh"
 
 namespace {
 
@@ -35,14 +40,26 @@ std::vector<T> vec(const T* p, size_t n) { return std::vector<T>(p, p + n); }
 
 }  // namespace
 
+// host copies of the plan tables the scenario-specialised code generator (gen_spec) walks
+struct HostTabs {
+  std::vector<double> alive_coef, ig_w;
+  std::vector<int> ig_c0, ig_w_off, ig_w_c2, ep_off, ep, xg_off, xg_src, ag_off, ag_src;
+  std::vector<float> ep_coef, xg_coef, ag_coef;
+};
+
 struct epi_engine {
   int device = 0, precision = 0, N = 0;
+  HostTabs tabs;
+  // scenario-specialised build of the cell kernel (epi_spec_attach)
+  void* spec_lib = nullptr;
+  int (*spec_launch)(const DevPlan*, const DevState*, const epi::StepArgs*, int, int, size_t, void*) = nullptr;
   EpiDesc d{};                      // scalars only are valid after create
   DevPlan plan{};
   DevState S{}, init{};
   std::vector<void*> allocs;
   char *big_scratch = nullptr, *small_scratch = nullptr;
-  int cta_mode = 0, threads = 128, wpb = 4, grid = 1;
+  int cta_mode = 0, threads = 128, wpb = 4, grid = 1;  // cta_mode: 0 warp team, 1 CTA team, 2 cell kernel
+  int cellW = 32;                   // lanes per warp of the cell kernel (32 on the device; the host emulation shrinks it)
   size_t smem_bytes = 0, scratch_bytes = 0;
   int64_t launches = 0;
   // host-buffer path
@@ -56,10 +73,19 @@ struct epi_engine {
   std::vector<int> acc_flat_host;   // [n_acc]
   size_t real_size() const { return precision == EPI_FP64 ? 8 : 4; }
 
+  bool host_only = false;           // plan compiled without a device (epi_spec_source_desc): tables stay on the host
+  std::vector<void*> host_allocs;
   template <class T>
   T* up(const std::vector<T>& v) {
     T* p = nullptr;
     size_t n = v.size() ? v.size() : 1;
+    if (host_only) {
+      p = (T*)calloc(n, sizeof(T));
+      if (!p) throw std::bad_alloc();
+      host_allocs.push_back(p);
+      if (v.size()) memcpy(p, v.data(), v.size() * sizeof(T));
+      return p;
+    }
     CK(cudaMalloc(&p, n * sizeof(T)));
     allocs.push_back(p);
     if (v.size()) CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
@@ -385,6 +411,20 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
     ig_w_off.push_back((int)ig_w.size());
   }
 
+  // distinct parameters the infectious groups read (the cell kernel keeps their per-env (y, gap) tables)
+  std::vector<int> igp, ig_p0i, ig_npi, ig_dpi;
+  {
+    auto idx_of = [&](int p) {
+      for (size_t i = 0; i < igp.size(); i++) if (igp[i] == p) return (int)i;
+      igp.push_back(p);
+      return (int)igp.size() - 1;
+    };
+    for (int p : ig_p0) ig_p0i.push_back(idx_of(p));
+    for (int p : ig_np) ig_npi.push_back(idx_of(p));
+    for (int p : ig_dp) ig_dpi.push_back(idx_of(p));
+  }
+  P.n_igp = (int)igp.size();
+
   // ---- gather lists
   std::vector<std::vector<std::pair<int, float>>> xg(C);
   std::map<int, int> acc_of_flat;  // flat row (in LG units) -> acc id
@@ -417,6 +457,13 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
   std::vector<float> xg_coef, ag_coef;
   for (auto& v : xg) { for (auto& pr : v) { xg_src.push_back(pr.first); xg_coef.push_back(pr.second); } xg_off.push_back((int)xg_src.size()); }
   for (auto& v : ag) { for (auto& pr : v) { ag_src.push_back(pr.first); ag_coef.push_back(pr.second); } ag_off.push_back((int)ag_src.size()); }
+
+  {
+    HostTabs& T = h->tabs;
+    T.alive_coef = vec(d.alive_coef, C); T.ig_w = ig_w; T.ig_c0 = ig_c0; T.ig_w_off = ig_w_off; T.ig_w_c2 = ig_w_c2;
+    T.ep_off = ep_off; T.ep = ep; T.ep_coef = vec(d.sum_coef, d.NS);
+    T.xg_off = xg_off; T.xg_src = xg_src; T.xg_coef = xg_coef; T.ag_off = ag_off; T.ag_src = ag_src; T.ag_coef = ag_coef;
+  }
 
   // ---- workspace layout
   const int64_t rs = (int64_t)h->real_size();
@@ -466,8 +513,137 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
   P.ep_off = h->up(ep_off); P.ep = h->up(ep); P.ep_coef = h->up(vec(d.sum_coef, d.NS));
   P.ig_c0 = h->up(ig_c0); P.ig_p0 = h->up(ig_p0); P.ig_np_off = h->up(ig_np_off); P.ig_np = h->up(ig_np);
   P.ig_dp_off = h->up(ig_dp_off); P.ig_dp = h->up(ig_dp); P.ig_w_off = h->up(ig_w_off); P.ig_w_c2 = h->up(ig_w_c2); P.ig_w = h->up(ig_w);
+  P.igp = h->up(igp); P.ig_p0i = h->up(ig_p0i); P.ig_npi = h->up(ig_npi); P.ig_dpi = h->up(ig_dpi);
   P.xg_off = h->up(xg_off); P.xg_src = h->up(xg_src); P.xg_coef = h->up(xg_coef);
   P.ag_off = h->up(ag_off); P.ag_src = h->up(ag_src); P.ag_coef = h->up(ag_coef); P.acc_flat = h->up(acc_flat);
+}
+
+// shared-memory layout of the cell kernel for warps of W lanes (epi_cell.cuh)
+void build_cell_layout(epi_engine* h, int W) {
+  DevPlan& P = h->plan;
+  CellLayout& Y = P.cl;
+  const int64_t rs = (int64_t)h->real_size();
+  const int64_t C = P.C, G = P.G, F = P.F, n_lc = P.n_lc, NG = P.NG, nC = (int64_t)P.I * P.L;
+  Y = CellLayout{};
+  Y.epw = W / P.LG;
+  int64_t o = 0;
+  auto take = [&](int64_t bytes) { int64_t r = o; o = align16(o + bytes); return r; };
+  const int64_t nS = P.has_src64 ? P.n_slot : 0;
+  Y.l_X = take(8 * C * W); Y.l_ys = take(rs * C * W); Y.l_K = take(rs * 7 * C * W);
+  Y.l_fl = take(rs * P.NSRC * W); Y.l_FB = take(rs * P.NSRC * W); Y.l_FE = take(rs * P.NSRC * W);
+  Y.l_cmA = take(rs * (1 + NG) * W); Y.l_cmB = take(rs * (1 + NG) * W);
+  Y.l_mvY = take(4 * (int64_t)P.n_slot * W); Y.l_mvD = take(4 * (int64_t)P.n_slot * W);
+  Y.l_ysS = take(8 * nS * W); Y.l_KS = take(8 * 7 * nS * W); Y.l_red = take(8 * W);
+  Y.e_base = o;
+  o = 0;
+  Y.e_mult_y = take(4 * (int64_t)P.n_cls); Y.e_mult_d = take(4 * (int64_t)P.n_cls);
+  Y.e_cpv = take(4 * (int64_t)P.NCP); Y.e_act = take(P.I);
+  Y.e_expr = take(8 * (int64_t)P.n_expr); Y.e_sel = take(8 * (int64_t)P.n_sel);
+  Y.e_mpy = take(4 * n_lc * P.P * G); Y.e_mpg = take(4 * n_lc * P.P * G); Y.e_mpt0 = take(4 * n_lc * P.P * G);
+  Y.e_mpFy = take(4 * (int64_t)P.n_igp * n_lc * F * G); Y.e_mpFg = take(4 * (int64_t)P.n_igp * n_lc * F * G);
+  Y.e_coefS = take(rs * NG * n_lc * F * G); Y.e_Tnum = take(4 * n_lc * F * G * G);
+  Y.e_Tden = take(P.has_ft_ops ? rs * n_lc * F * G * G : 0);
+  Y.e_fi_y = take(4 * n_lc * F * G * G); Y.e_fi_gap = take(4 * n_lc * F * G * G);
+  Y.e_ft_y = take(4 * n_lc * F * G); Y.e_ft_gap = take(4 * n_lc * F * G);
+  Y.e_cost = take(8 * nC); Y.e_crY = take(8 * nC); Y.e_crD = take(8 * nC);
+  Y.e_bytes = o;
+  Y.warp_bytes = Y.e_base + Y.e_bytes * Y.epw;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// scenario-specialised code generator: the per-cell program of the cell kernel as straight-line CUDA
+// (same operations in the same order as the interpreted path of epi_cell.cuh)
+// ------------------------------------------------------------------------------------------
+std::string hexf(float v) { char b[64]; snprintf(b, sizeof b, "(real)%af", (double)v); return b; }
+std::string hexd(double v) { char b[64]; snprintf(b, sizeof b, "(real)%a", v); return b; }
+
+std::string gen_spec(const epi_engine* h) {
+  const DevPlan& P = h->plan;
+  const HostTabs& T = h->tabs;
+  std::ostringstream o;
+  o << "namespace epi { namespace spec {\n";
+  o << "typedef " << (h->precision == EPI_FP64 ? "double" : "float") << " real;\n";
+  o << "constexpr int C = " << P.C << ", L = " << P.L << ", G = " << P.G << ", F = " << P.F << ", P = " << P.P << ", I = " << P.I
+    << ", LG = " << P.LG << ", CLG = " << P.CLG << ", nnz = " << P.nnz << ", n_lc = " << P.n_lc << ", E = " << P.E
+    << ", NG = " << P.NG << ", NSRC = " << P.NSRC << ", n_acc = " << P.n_acc << ", n_slot = " << P.n_slot
+    << ", has_ft_ops = " << P.has_ft_ops << ", has_src64 = " << P.has_src64 << ";\n";
+  auto arr = [&](const char* name, const std::vector<int>& v) {
+    o << "__device__ constexpr int " << name << "[" << (v.empty() ? 1 : v.size()) << "] = {";
+    if (v.empty()) o << "0";
+    for (size_t i = 0; i < v.size(); i++) o << (i ? ", " : "") << v[i];
+    o << "};\n";
+  };
+  std::vector<int> s1(P.slot_c1, P.slot_c1 + P.n_slot), s2(P.slot_c2, P.slot_c2 + P.n_slot);
+  arr("slot_c1", s1); arr("slot_c2", s2); arr("ig_c0", T.ig_c0);
+  // phase A
+  o << "__device__ __forceinline__ void phaseA(const real* y, real& alive, real* xw) {\n  alive = 0;\n";
+  for (int c = 0; c < P.C; c++)
+    if (T.alive_coef[c] != 0.0) o << "  alive += y[" << c << "] * " << hexd(T.alive_coef[c]) << ";\n";
+  for (int k = 0; k < P.NG; k++) {
+    o << "  xw[" << k << "] = 0;\n";
+    for (int q = T.ig_w_off[k]; q < T.ig_w_off[k + 1]; q++)
+      o << "  xw[" << k << "] += " << hexd(T.ig_w[q]) << " * y[" << T.ig_w_c2[q] << "];\n";
+  }
+  o << "}\n";
+  // regular edges
+  o << "__device__ __forceinline__ void flows(const real* y, real alive, const float* mp, real* f) {\n";
+  auto val = [&](int fac) {
+    int kind = fac >> 24, idx = fac & 0xffffff;
+    std::ostringstream v;
+    if (kind == 0) v << "(real)mp[" << idx * P.G << "]";
+    else if (kind == 1) v << "alive";
+    else v << "y[" << idx << "]";
+    return v.str();
+  };
+  for (int e = 0; e < P.E; e++) {
+    const int* ep = T.ep.data() + T.ep_off[e];
+    int n = *ep++;
+    o << "  { real n = (real)1";
+    for (int q = 0; q < n; q++) o << " * " << val(*ep++);
+    o << ";";
+    int ns = *ep++;
+    if (ns == 0) {
+      o << " f[" << e << "] = n; }\n";
+    } else {
+      o << " real dn = 0;";
+      for (int sidx = 0; sidx < ns; sidx++) {
+        o << " dn += " << hexf(T.ep_coef[*ep++]);
+        int nf = *ep++;
+        for (int q = 0; q < nf; q++) o << " * " << val(*ep++);
+        o << ";";
+      }
+      o << " f[" << e << "] = dn > 0 ? n / dn : n; }\n";
+    }
+  }
+  o << "}\n";
+  // scatter into dX
+  o << "__device__ __forceinline__ void dx(const real* f, real* d) {\n";
+  for (int c = 0; c < P.C; c++) {
+    o << "  d[" << c << "] = 0;";
+    for (int q = T.xg_off[c]; q < T.xg_off[c + 1]; q++) o << " d[" << c << "] += f[" << T.xg_src[q] << "] * " << hexf(T.xg_coef[q]) << ";";
+    o << "\n";
+  }
+  o << "}\n";
+  // accumulator derivatives of a flow column (col already offset by the lane; stride 32)
+  o << "__device__ __forceinline__ void acc(const real* col, real* out) {\n";
+  for (int a = 0; a < P.n_acc; a++) {
+    o << "  out[" << a << "] = 0;";
+    for (int q = T.ag_off[a]; q < T.ag_off[a + 1]; q++) o << " out[" << a << "] += col[" << T.ag_src[q] * 32 << "] * " << hexf(T.ag_coef[q]) << ";";
+    o << "\n";
+  }
+  o << "}\n}}\n";
+  std::string body = o.str();
+  // key: FNV-1a of the body + the ABI of the structs passed by value
+  uint64_t k = 1469598103934665603ull;
+  auto mix = [&](const void* p, size_t n) { for (size_t i = 0; i < n; i++) { k ^= ((const unsigned char*)p)[i]; k *= 1099511628211ull; } };
+  mix(body.data(), body.size());
+  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 3 /* kernel source revision */};
+  mix(abi, sizeof abi);
+  char kb[32];
+  snprintf(kb, sizeof kb, "%016llx", (unsigned long long)k);
+  return std::string("// GENERATED by libepi_b200 (epi_engine.cu: gen_spec) - scenario-specialised per-cell program\n#define EPI_SPEC 1\n#define EPI_SPEC_KEY \"") +
+         kb + "\"\n" + body;
 }
 
 void alloc_state(epi_engine* h, DevState& S, int N) {
@@ -491,6 +667,28 @@ void choose_launch(epi_engine* h) {
   const int64_t smem_max = (int64_t)prop.sharedMemPerBlockOptin - 1024;  // leave room for static smem
   const int sms = prop.multiProcessorCount;
   int64_t per_env = P.small_bytes + P.big_bytes;
+  const char* force = getenv("EPI_TEAM");  // debugging aid: "warp" / "cta" force the team kernels
+  P.cl.enabled = 0;
+  if (P.LG <= 32 && !(force && (!strcmp(force, "warp") || !strcmp(force, "cta")))) {
+#ifdef EPI_HOST_EMU
+    int W = P.LG * (h->N < 32 / P.LG ? h->N : 32 / P.LG);  // as many lanes as the test's envs need
+#else
+    int W = 32;
+#endif
+    build_cell_layout(h, W);
+    if (P.cl.warp_bytes <= smem_max) {
+      // CELL kernel: one lane per (env, locale, group), EPW envs per warp, one warp per CTA
+      P.cl.enabled = 1;
+      h->cta_mode = 2; h->cellW = W;
+      P.small_in_smem = P.big_in_smem = 1;
+      h->wpb = 1; h->threads = W;
+      h->smem_bytes = (size_t)P.cl.warp_bytes;
+      h->grid = (h->N + P.cl.epw - 1) / P.cl.epw;
+      h->scratch_bytes = 0;
+      return;
+    }
+  }
+  if (force && !strcmp(force, "cta")) per_env = INT64_MAX / 16;
   if (per_env * 8 <= (int64_t)prop.sharedMemPerMultiprocessor - 8 * 1024 || per_env <= 28 * 1024) {
     // WARP teams: the whole working set of an env in shared memory
     h->cta_mode = 0;
@@ -540,10 +738,37 @@ void launch_t(epi_engine* h, const DevState& S, const epi::StepArgs& a, int grid
   h->launches++;
 }
 
+template <class real>
+void launch_cell(epi_engine* h, const DevState& S, const epi::StepArgs& a, cudaStream_t st) {
+  const int epw = h->plan.cl.epw;
+  const int grid = (a.N + epw - 1) / epw;
+#ifdef EPI_HOST_EMU
+  (void)st;
+  emu::run_warps(grid, h->cellW, (size_t)h->plan.cl.warp_bytes, [&](char* smem, int lane, int group) {
+    epi::cell::step_warp<real>(h->plan, S, a, smem, lane, group);
+  });
+#else
+  if (h->spec_launch) {
+    int rc = h->spec_launch(&h->plan, &S, &a, grid, h->threads, h->smem_bytes, (void*)st);
+    if (rc != 0) throw CudaFail{std::string("specialised cell kernel launch: ") + cudaGetErrorString((cudaError_t)rc)};
+  } else {
+    auto kern = epi::cell::cell_kernel<real>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    kern<<<grid, h->threads, h->smem_bytes, st>>>(h->plan, S, a);
+    CK(cudaGetLastError());
+  }
+#endif
+  h->launches++;
+}
+
 void launch(epi_engine* h, const DevState& S, epi::StepArgs a, cudaStream_t st) {
+  a.dbg_attempts = (a.N == h->N) ? h->dbg_attempts : nullptr;
+  if (h->cta_mode == 2) {
+    if (h->precision == EPI_FP64) launch_cell<double>(h, S, a, st); else launch_cell<float>(h, S, a, st);
+    return;
+  }
   a.big_scratch = h->big_scratch;
   a.small_scratch = h->small_scratch;
-  a.dbg_attempts = (a.N == h->N) ? h->dbg_attempts : nullptr;
   int grid = h->grid;
   if (a.N < h->N) grid = 1;
   if (h->precision == EPI_FP64) {
@@ -657,6 +882,7 @@ void epi_destroy(epi_t* h) {
   if (h->h_rew) cudaFreeHost(h->h_rew);
   if (h->h_done) cudaFreeHost(h->h_done);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->spec_lib) dlclose(h->spec_lib);
   delete h;
 }
 
@@ -669,7 +895,8 @@ int epi_info(const epi_t* h, EpiInfo* o) {
   o->n_envs = h->N; o->precision = h->precision; o->device = h->device; o->obs_dim = P.CLG; o->action_dim = P.A;
   o->ncp = P.NCP; o->n_itv = P.I; o->horizon = P.horizon; o->n_flat = P.n_flat; o->n_acc = P.n_acc; o->n_slot = P.n_slot;
   o->n_lc = P.n_lc; o->n_groups_inf = P.NG; o->n_cls = P.n_cls; o->team_kind = h->cta_mode; o->threads = h->threads;
-  o->grid = h->grid; o->envs_per_cta = h->cta_mode ? 1 : h->wpb; o->smem_bytes = (int64_t)h->smem_bytes;
+  o->grid = h->grid; o->envs_per_cta = h->cta_mode == 2 ? h->plan.cl.epw : (h->cta_mode ? 1 : h->wpb); o->smem_bytes = (int64_t)h->smem_bytes;
+  o->specialized = h->spec_launch ? 1 : 0; o->reserved = 0;
   o->small_bytes = P.small_bytes; o->big_bytes = P.big_bytes; o->scratch_bytes = (int64_t)h->scratch_bytes;
   int64_t rs = (int64_t)h->real_size();
   o->state_bytes_per_env = 8 * (P.CLG + (int64_t)P.n_chg * P.LG) + rs * (int64_t)P.n_acc * P.LG + 16 * (int64_t)P.I * P.L +
@@ -726,6 +953,8 @@ int epi_step_host(epi_t* h, const float* actions_host, int n_days, void* obs_out
       CK(cudaMallocHost(&h->h_obs, N * CLG * rs)); h->d_obs = h->dalloc<char>(N * CLG * rs);
       CK(cudaMallocHost(&h->h_rew, N * 8)); h->d_rew = h->dalloc<double>(N);
       CK(cudaMallocHost(&h->h_done, N)); h->d_done = h->dalloc<uint8_t>(N);
+      // dalloc's cudaMemset runs on the legacy default stream, which h->stream (non-blocking) does not wait for
+      CK(cudaDeviceSynchronize());
     }
     if (h->plan.A > 0) {
       memcpy(h->h_act, actions_host, N * h->plan.A * 4);
@@ -831,5 +1060,64 @@ int epi_set_state(epi_t* h, int what, const void* in, size_t bytes) {
 }
 
 int64_t epi_launch_count(const epi_t* h) { return h ? h->launches : 0; }
+
+int epi_spec_source(epi_t* h, char* buf, size_t cap, size_t* need) {
+  if (!h) return EPI_E_INVALID;
+  return guarded(h, [&] {
+    if (h->cta_mode != 2) throw Unsupported{"scenario specialisation exists for the cell kernel only (L*G <= 32)"};
+    std::string src = gen_spec(h);
+    if (need) *need = src.size() + 1;
+    if (buf && cap) {
+      size_t n = src.size() < cap - 1 ? src.size() : cap - 1;
+      memcpy(buf, src.data(), n);
+      buf[n] = 0;
+    }
+  });
+}
+
+int epi_spec_source_desc(const EpiDesc* desc, int precision, char* buf, size_t cap, size_t* need) {
+  if (!desc || (precision != EPI_FP64 && precision != EPI_FP32)) return EPI_E_INVALID;
+  epi_engine* h = new epi_engine();
+  h->precision = precision; h->N = 1; h->host_only = true;
+  int rc = guarded(nullptr, [&] {
+    h->d = *desc;
+    build_plan(h, *desc);
+    if (h->plan.LG > 32) throw Unsupported{"scenario specialisation exists for the cell kernel only (L*G <= 32)"};
+    std::string src = gen_spec(h);
+    if (need) *need = src.size() + 1;
+    if (buf && cap) {
+      size_t n = src.size() < cap - 1 ? src.size() : cap - 1;
+      memcpy(buf, src.data(), n);
+      buf[n] = 0;
+    }
+  });
+  for (void* p : h->host_allocs) free(p);
+  delete h;
+  return rc;
+}
+
+int epi_spec_attach(epi_t* h, const char* so_path) {
+  if (!h || !so_path) return EPI_E_INVALID;
+  return guarded(h, [&] {
+    if (h->cta_mode != 2) throw Unsupported{"scenario specialisation exists for the cell kernel only (L*G <= 32)"};
+#ifdef EPI_HOST_EMU
+    throw Unsupported{"no specialised kernels in the host emulation"};
+#else
+    void* lib = dlopen(so_path, RTLD_NOW | RTLD_LOCAL);
+    if (!lib) throw Invalid{std::string("dlopen failed: ") + dlerror()};
+    auto keyf = (const char* (*)())dlsym(lib, "epi_spec_key");
+    auto lf = (int (*)(const DevPlan*, const DevState*, const epi::StepArgs*, int, int, size_t, void*))dlsym(lib, "epi_spec_launch");
+    std::string src = gen_spec(h);
+    size_t p0 = src.find("EPI_SPEC_KEY \"") + 14;
+    std::string want = src.substr(p0, 16);
+    if (!keyf || !lf || want != keyf()) {
+      dlclose(lib);
+      throw Invalid{"specialised library does not match this scenario / build (key mismatch)"};
+    }
+    h->spec_lib = lib;
+    h->spec_launch = lf;
+#endif
+  });
+}
 
 }  // extern "C"

@@ -18,6 +18,18 @@
 #define EPI_MAX_SLOTS 8
 #define EPI_MAX_SEL 32
 
+// shared-memory layout of the cell kernel (epi_cell.cuh): byte offsets inside one warp's block.
+// Per-lane columns hold element i of lane ln at off + (i * W + ln) * sizeof(T); the per-env (slot)
+// tables start at e_base + slot * e_bytes.
+struct CellLayout {
+  int enabled, epw;  // envs per warp = W / (L*G)
+  int64_t l_X, l_ys, l_K, l_fl, l_FB, l_FE, l_cmA, l_cmB, l_mvY, l_mvD, l_ysS, l_KS, l_red;
+  int64_t e_base, e_bytes;
+  int64_t e_mult_y, e_mult_d, e_cpv, e_act, e_expr, e_sel, e_mpy, e_mpg, e_mpt0, e_mpFy, e_mpFg, e_coefS, e_Tnum,
+      e_Tden, e_fi_y, e_fi_gap, e_ft_y, e_ft_gap, e_cost, e_crY, e_crD;
+  int64_t warp_bytes;
+};
+
 struct DevPlan {
   // ---- dimensions
   int C, L, G, F, P, I, A, NCP, LG, CLG, nnz, n_lc;
@@ -85,6 +97,8 @@ struct DevPlan {
   // ---- infectious groups
   const int *ig_c0, *ig_p0, *ig_np_off, *ig_np, *ig_dp_off, *ig_dp, *ig_w_off, *ig_w_c2;
   const double* ig_w;
+  int n_igp;                            // distinct parameters used by infectious groups
+  const int *igp, *ig_p0i, *ig_npi, *ig_dpi; // [n_igp] parameter ids; ig_p0 / ig_np / ig_dp as indices into igp
   // ---- gather lists
   const int *xg_off, *xg_src; const float* xg_coef;    // [C+1]
   const int *ag_off, *ag_src; const float* ag_coef;    // [n_acc+1]
@@ -96,6 +110,7 @@ struct DevPlan {
       o_ft_y, o_ft_gap;                                  // small region (bytes)
   int64_t o_X, o_ys, o_K, o_accY, o_accB, o_accE, o_accF, o_accF2, o_flows, o_alive, o_Xw, o_Ag, o_Wg, o_s, o_r,
       o_mvY, o_mvD, o_cost, o_crY, o_crD, o_ysS, o_KS;   // big region (bytes)
+  CellLayout cl;
   int has_src64;  // fp32 mode with move slots: the slots' source compartments are carried in double
 };
 

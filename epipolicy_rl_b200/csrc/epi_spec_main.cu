@@ -1,0 +1,17 @@
+// epi_spec_main.cu — translation unit of a scenario-specialised build of the cell kernel.
+// Compiled by epipolicy_rl_b200/spec.py:  nvcc ... -DEPI_SPEC_HEADER='"<generated header>"' -shared
+// The generated header (epi_spec_source, include/epi_b200.h) defines EPI_SPEC, EPI_SPEC_KEY and the
+// scenario's per-cell program in namespace epi::spec; epi_cell.cuh then compiles its specialised path.
+#include EPI_SPEC_HEADER
+#include "epi_cell.cuh"
+
+extern "C" const char* epi_spec_key() { return EPI_SPEC_KEY; }
+
+extern "C" int epi_spec_launch(const DevPlan* P, const DevState* S, const epi::StepArgs* a, int grid, int threads,
+                               size_t smem, void* stream) {
+  auto kern = epi::cell::cell_kernel<epi::spec::real>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  kern<<<grid, threads, smem, (cudaStream_t)stream>>>(*P, *S, *a);
+  return (int)cudaGetLastError();
+}

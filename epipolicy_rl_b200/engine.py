@@ -43,6 +43,13 @@ class BatchedEpidemic:
         self.info = _lib.EpiInfo()
         self._ck(self.L.epi_info(self._h, ctypes.byref(self.info)))
         self.obs_dim, self.action_dim = self.info.obs_dim, self.info.action_dim
+        if self.info.team_kind == 2:
+            # scenario-specialised build of the cell kernel (spec.py); the interpreted kernel runs if absent
+            from . import spec as _spec
+            path = _spec.ensure(desc, self.precision)
+            if path is not None:
+                self._ck(self.L.epi_spec_attach(self._h, path.encode()))
+                self._ck(self.L.epi_info(self._h, ctypes.byref(self.info)))
         with torch.cuda.device(dev):
             self.obs = torch.empty((self.n_envs, self.obs_dim), dtype=self.dtype, device=dev)
             self.reward = torch.zeros(self.n_envs, dtype=torch.float64, device=dev)

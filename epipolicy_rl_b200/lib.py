@@ -12,13 +12,15 @@ LIB_PATH = os.path.join(_HERE, "libepi_b200.so")
 
 EPI_FP64, EPI_FP32 = 0, 1
 EXPORTS = ["epi_create", "epi_destroy", "epi_last_error", "epi_info", "epi_reset", "epi_step", "epi_step_plan",
-           "epi_step_host", "epi_get_state", "epi_set_state", "epi_launch_count"]
+           "epi_step_host", "epi_get_state", "epi_set_state", "epi_launch_count", "epi_spec_source", "epi_spec_source_desc",
+           "epi_spec_attach"]
 
 
 class EpiInfo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "n_envs", "precision", "device", "obs_dim", "action_dim", "ncp", "n_itv", "horizon", "n_flat", "n_acc",
-        "n_slot", "n_lc", "n_groups_inf", "n_cls", "team_kind", "threads", "grid", "envs_per_cta")] + [
+        "n_slot", "n_lc", "n_groups_inf", "n_cls", "team_kind", "threads", "grid", "envs_per_cta", "specialized",
+        "reserved")] + [
         (n, ctypes.c_int64) for n in ("smem_bytes", "small_bytes", "big_bytes", "scratch_bytes", "state_bytes_per_env")]
 
 
@@ -68,4 +70,10 @@ def bind(L):
     L.epi_set_state.argtypes = [P, I, P, SZ]
     L.epi_launch_count.restype = ctypes.c_int64
     L.epi_launch_count.argtypes = [P]
+    L.epi_spec_source.restype = I
+    L.epi_spec_source.argtypes = [P, P, SZ, ctypes.POINTER(SZ)]
+    L.epi_spec_source_desc.restype = I
+    L.epi_spec_source_desc.argtypes = [ctypes.POINTER(CEpiDesc), I, P, SZ, ctypes.POINTER(SZ)]
+    L.epi_spec_attach.restype = I
+    L.epi_spec_attach.argtypes = [P, ctypes.c_char_p]
     return L

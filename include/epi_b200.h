@@ -36,8 +36,10 @@ typedef struct EpiInfo {
   int32_t horizon;
   int32_t n_flat;      /* length of the reference's flat ODE state */
   int32_t n_acc, n_slot, n_lc, n_groups_inf, n_cls;
-  int32_t team_kind;   /* 0 = warp per env, 1 = CTA per env */
+  int32_t team_kind;   /* 0 = warp per env, 1 = CTA per env, 2 = cell kernel (lane per (env, locale, group)) */
   int32_t threads, grid, envs_per_cta;
+  int32_t specialized; /* 1 once a scenario-specialised build of the cell kernel is attached */
+  int32_t reserved;
   int64_t smem_bytes, small_bytes, big_bytes, scratch_bytes, state_bytes_per_env;
 } EpiInfo;
 
@@ -84,6 +86,17 @@ int epi_step_host(epi_t* h, const float* actions_host, int n_days, void* obs_out
  * Host buffers; sizes are checked. */
 int epi_get_state(epi_t* h, int what, void* out_host, size_t bytes);
 int epi_set_state(epi_t* h, int what, const void* in_host, size_t bytes);
+
+/* Scenario specialisation of the cell kernel (the reference JIT-compiles its RHS with numba; this is the
+ * analogue). epi_spec_source writes a generated CUDA header (NUL-terminated, `*need` = bytes required)
+ * holding the scenario's per-cell program as straight-line code; the caller compiles
+ * csrc/epi_spec_main.cu with -DEPI_SPEC_HEADER="that file" into a shared object (spec.py does it with nvcc,
+ * caching by the key inside the header) and hands the path to epi_spec_attach, which checks the key and
+ * routes subsequent launches to it. Without an attached build the interpreted cell kernel runs. */
+int epi_spec_source(epi_t* h, char* buf, size_t cap, size_t* need);
+/* the same text from a descriptor alone: needs no CUDA device (ahead-of-time builds) */
+int epi_spec_source_desc(const EpiDesc* desc, int precision, char* buf, size_t cap, size_t* need);
+int epi_spec_attach(epi_t* h, const char* so_path);
 
 /* number of kernel launches issued by this handle so far (bench bookkeeping) */
 int64_t epi_launch_count(const epi_t* h);

@@ -1,6 +1,8 @@
 // Fake <cuda_runtime.h> for the HOST EMULATION build of epipolicy_rl_b200/csrc (tests only).
 // With -DEPI_HOST_EMU -Itests/emu the product sources compile with plain g++: every "device" function
-// runs on the CPU with a one-thread team, device memory is malloc. This lets the CPU test suite cover
+// runs on the CPU, device memory is malloc. The team kernels run with a one-thread team; the cell kernel
+// (epi_cell.cuh) runs each warp as `warp_width` host threads with a pthread barrier as __syncwarp, so the
+// lane-level code (shared-memory staging, votes, reductions) is executed exactly as written. This lets the CPU test suite cover
 // the EpiDesc -> DevPlan compiler, the C-ABI semantics and the kernel arithmetic without a GPU, and
 // compare them with the oracle. It is NOT a product path: nothing in epipolicy_rl_b200/ loads it.
 #pragma once
@@ -8,6 +10,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
+#include <functional>
+#include <vector>
 
 #define __device__
 #define __global__
@@ -33,9 +38,53 @@ inline double __dsub_rn(double a, double b) { return a - b; }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline long long __double_as_longlong(double d) { long long r; memcpy(&r, &d, 8); return r; }
 inline double __longlong_as_double(long long l) { double r; memcpy(&r, &l, 8); return r; }
+namespace emu {
+static int warp_width = 1;                                // lanes per emulated warp (set per launch)
+static thread_local pthread_barrier_t* warp_barrier = nullptr;
+static thread_local int lane_id = 0;
+static thread_local int* vote_buf = nullptr;
+}  // namespace emu
 inline void __syncthreads() {}
-inline void __syncwarp() {}
+inline void __syncwarp() { if (emu::warp_barrier) pthread_barrier_wait(emu::warp_barrier); }
 template <class T> inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
+inline int __any_sync(unsigned, int pred) {
+  if (!emu::warp_barrier) return pred;
+  emu::vote_buf[emu::lane_id] = pred;
+  pthread_barrier_wait(emu::warp_barrier);
+  int r = 0;
+  for (int i = 0; i < emu::warp_width; i++) r |= emu::vote_buf[i];
+  pthread_barrier_wait(emu::warp_barrier);
+  return r;
+}
+namespace emu {
+// run `n_warps` warps one after the other, each as `width` lock-stepped host threads
+inline void run_warps(int n_warps, int width, size_t smem_bytes, const std::function<void(char*, int, int)>& body) {
+  warp_width = width;
+  std::vector<char> smem(smem_bytes + 64);
+  std::vector<int> votes(width);
+  for (int w = 0; w < n_warps; w++) {
+    memset(smem.data(), 0, smem.size());
+    pthread_barrier_t bar;
+    pthread_barrier_init(&bar, nullptr, (unsigned)width);
+    struct Arg { const std::function<void(char*, int, int)>* body; char* smem; int lane, warp; pthread_barrier_t* bar; int* votes; };
+    std::vector<Arg> args(width);
+    std::vector<pthread_t> th(width);
+    char* base = (char*)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
+    for (int l = 0; l < width; l++) {
+      args[l] = Arg{&body, base, l, w, &bar, votes.data()};
+      pthread_create(&th[l], nullptr, [](void* p) -> void* {
+        Arg* a = (Arg*)p;
+        warp_barrier = a->bar; lane_id = a->lane; vote_buf = a->votes;
+        (*a->body)(a->smem, a->lane, a->warp);
+        warp_barrier = nullptr;
+        return nullptr;
+      }, &args[l]);
+    }
+    for (int l = 0; l < width; l++) pthread_join(th[l], nullptr);
+    pthread_barrier_destroy(&bar);
+  }
+}
+}  // namespace emu
 
 typedef int cudaError_t;
 typedef void* cudaStream_t;

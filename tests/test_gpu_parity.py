@@ -204,3 +204,25 @@ def test_single_env_twin_matches_reference_weekly():
         obs, r, done, info = env.step(z["rnd_actions"][w])
         assert x_err(obs, z["rnd_obs_weekly"][w], d) <= 1e-9
         assert abs(r - z["rnd_rewards"][w]) <= 1e-9 * abs(r) and done is False and info == {}
+
+
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+def test_specialised_kernel_equals_interpreted_kernel(prec, monkeypatch):
+    """The scenario-specialised build (spec.py) and the interpreted cell kernel run the same operations in the
+    same order: trajectories agree to rounding, RK45 step counts are identical."""
+    d, _ = load("COVID_C")
+    a = torch.rand((5, 64, d.A), generator=torch.Generator().manual_seed(11))
+    es = _engine(d, 64, prec)
+    monkeypatch.setenv("EPI_SPEC", "0")
+    eg = _engine(d, 64, prec)
+    monkeypatch.delenv("EPI_SPEC")
+    assert es.info.team_kind == 2 and es.info.specialized == 1 and eg.info.specialized == 0
+    for s in range(5):
+        o1, r1, _ = es.step(a[s].cuda(), 7)
+        o2, r2, _ = eg.step(a[s].cuda(), 7)
+        assert np.array_equal(es.get_state("trace"), eg.get_state("trace"))
+    tol = 1e-12 if prec == "fp64" else 1e-5
+    assert x_err(es.get_state("X"), eg.get_state("X"), d) <= tol
+    assert np.allclose(r1.cpu().numpy(), r2.cpu().numpy(), rtol=tol)
+    es.close()
+    eg.close()
