@@ -568,6 +568,18 @@ std::string gen_spec(const epi_engine* h) {
     << ", LG = " << P.LG << ", CLG = " << P.CLG << ", nnz = " << P.nnz << ", n_lc = " << P.n_lc << ", E = " << P.E
     << ", NG = " << P.NG << ", NSRC = " << P.NSRC << ", n_acc = " << P.n_acc << ", n_slot = " << P.n_slot
     << ", has_ft_ops = " << P.has_ft_ops << ", has_src64 = " << P.has_src64 << ";\n";
+  {
+    const CellLayout& Y = P.cl;  // built for 32-lane warps
+    o << "constexpr int l_X = " << Y.l_X << ", l_ys = " << Y.l_ys << ", l_K = " << Y.l_K << ", l_fl = " << Y.l_fl << ", l_FB = " << Y.l_FB
+      << ", l_FE = " << Y.l_FE << ", l_cmA = " << Y.l_cmA << ", l_cmB = " << Y.l_cmB << ", l_mvY = " << Y.l_mvY << ", l_mvD = " << Y.l_mvD
+      << ", l_ysS = " << Y.l_ysS << ", l_KS = " << Y.l_KS << ", l_red = " << Y.l_red << ";\n";
+    o << "constexpr int e_base = " << Y.e_base << ", e_bytes = " << Y.e_bytes << ", e_mult_y = " << Y.e_mult_y << ", e_mult_d = " << Y.e_mult_d
+      << ", e_cpv = " << Y.e_cpv << ", e_act = " << Y.e_act << ", e_expr = " << Y.e_expr << ", e_sel = " << Y.e_sel << ", e_mpy = " << Y.e_mpy
+      << ", e_mpg = " << Y.e_mpg << ", e_mpt0 = " << Y.e_mpt0 << ", e_mpFy = " << Y.e_mpFy << ", e_mpFg = " << Y.e_mpFg
+      << ", e_coefS = " << Y.e_coefS << ", e_Tnum = " << Y.e_Tnum << ", e_Tden = " << Y.e_Tden << ", e_fi_y = " << Y.e_fi_y
+      << ", e_fi_gap = " << Y.e_fi_gap << ", e_ft_y = " << Y.e_ft_y << ", e_ft_gap = " << Y.e_ft_gap << ", e_cost = " << Y.e_cost
+      << ", e_crY = " << Y.e_crY << ", e_crD = " << Y.e_crD << ", warp_bytes = " << Y.warp_bytes << ";\n";
+  }
   auto arr = [&](const char* name, const std::vector<int>& v) {
     o << "__device__ constexpr int " << name << "[" << (v.empty() ? 1 : v.size()) << "] = {";
     if (v.empty()) o << "0";
@@ -638,7 +650,7 @@ std::string gen_spec(const epi_engine* h) {
   uint64_t k = 1469598103934665603ull;
   auto mix = [&](const void* p, size_t n) { for (size_t i = 0; i < n; i++) { k ^= ((const unsigned char*)p)[i]; k *= 1099511628211ull; } };
   mix(body.data(), body.size());
-  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 3 /* kernel source revision */};
+  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 4 /* generator revision */};
   mix(abi, sizeof abi);
   char kb[32];
   snprintf(kb, sizeof kb, "%016llx", (unsigned long long)k);
@@ -1083,6 +1095,7 @@ int epi_spec_source_desc(const EpiDesc* desc, int precision, char* buf, size_t c
     h->d = *desc;
     build_plan(h, *desc);
     if (h->plan.LG > 32) throw Unsupported{"scenario specialisation exists for the cell kernel only (L*G <= 32)"};
+    build_cell_layout(h, 32);
     std::string src = gen_spec(h);
     if (need) *need = src.size() + 1;
     if (buf && cap) {
