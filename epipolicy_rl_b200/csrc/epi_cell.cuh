@@ -34,11 +34,6 @@
 namespace epi {
 namespace cell {
 
-#ifdef EPI_HOST_EMU
-#define EPI_W (emu::warp_width)
-#else
-#define EPI_W 32
-#endif
 #define EPI_FULL 0xffffffffu
 
 // float copies of the tableau for the fp32 mode (no F2F in the stage algebra)
@@ -63,8 +58,9 @@ __device__ __forceinline__ double rkE(double, int j) { return RK_E[j]; }
 #define T_ys real
 #define T_K real
 #define T_fl real
-#define T_FB real
-#define T_FE real
+#define T_FBE real2
+#define T_accY real
+#define T_tdc real
 #define T_cmA real
 #define T_cmB real
 #define T_mvY float
@@ -98,6 +94,7 @@ __device__ __forceinline__ double rkE(double, int j) { return RK_E[j]; }
 // dimensions and layout are compile-time constants; every access indexes the dynamic shared array itself,
 // so the compiler knows the address space and folds the offsets into the instruction
 #define DIM(x) (spec::x)
+#define EPI_LW (spec::LW)
 #define SLOT_C1(i) (spec::slot_c1[i])
 #define SLOT_C2(i) (spec::slot_c2[i])
 extern __shared__ __align__(16) char cell_smem[];
@@ -105,21 +102,31 @@ extern __shared__ __align__(16) char cell_smem[];
 #define ENVP(arr) ((T_##arr*)(cell_smem + (spec::e_base + spec::e_##arr) + c.ebase))
 #else
 #define DIM(x) (P.x)
+#define EPI_LW (P.cl.lw)
 #define SLOT_C1(i) (P.slot_c1[i])
 #define SLOT_C2(i) (P.slot_c2[i])
 #define COLP(arr) ((T_##arr*)(c.wbase + P.cl.l_##arr))
 #define ENVP(arr) ((T_##arr*)(c.wbase + (P.cl.e_base + P.cl.e_##arr) + c.ebase))
 #endif
 // element i of my lane / of lane ln in a per-lane column; entry i of a table of my env
-#define LA(arr, i) (COLP(arr)[(i) * EPI_W + c.lane])
-#define LO(arr, i, ln) (COLP(arr)[(i) * EPI_W + (ln)])
+// (columns are LW = EPW * L*G lanes wide: the idle lanes of a warp own no shared memory)
+#define LA(arr, i) (COLP(arr)[(i) * EPI_LW + c.lane])
+#define LO(arr, i, ln) (COLP(arr)[(i) * EPI_LW + (ln)])
 #define EV(arr, i) (ENVP(arr)[i])
+#define WT(arr, i) (COLP(arr)[i])  // warp-wide table
+
+template <class T> struct Pair { T x, y; };
+template <> struct __align__(8) Pair<float> { float x, y; };
+template <> struct __align__(16) Pair<double> { double x, y; };
+#define real2 Pair<real>
 
 struct Cx {
   int lane, slot, cell, j, u, lc, l0;  // l0: first lane of my env
   int ebase;                           // byte offset of my env's table block: slot * e_bytes
   bool valid;                          // lane carries a cell of a slot < EPW
   char* wbase;                         // the warp's shared-memory block (generic build)
+  unsigned cover;                      // bit sl: move slot sl covers my cell
+  float mB[4], mD[4];                  // dense mobility column / row of my cell (specialised builds with L <= 4)
 };
 
 __device__ __forceinline__ void bind(const DevPlan& P, char* warp_base, int lane, Cx& c) {
@@ -136,15 +143,24 @@ __device__ __forceinline__ void bind(const DevPlan& P, char* warp_base, int lane
   c.l0 = c.slot * LG;
 #ifdef EPI_SPEC
   c.ebase = c.slot * (int)spec::e_bytes;
+  if (spec::dense_mob) {
+#pragma unroll
+    for (int i = 0; i < (spec::dense_mob ? spec::L : 1); i++) {
+      c.mB[i] = __ldg(P.mob_dense_csc + c.cell * spec::L + i);
+      c.mD[i] = __ldg(P.mob_dense_csr + c.cell * spec::L + i);
+    }
+  }
 #else
   c.ebase = c.slot * (int)P.cl.e_bytes;
 #endif
+  c.cover = 0;
+  for (int sl = 0; sl < DIM(n_slot); sl++) c.cover |= (__ldg(P.slot_cover + sl * LG + c.cell) ? 1u : 0u) << sl;
 }
 
 // sum over the lanes of my env, in lane order; every lane of the env gets the bit-identical result
 #define TEAM_SUM(out, v, on_)                                           \
   {                                                                     \
-    LA(red, 0) = (on_) ? (double)(v) : 0.0;                             \
+    if (c.valid) LA(red, 0) = (on_) ? (double)(v) : 0.0;                \
     __syncwarp();                                                       \
     double s_ = 0;                                                      \
     if (on_)                                                            \
@@ -154,18 +170,26 @@ __device__ __forceinline__ void bind(const DevPlan& P, char* warp_base, int lane
   }
 
 // all accumulator derivatives of a flow column: generated straight-line code under EPI_SPEC
+// column views for the gathers: (pointer to my lane's element 0, stride between elements in `real`s)
+#define COL_fl (&LA(fl, 0)), EPI_LW
+#define COL_FB (&LA(FBE, 0).x), 2 * EPI_LW
+#define COL_FE (&LA(FBE, 0).y), 2 * EPI_LW
 #ifdef EPI_SPEC
-#define ACC_DECL(name, arr) real name[spec::n_acc > 0 ? spec::n_acc : 1]; spec::acc(&LA(arr, 0), name)
-#define ACC_AT(name, arr, a) (name[a])
+#define ACC_DECL(name, ...) real name[spec::n_acc > 0 ? spec::n_acc : 1]; acc_all<real>(__VA_ARGS__, name)
+#define ACC_AT(name, a, ...) (name[a])
+template <class real>
+__device__ __forceinline__ void acc_all(const real* col, int stride, real* out) {
+  if (stride == spec::LW) spec::acc<spec::LW>(col, out); else spec::acc<2 * spec::LW>(col, out);
+}
 #else
-#define ACC_DECL(name, arr)
-#define ACC_AT(name, arr, a) acc_gather<real>(P, c, COLP(arr), a)
+#define ACC_DECL(name, ...)
+#define ACC_AT(name, a, ...) acc_gather<real>(P, __VA_ARGS__, a)
 // d acc_a from a flow column (cumulative_move / gain / lost derivative, obj/edge.py:76-111 inverted)
 template <class real>
-__device__ __forceinline__ real acc_gather(const DevPlan& P, const Cx& c, const real* col, int a) {
+__device__ __forceinline__ real acc_gather(const DevPlan& P, const real* col, int stride, int a) {
   real d = 0;
   for (int q = __ldg(P.ag_off + a); q < __ldg(P.ag_off + a + 1); q++)
-    d += col[__ldg(P.ag_src + q) * EPI_W + c.lane] * (real)__ldg(P.ag_coef + q);
+    d += col[__ldg(P.ag_src + q) * stride] * (real)__ldg(P.ag_coef + q);
   return d;
 }
 #endif
@@ -260,6 +284,20 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Cx& c, bool on, bool
     real a = 0, xs[EPI_MAX_NG];
 #pragma unroll
     for (int k = 0; k < EPI_MAX_NG; k++) xs[k] = 0;
+#ifdef EPI_SPEC
+    if (spec::dense_mob) {
+      // dense over the L source locales in ascending order (zeros where the pattern has no entry: exact)
+#pragma unroll
+      for (int i = 0; i < (spec::dense_mob ? spec::L : 1); i++) {
+        int src = c.l0 + i * G + c.u;
+        real val = (real)c.mB[i];
+        a += LO(cmA, 0, src) * val;
+#pragma unroll
+        for (int k = 0; k < EPI_MAX_NG; k++)
+          if (k < NG) xs[k] += LO(cmA, 1 + k, src) * val;
+      }
+    } else
+#endif
     for (int q = __ldg(P.csc_indptr + c.j); q < __ldg(P.csc_indptr + c.j + 1); q++) {
       int src = c.l0 + __ldg(P.csc_indices + q) * G + c.u;
       real val = (real)__ldg(P.mx_csc + c.u * nnz + q);
@@ -285,10 +323,8 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Cx& c, bool on, bool
       real den = 0;
       if (DIM(has_ft_ops)) {
         for (int u = 0; u < G; u++) den += LO(cmB, 0, row + u) * EV(Tden, tb + u);
-      } else if (sizeof(real) == 8) {
-        for (int u = 0; u < G; u++) den += LO(cmB, 0, row + u) * (real)__ldg(P.Tden_const64 + tb + u);
       } else {
-        for (int u = 0; u < G; u++) den += LO(cmB, 0, row + u) * (real)__ldg(P.Tden_const + tb + u);
+        for (int u = 0; u < G; u++) den += LO(cmB, 0, row + u) * WT(tdc, tb + u);
       }
       if (den <= (real)1e-15) den = 1;
       real inv = (real)1 / den;
@@ -312,6 +348,18 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Cx& c, bool on, bool
 #pragma unroll
     for (int k = 0; k < EPI_MAX_NG; k++) rs[k] = 0;
     if (NG > 0) {
+#ifdef EPI_SPEC
+      if (spec::dense_mob) {
+#pragma unroll
+        for (int i = 0; i < (spec::dense_mob ? spec::L : 1); i++) {
+          int dst = c.l0 + i * G + c.u;
+          real val = (real)c.mD[i];
+#pragma unroll
+          for (int k = 0; k < EPI_MAX_NG; k++)
+            if (k < NG) rs[k] += LO(cmA, 1 + k, dst) * val;
+        }
+      } else
+#endif
       for (int q = __ldg(P.csr_indptr + c.j); q < __ldg(P.csr_indptr + c.j + 1); q++) {
         int dst = c.l0 + __ldg(P.csr_indices + q) * G + c.u;
         real val = (real)__ldg(P.mx_csr + c.u * nnz + q);
@@ -333,7 +381,7 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Cx& c, bool on, bool
     for (int sl = 0; sl < spec::n_slot; sl++) {
       real nv = 0;
       const int c1 = spec::slot_c1[sl], c2 = spec::slot_c2[sl];
-      if (__ldg(P.slot_cover + sl * LG + c.cell) && ((ex_bits >> sl) & 0x10001)) {
+      if (((c.cover >> sl) & 1) && ((ex_bits >> sl) & 0x10001)) {
         float my = ((ex_bits >> sl) & 1) ? LA(mvY, sl) : 0.0f;
         float md = ((ex_bits >> (16 + sl)) & 1) ? LA(mvD, sl) : 0.0f;
         float v = __fadd_rn(__fmul_rn(__fsub_rn(md, my), qf), my);  // coo.py scale/add in f32
@@ -355,14 +403,18 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Cx& c, bool on, bool
     if (acc_mode == 1) {
 #pragma unroll
       for (int i = 0; i < spec::NSRC; i++) {
-        LA(FB, i) += bw * f[i];
-        LA(FE, i) += ew * f[i];
+        real2 p = LA(FBE, i);
+        p.x += bw * f[i];
+        p.y += ew * f[i];
+        LA(FBE, i) = p;
       }
     } else if (acc_mode == 2) {
 #pragma unroll
       for (int i = 0; i < spec::NSRC; i++) {
-        LA(FB, i) = bw * f[i];
-        LA(FE, i) = ew * f[i];
+        real2 p;
+        p.x = bw * f[i];
+        p.y = ew * f[i];
+        LA(FBE, i) = p;
       }
     }
     if (keep_fl) {
@@ -405,7 +457,7 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Cx& c, bool on, bool
     for (int sl = 0; sl < P.n_slot; sl++) {
       real nv = 0;
       const int c1 = P.slot_c1[sl], c2 = P.slot_c2[sl];
-      if (__ldg(P.slot_cover + sl * LG + c.cell) && ((ex_bits >> sl) & 0x10001)) {
+      if (((c.cover >> sl) & 1) && ((ex_bits >> sl) & 0x10001)) {
         float my = ((ex_bits >> sl) & 1) ? LA(mvY, sl) : 0.0f;
         float md = ((ex_bits >> (16 + sl)) & 1) ? LA(mvD, sl) : 0.0f;
         float v = __fadd_rn(__fmul_rn(__fsub_rn(md, my), qf), my);  // coo.py scale/add in f32
@@ -426,14 +478,18 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Cx& c, bool on, bool
     if (acc_mode == 1) {
       for (int i = 0; i < P.NSRC; i++) {
         real f = LA(fl, i);
-        LA(FB, i) += bw * f;
-        LA(FE, i) += ew * f;
+        real2 p = LA(FBE, i);
+        p.x += bw * f;
+        p.y += ew * f;
+        LA(FBE, i) = p;
       }
     } else if (acc_mode == 2) {
       for (int i = 0; i < P.NSRC; i++) {
         real f = LA(fl, i);
-        LA(FB, i) = bw * f;
-        LA(FE, i) = ew * f;
+        real2 p;
+        p.x = bw * f;
+        p.y = ew * f;
+        LA(FBE, i) = p;
       }
     }
 #endif
@@ -446,7 +502,7 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Cx& c, bool on, bool
 // ------------------------------------------------------------------------------------------
 template <class real>
 __device__ __forceinline__ int prologue(const DevPlan& P, const Cx& c, bool on, int variant, double* Xprev_g,
-                                        int ex_y_bits, bool& dyn) {
+                                        int ex_y_bits, bool& dyn, bool& tabs_current) {
   const int LG = DIM(LG), G = DIM(G), L = DIM(L), C = DIM(C), F = DIM(F), PP = DIM(P);
   // 1. select sums (executor.py:346-359, ['Value'].sum())
   for (int s = 0; s < P.n_sel; s++) {
@@ -499,8 +555,11 @@ __device__ __forceinline__ int prologue(const DevPlan& P, const Cx& c, bool on, 
     TEAM_SUM(tot, diff, on);
     dyn = tot > 0;
   }
+  // the (y, gap) parameter tables and the time-t tables depend on the multipliers only: when yesterday's and
+  // today's are equal for the second day in a row they are already right (y = today's value, gap = 0)
+  const bool rebuild = dyn || !tabs_current;
   int ex_d = 0;
-  if (on) {
+  if (on && rebuild) {
     // 4. facility tables of yesterday and today -> (y, gap)   (parameter.py:64-65,:73-74)
     for (int row = c.cell; row < P.n_lc * F * G; row += LG) {
       float a[32], b[32];  // G <= 32 (checked on the host)
@@ -551,6 +610,8 @@ __device__ __forceinline__ int prologue(const DevPlan& P, const Cx& c, bool on, 
       EV(mpFy, i) = y;
       EV(mpFg, i) = __fsub_rn(d, y);
     }
+  }
+  if (on) {
     // 5. move table of today (nb_move, executor.py:166-234; different compartment, same locale)
     for (int sl = 0; sl < DIM(n_slot); sl++) LA(mvD, sl) = 0.0f;
   }
@@ -600,7 +661,8 @@ __device__ __forceinline__ int prologue(const DevPlan& P, const Cx& c, bool on, 
     }
   }
   __syncwarp();
-  if (on && !dyn) fill_tables<real>(P, c, 0.0f);  // constant over the day: filled once (the final barrier of rhs orders it)
+  if (on && !dyn && rebuild) fill_tables<real>(P, c, 0.0f);  // constant over the day: filled once
+  tabs_current = !dyn;
   __syncwarp();
   return (ex_y_bits & 0xffff) | (ex_d << 16);
 }
@@ -618,8 +680,8 @@ __device__ __forceinline__ int prologue(const DevPlan& P, const Cx& c, bool on, 
 // threshold.
 // ------------------------------------------------------------------------------------------
 template <class real>
-__device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on, bool dyn, int ex_bits, real* accY_g,
-                                         int* trace, double* last_err_out, double* dbg) {
+__device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on, bool dyn, int ex_bits, int* trace,
+                                         double* last_err_out, double* dbg) {
   const double rtol = 1e-3, atol = 1e-6;
   const real rtolr = (real)1e-3, atolr = (real)1e-6;
   const int C = DIM(C), LG = DIM(LG), nC = DIM(I) * DIM(L), nS = DIM(has_src64) ? DIM(n_slot) : 0, NSRC = DIM(NSRC),
@@ -699,11 +761,11 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on,
           a0 += a * a; a1 += b * b;
         }
         {
-          ACC_DECL(g0, fl);
+          ACC_DECL(g0, COL_fl);
 #pragma unroll
           for (int a_ = 0; a_ < n_acc; a_++) {
-            real yv = accY_g[a_ * LG], sc = atolr + fabs(yv) * rtolr;
-            real a = yv / sc, b = ACC_AT(g0, fl, a_) / sc;
+            real yv = LA(accY, a_), sc = atolr + fabs(yv) * rtolr;
+            real a = yv / sc, b = ACC_AT(g0, a_, COL_fl) / sc;
             a0 += a * a; a1 += b * b;
           }
         }
@@ -713,7 +775,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on,
           double a = yv / sc, b = EV(crY, i) / sc;  // q(0) = 0
           s0 += a * a; s1 += b * b;
         }
-        for (int i = 0; i < NSRC; i++) LA(FE, i) = LA(fl, i);  // stage-0 flows, needed once more in phase 1
+        for (int i = 0; i < NSRC; i++) LA(FBE, i).y = LA(fl, i);  // stage-0 flows, needed once more in phase 1
       }
       TEAM_SUM(d0, s0, on);
       TEAM_SUM(d1, s1, on);
@@ -733,12 +795,12 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on,
           a2 += a * a;
         }
         {
-          ACC_DECL(g1, fl);
-          ACC_DECL(g0, FE);
+          ACC_DECL(g1, COL_fl);
+          ACC_DECL(g0, COL_FE);
 #pragma unroll
           for (int a_ = 0; a_ < n_acc; a_++) {
-            real sc = atolr + fabs((real)accY_g[a_ * LG]) * rtolr;
-            real a = (ACC_AT(g1, fl, a_) - ACC_AT(g0, FE, a_)) / sc;
+            real sc = atolr + fabs(LA(accY, a_)) * rtolr;
+            real a = (ACC_AT(g1, a_, COL_fl) - ACC_AT(g0, a_, COL_FE)) / sc;
             a2 += a * a;
           }
         }
@@ -749,9 +811,11 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on,
         }
         // stage-0 contributions of the first attempt
         for (int i = 0; i < NSRC; i++) {
-          real f = LA(FE, i);
-          LA(FB, i) = rkB(real(0), 0) * f;
-          LA(FE, i) = rkE(real(0), 0) * f;
+          real f = LA(FBE, i).y;
+          real2 p;
+          p.x = rkB(real(0), 0) * f;
+          p.y = rkE(real(0), 0) * f;
+          LA(FBE, i) = p;
         }
       }
       TEAM_SUM(d2, s2, on);
@@ -778,12 +842,12 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on,
           ae += a * a;
         }
         {
-          ACC_DECL(gB, FB);
-          ACC_DECL(gE, FE);
+          ACC_DECL(gB, COL_FB);
+          ACC_DECL(gE, COL_FE);
 #pragma unroll
           for (int a_ = 0; a_ < n_acc; a_++) {
-            real yv = accY_g[a_ * LG], yn = yv + (real)h * ACC_AT(gB, FB, a_);
-            real sc = atolr + fmax(fabs(yv), fabs(yn)) * rtolr, a = ACC_AT(gE, FE, a_) * (real)h / sc;
+            real yv = LA(accY, a_), yn = yv + (real)h * ACC_AT(gB, a_, COL_FB);
+            real sc = atolr + fmax(fabs(yv), fabs(yn)) * rtolr, a = ACC_AT(gE, a_, COL_FE) * (real)h / sc;
             ae += a * a;
           }
         }
@@ -840,14 +904,16 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on,
           LA(KS, q) = LA(KS, 6 * nS + q);
         }
         {
-          ACC_DECL(gB, FB);
+          ACC_DECL(gB, COL_FB);
 #pragma unroll
-          for (int a_ = 0; a_ < n_acc; a_++) accY_g[a_ * LG] += hr * ACC_AT(gB, FB, a_);
+          for (int a_ = 0; a_ < n_acc; a_++) LA(accY, a_) += hr * ACC_AT(gB, a_, COL_FB);
         }
         for (int i = 0; i < NSRC; i++) {  // the last stage's flows open the next attempt (FSAL)
           real f = LA(fl, i);
-          LA(FB, i) = rkB(real(0), 0) * f;
-          LA(FE, i) = rkE(real(0), 0) * f;
+          real2 p;
+          p.x = rkB(real(0), 0) * f;
+          p.y = rkE(real(0), 0) * f;
+          LA(FBE, i) = p;
         }
         for (int i = c.cell; i < nC; i += LG) {
           double cy = EV(crY, i), cg = EV(crD, i) - cy, sb = 0;
@@ -885,14 +951,19 @@ __device__ __forceinline__ void step_warp(const DevPlan& P, const DevState& S, c
   const bool on0 = c.valid && env < a.N;
   const size_t e = on0 ? (size_t)env : 0;
 
+  // ---- the constant FOI-denominator kernel (no FT_MUL ops) as a warp-wide table
+  if (!DIM(has_ft_ops) && c.lane < EPI_LW)
+    for (int i = c.lane; i < DIM(n_lc) * DIM(F) * DIM(G) * DIM(G); i += EPI_LW)
+      WT(tdc, i) = sizeof(real) == 8 ? (real)__ldg(P.Tden_const64 + i) : (real)__ldg(P.Tden_const + i);
   // ---- load the env's persistent state
   double* gX = S.X + e * CLG;
-  real* gAcc = (real*)S.acc + e * nA + c.cell;  // accumulators stay in HBM/L2: touched once per RK45 attempt
+  real* gAcc = (real*)S.acc + e * nA + c.cell;
   double* gXprev = S.Xprev + e * P.n_chg * LG;
   int* meta = S.meta + e * 8;
   if (on0) {
     for (int k = 0; k < C; k++) LA(X, k) = gX[k * LG + c.cell];
     for (int s = 0; s < DIM(n_slot); s++) LA(mvY, s) = S.mvY[e * nM + s * LG + c.cell];
+    for (int a_ = 0; a_ < DIM(n_acc); a_++) LA(accY, a_) = gAcc[a_ * LG];
     for (int i = c.cell; i < nC; i += LG) {
       EV(cost, i) = S.cost[e * nC + i];
       EV(crY, i) = S.crY[e * nC + i];
@@ -913,17 +984,17 @@ __device__ __forceinline__ void step_warp(const DevPlan& P, const DevState& S, c
   __syncwarp();
 
   double reward = 0;
-  bool on = on0;
+  bool on = on0, tabs_current = false;
   const int n_days = a.init_only ? 1 : a.n_days;
   for (int day = 0; day < n_days; day++) {
     if (!__any_sync(EPI_FULL, on)) break;
     bool dyn = true;
-    int ex_bits = prologue<real>(P, c, on, a.variant, gXprev, ex_y, dyn);
+    int ex_bits = prologue<real>(P, c, on, a.variant, gXprev, ex_y, dyn, tabs_current);
     if (!a.init_only) {
       double c0 = 0, c1 = 0;
       if (on)
         for (int i = c.cell; i < nC; i += LG) c0 += EV(cost, i);
-      rk45_day<real>(P, c, on, dyn, ex_bits, gAcc, meta, S.last_err + e,
+      rk45_day<real>(P, c, on, dyn, ex_bits, meta, S.last_err + e,
                      a.dbg_attempts ? a.dbg_attempts + e * 128 : nullptr);
       if (on)
         for (int i = c.cell; i < nC; i += LG) c1 += EV(cost, i);
@@ -950,6 +1021,7 @@ __device__ __forceinline__ void step_warp(const DevPlan& P, const DevState& S, c
       if (a.obs_out) ((real*)a.obs_out)[e * CLG + k * LG + c.cell] = (real)x;
     }
     for (int s = 0; s < DIM(n_slot); s++) S.mvY[e * nM + s * LG + c.cell] = LA(mvY, s);
+    for (int a_ = 0; a_ < DIM(n_acc); a_++) gAcc[a_ * LG] = LA(accY, a_);
     for (int i = c.cell; i < nC; i += LG) {
       S.cost[e * nC + i] = EV(cost, i);
       S.crY[e * nC + i] = EV(crY, i);

@@ -280,6 +280,24 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
     }
   }
 
+  // dense column / row of every cell for tiny locale counts (specialised cell kernel); only when the pattern's
+  // indices are ascending, so that the dense loop adds the non-zeros in the reference's order
+  std::vector<float> dense_csc, dense_csr;
+  if (L <= 4) {
+    bool asc = true;
+    for (int r = 0; r < L && asc; r++) {
+      for (int k = d.csr_indptr[r] + 1; k < d.csr_indptr[r + 1]; k++) asc = asc && d.csr_indices[k - 1] < d.csr_indices[k];
+      for (int k = d.csc_indptr[r] + 1; k < d.csc_indptr[r + 1]; k++) asc = asc && d.csc_indices[k - 1] < d.csc_indices[k];
+    }
+    if (asc) {
+      dense_csc.assign((size_t)LG * L, 0.0f); dense_csr.assign((size_t)LG * L, 0.0f);
+      for (int j = 0; j < L; j++) for (int g = 0; g < G; g++) {
+        for (int k = d.csc_indptr[j]; k < d.csc_indptr[j + 1]; k++) dense_csc[((size_t)j * G + g) * L + d.csc_indices[k]] = mx_csc[(size_t)g * d.nnz + k];
+        for (int k = d.csr_indptr[j]; k < d.csr_indptr[j + 1]; k++) dense_csr[((size_t)j * G + g) * L + d.csr_indices[k]] = mx_csr[(size_t)g * d.nnz + k];
+      }
+    }
+  }
+
   // ---- selects
   std::vector<uint8_t> sel_c((size_t)d.NSEL * C), sel_l((size_t)d.NSEL * L), sel_g((size_t)d.NSEL * G);
   std::vector<int> sel_mode(d.NSEL), chg_slot(C, -1);
@@ -497,6 +515,8 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
   P.alive_coef = h->up(vec(d.alive_coef, C)); P.X0 = h->up(vec(d.X0, (size_t)C * LG)); P.lclass = h->up(lclass);
   P.mp0 = h->up(mp0); P.ft0 = h->up(ft0); P.fi0 = h->up(fi0); P.mp_cls = h->up(mp_cls); P.ft_cls = h->up(ft_cls); P.fi_cls = h->up(fi_cls);
   P.Tden_const = h->up(tden); P.Tden_const64 = h->up(tden64); P.mx_csr = h->up(mx_csr); P.mx_csc = h->up(mx_csc);
+  P.mob_dense_csc = dense_csc.empty() ? nullptr : h->up(dense_csc);
+  P.mob_dense_csr = dense_csr.empty() ? nullptr : h->up(dense_csr);
   P.csr_indptr = h->up(vec(d.csr_indptr, L + 1)); P.csr_indices = h->up(vec(d.csr_indices, d.nnz));
   P.csc_indptr = h->up(vec(d.csc_indptr, L + 1)); P.csc_indices = h->up(vec(d.csc_indices, d.nnz));
   P.cls_off = h->up(cls_off); P.cls_op = h->up(cls_op);
@@ -526,11 +546,13 @@ void build_cell_layout(epi_engine* h, int W) {
   const int64_t C = P.C, G = P.G, F = P.F, n_lc = P.n_lc, NG = P.NG, nC = (int64_t)P.I * P.L;
   Y = CellLayout{};
   Y.epw = W / P.LG;
+  Y.lw = W = Y.epw * P.LG;
   int64_t o = 0;
   auto take = [&](int64_t bytes) { int64_t r = o; o = align16(o + bytes); return r; };
   const int64_t nS = P.has_src64 ? P.n_slot : 0;
   Y.l_X = take(8 * C * W); Y.l_ys = take(rs * C * W); Y.l_K = take(rs * 7 * C * W);
-  Y.l_fl = take(rs * P.NSRC * W); Y.l_FB = take(rs * P.NSRC * W); Y.l_FE = take(rs * P.NSRC * W);
+  Y.l_fl = take(rs * P.NSRC * W); Y.l_FBE = take(2 * rs * P.NSRC * W); Y.l_accY = take(rs * (int64_t)P.n_acc * W);
+  Y.l_tdc = take(P.has_ft_ops ? 0 : rs * n_lc * F * G * G);
   Y.l_cmA = take(rs * (1 + NG) * W); Y.l_cmB = take(rs * (1 + NG) * W);
   Y.l_mvY = take(4 * (int64_t)P.n_slot * W); Y.l_mvD = take(4 * (int64_t)P.n_slot * W);
   Y.l_ysS = take(8 * nS * W); Y.l_KS = take(8 * 7 * nS * W); Y.l_red = take(8 * W);
@@ -567,11 +589,12 @@ std::string gen_spec(const epi_engine* h) {
   o << "constexpr int C = " << P.C << ", L = " << P.L << ", G = " << P.G << ", F = " << P.F << ", P = " << P.P << ", I = " << P.I
     << ", LG = " << P.LG << ", CLG = " << P.CLG << ", nnz = " << P.nnz << ", n_lc = " << P.n_lc << ", E = " << P.E
     << ", NG = " << P.NG << ", NSRC = " << P.NSRC << ", n_acc = " << P.n_acc << ", n_slot = " << P.n_slot
-    << ", has_ft_ops = " << P.has_ft_ops << ", has_src64 = " << P.has_src64 << ";\n";
+    << ", has_ft_ops = " << P.has_ft_ops << ", has_src64 = " << P.has_src64
+    << ", dense_mob = " << (P.mob_dense_csc ? 1 : 0) << ";\n";
   {
     const CellLayout& Y = P.cl;  // built for 32-lane warps
-    o << "constexpr int l_X = " << Y.l_X << ", l_ys = " << Y.l_ys << ", l_K = " << Y.l_K << ", l_fl = " << Y.l_fl << ", l_FB = " << Y.l_FB
-      << ", l_FE = " << Y.l_FE << ", l_cmA = " << Y.l_cmA << ", l_cmB = " << Y.l_cmB << ", l_mvY = " << Y.l_mvY << ", l_mvD = " << Y.l_mvD
+    o << "constexpr int l_X = " << Y.l_X << ", l_ys = " << Y.l_ys << ", l_K = " << Y.l_K << ", l_fl = " << Y.l_fl << ", l_FBE = " << Y.l_FBE
+      << ", l_accY = " << Y.l_accY << ", l_tdc = " << Y.l_tdc << ", LW = " << Y.lw << ", l_cmA = " << Y.l_cmA << ", l_cmB = " << Y.l_cmB << ", l_mvY = " << Y.l_mvY << ", l_mvD = " << Y.l_mvD
       << ", l_ysS = " << Y.l_ysS << ", l_KS = " << Y.l_KS << ", l_red = " << Y.l_red << ";\n";
     o << "constexpr int e_base = " << Y.e_base << ", e_bytes = " << Y.e_bytes << ", e_mult_y = " << Y.e_mult_y << ", e_mult_d = " << Y.e_mult_d
       << ", e_cpv = " << Y.e_cpv << ", e_act = " << Y.e_act << ", e_expr = " << Y.e_expr << ", e_sel = " << Y.e_sel << ", e_mpy = " << Y.e_mpy
@@ -638,10 +661,10 @@ std::string gen_spec(const epi_engine* h) {
   }
   o << "}\n";
   // accumulator derivatives of a flow column (col already offset by the lane; stride 32)
-  o << "__device__ __forceinline__ void acc(const real* col, real* out) {\n";
+  o << "template <int STRIDE> __device__ __forceinline__ void acc(const real* col, real* out) {\n";
   for (int a = 0; a < P.n_acc; a++) {
     o << "  out[" << a << "] = 0;";
-    for (int q = T.ag_off[a]; q < T.ag_off[a + 1]; q++) o << " out[" << a << "] += col[" << T.ag_src[q] * 32 << "] * " << hexf(T.ag_coef[q]) << ";";
+    for (int q = T.ag_off[a]; q < T.ag_off[a + 1]; q++) o << " out[" << a << "] += col[" << T.ag_src[q] << " * STRIDE] * " << hexf(T.ag_coef[q]) << ";";
     o << "\n";
   }
   o << "}\n}}\n";
@@ -650,7 +673,7 @@ std::string gen_spec(const epi_engine* h) {
   uint64_t k = 1469598103934665603ull;
   auto mix = [&](const void* p, size_t n) { for (size_t i = 0; i < n; i++) { k ^= ((const unsigned char*)p)[i]; k *= 1099511628211ull; } };
   mix(body.data(), body.size());
-  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 4 /* generator revision */};
+  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 5 /* generator revision */};
   mix(abi, sizeof abi);
   char kb[32];
   snprintf(kb, sizeof kb, "%016llx", (unsigned long long)k);
@@ -693,7 +716,7 @@ void choose_launch(epi_engine* h) {
       P.cl.enabled = 1;
       h->cta_mode = 2; h->cellW = W;
       P.small_in_smem = P.big_in_smem = 1;
-      h->wpb = 1; h->threads = W;
+      h->wpb = 1; h->threads = W;  // (the emulation runs LW host threads per warp)
       h->smem_bytes = (size_t)P.cl.warp_bytes;
       h->grid = (h->N + P.cl.epw - 1) / P.cl.epw;
       h->scratch_bytes = 0;

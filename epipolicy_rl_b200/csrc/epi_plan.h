@@ -22,8 +22,9 @@
 // Per-lane columns hold element i of lane ln at off + (i * W + ln) * sizeof(T); the per-env (slot)
 // tables start at e_base + slot * e_bytes.
 struct CellLayout {
-  int enabled, epw;  // envs per warp = W / (L*G)
-  int64_t l_X, l_ys, l_K, l_fl, l_FB, l_FE, l_cmA, l_cmB, l_mvY, l_mvD, l_ysS, l_KS, l_red;
+  int enabled, epw;  // envs per warp = 32 / (L*G)
+  int lw;            // lanes that carry a cell = epw * L*G = width of a per-lane column
+  int64_t l_X, l_ys, l_K, l_fl, l_FBE, l_accY, l_tdc, l_cmA, l_cmB, l_mvY, l_mvD, l_ysS, l_KS, l_red;
   int64_t e_base, e_bytes;
   int64_t e_mult_y, e_mult_d, e_cpv, e_act, e_expr, e_sel, e_mpy, e_mpg, e_mpt0, e_mpFy, e_mpFg, e_coefS, e_Tnum,
       e_Tden, e_fi_y, e_fi_gap, e_ft_y, e_ft_gap, e_cost, e_crY, e_crD;
@@ -57,6 +58,7 @@ struct DevPlan {
   const double* Tden_const64;
   const float* mx_csr;       // [G,nnz] combined mobility on the union pattern (core_optimize.py:69-92)
   const float* mx_csc;       // [G,nnz]
+  const float *mob_dense_csc, *mob_dense_csr; // [LG,L] dense column / row of every cell when L <= 4 (else null)
   const int *csr_indptr, *csr_indices, *csc_indptr, *csc_indices;
   // ---- multiplier classes
   const int* cls_off;        // [n_cls+1]
