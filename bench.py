@@ -240,6 +240,11 @@ def run_ours(args):
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = n_envs * base_b / (ms_per_step * 1e-3) / 1e9
+        # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(f"{args.workload}:{args.precision}:{n_envs}", {}).get("dram_bytes_per_launch")
         cpu_v, cpu_dt = cpu_port_rate(desc, args.cpu_sample_envs, args.cpu_sample_steps)
         line = {
             "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -247,10 +252,12 @@ def run_ours(args):
             "dtype": "f32" if args.precision == "fp32" else "f64", "data": "synthetic",
             "config": {"workload": workload_name(args, desc), "envs_per_gpu": n_envs, "days_per_step": PERIOD,
                        "sim_days_per_s": value * PERIOD, "l2": "flushed between timed steps (256 MiB write)",
-                       "team": "cta" if info.team_kind else "warp", "threads": info.threads, "grid": info.grid,
+                       "kernel": {0: "warp-team", 1: "cta-team", 2: "cell"}[info.team_kind] +
+                                 ("+specialised" if info.specialized else ""),
+                       "threads": info.threads, "grid": info.grid,
                        "smem_bytes": info.smem_bytes, "collective": "all_gather obs/reward/done" if world > 1 else "none"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "bytes_per_env_launch": base_b,
+                         "traffic": traffic, "peak_source": peak_src, "bytes_per_env_launch": base_b,
                          "bytes_per_env_launch_with_rk45_accumulators": ctrl_b,
                          "frac_with_rk45_accumulators": n_envs * ctrl_b / (ms_per_step * 1e-3) / 1e9 / peak},
             "cpu_baseline": {"value": cpu_v, "unit": "env-steps/s", "cores": 1, "kind": "port",
