@@ -27,6 +27,9 @@ WORKLOADS = {
     # name: (desc file or generator, default envs per GPU, description)
     "covid_c": ("tests/golden/desc_COVID_C.npz", 4096, "COVID_C.json x 4096 envs per GPU, fp32, random actions (BASELINE.json configs[2])"),
     "sirv_b": ("tests/golden/desc_SIRV_B.npz", 1024, "SIRV_B.json x 1024 envs per GPU (BASELINE.json configs[1])"),
+    "syn_s": ("tests/golden/desc_syn_s.npz", 4096, "synthetic COVID-like L=20 G=4 F=8 (epipolicy_rl_b200/synth.py)"),
+    "syn_m": ("tests/golden/desc_syn_m.npz", 1024, "synthetic COVID-like L=100 G=8 F=8 (epipolicy_rl_b200/synth.py)"),
+    "syn": ("tests/golden/desc_syn.npz", 296, "synthetic COVID-like L=1000 G=16 F=8 (BASELINE.json configs[3])"),
 }
 
 
@@ -92,14 +95,22 @@ class ClockSampler:
                 "samples": len(rows)}
 
 
-def cpu_port_rate(desc, n_envs, n_steps, seed=0):
-    """The oracle (C restatement of the reference), one host thread: env-steps/s on a bounded sample."""
+def cpu_port_rate(desc, n_envs, n_steps, seed=0, budget_s=12.0):
+    """The oracle (C restatement of the reference), one host thread: env-steps/s on a bounded sample
+    (at most n_envs x n_steps gym steps, cut down to about `budget_s` seconds of CPU work)."""
     from oracle.oracle import rollout
-    acts = np.random.default_rng(seed).uniform(0, 1, (n_envs, n_steps, desc.A)).astype(np.float32)
+    rng = np.random.default_rng(seed)
+    t0 = time.perf_counter()
+    rollout(desc, rng.uniform(0, 1, (1, 1, desc.A)).astype(np.float32), PERIOD, want_final=False)
+    one = time.perf_counter() - t0
+    if one * n_envs * n_steps > budget_s:
+        n_steps = max(1, min(n_steps, int(budget_s / one / max(n_envs, 1))))
+        n_envs = max(1, min(n_envs, int(budget_s / one / n_steps)))
+    acts = rng.uniform(0, 1, (n_envs, n_steps, desc.A)).astype(np.float32)
     t0 = time.perf_counter()
     rollout(desc, acts, PERIOD, want_final=False)
     dt = time.perf_counter() - t0
-    return n_envs * n_steps / dt, dt
+    return n_envs * n_steps / dt, dt, n_envs, n_steps
 
 
 def _ref_worker(args):
@@ -245,7 +256,7 @@ def run_ours(args):
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(f"{args.workload}:{args.precision}:{n_envs}", {}).get("dram_bytes_per_launch")
-        cpu_v, cpu_dt = cpu_port_rate(desc, args.cpu_sample_envs, args.cpu_sample_steps)
+        cpu_v, cpu_dt, cpu_ne, cpu_ns = cpu_port_rate(desc, args.cpu_sample_envs, args.cpu_sample_steps)
         line = {
             "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -261,7 +272,7 @@ def run_ours(args):
                          "bytes_per_env_launch_with_rk45_accumulators": ctrl_b,
                          "frac_with_rk45_accumulators": n_envs * ctrl_b / (ms_per_step * 1e-3) / 1e9 / peak},
             "cpu_baseline": {"value": cpu_v, "unit": "env-steps/s", "cores": 1, "kind": "port",
-                             "sample": f"{args.cpu_sample_envs} envs x {args.cpu_sample_steps} gym steps, {cpu_dt:.1f} s, "
+                             "sample": f"{cpu_ne} envs x {cpu_ns} gym steps, {cpu_dt:.1f} s, "
                                        "oracle/epi_oracle.c single thread"},
             "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks,
