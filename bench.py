@@ -263,7 +263,7 @@ def run_ours(args):
             "dtype": "f32" if args.precision == "fp32" else "f64", "data": "synthetic",
             "config": {"workload": workload_name(args, desc), "envs_per_gpu": n_envs, "days_per_step": PERIOD,
                        "sim_days_per_s": value * PERIOD, "l2": "flushed between timed steps (256 MiB write)",
-                       "kernel": {0: "warp-team", 1: "cta-team", 2: "cell"}[info.team_kind] +
+                       "kernel": {0: "warp-team", 1: "cta-team", 2: "cell", 3: "env"}[info.team_kind] +
                                  ("+specialised" if info.specialized else ""),
                        "threads": info.threads, "grid": info.grid,
                        "smem_bytes": info.smem_bytes, "collective": "all_gather obs/reward/done" if world > 1 else "none"},

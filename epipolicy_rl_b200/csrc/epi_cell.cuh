@@ -30,65 +30,13 @@
 // Reference call stack and precision map: see epi_kernels.cuh (same arithmetic, same rounding points).
 #pragma once
 #include "epi_kernels.cuh"
+#include "epi_rk.cuh"
 
 namespace epi {
 namespace cell {
+using namespace rk;
 
 #define EPI_FULL 0xffffffffu
-
-// float copies of the tableau for the fp32 mode (no F2F in the stage algebra)
-__constant__ float RK_A32[6][5] = {
-    {0, 0, 0, 0, 0},
-    {(float)(1.0 / 5), 0, 0, 0, 0},
-    {(float)(3.0 / 40), (float)(9.0 / 40), 0, 0, 0},
-    {(float)(44.0 / 45), (float)(-56.0 / 15), (float)(32.0 / 9), 0, 0},
-    {(float)(19372.0 / 6561), (float)(-25360.0 / 2187), (float)(64448.0 / 6561), (float)(-212.0 / 729), 0},
-    {(float)(9017.0 / 3168), (float)(-355.0 / 33), (float)(46732.0 / 5247), (float)(49.0 / 176), (float)(-5103.0 / 18656)}};
-__constant__ float RK_B32[7] = {(float)(35.0 / 384), 0, (float)(500.0 / 1113), (float)(125.0 / 192), (float)(-2187.0 / 6784), (float)(11.0 / 84), 0};
-__constant__ float RK_E32[7] = {(float)(-71.0 / 57600), 0, (float)(71.0 / 16695), (float)(-71.0 / 1920), (float)(17253.0 / 339200), (float)(-22.0 / 525), (float)(1.0 / 40)};
-__device__ __forceinline__ float rkA(float, int s, int j) { return RK_A32[s][j]; }
-__device__ __forceinline__ double rkA(double, int s, int j) { return RK_A[s][j]; }
-__device__ __forceinline__ float rkB(float, int j) { return RK_B32[j]; }
-__device__ __forceinline__ double rkB(double, int j) { return RK_B[j]; }
-__device__ __forceinline__ float rkE(float, int j) { return RK_E32[j]; }
-__device__ __forceinline__ double rkE(double, int j) { return RK_E[j]; }
-
-// per-lane columns and per-env tables: element types
-#define T_X double
-#define T_ys real
-#define T_K real
-#define T_fl real
-#define T_FBE real2
-#define T_accY real
-#define T_tdc real
-#define T_cmA real
-#define T_cmB real
-#define T_mvY float
-#define T_mvD float
-#define T_ysS double
-#define T_KS double
-#define T_red double
-#define T_mult_y float
-#define T_mult_d float
-#define T_cpv float
-#define T_act uint8_t
-#define T_expr double
-#define T_sel double
-#define T_mpy float
-#define T_mpg float
-#define T_mpt0 float
-#define T_mpFy float
-#define T_mpFg float
-#define T_coefS real
-#define T_Tnum float
-#define T_Tden real
-#define T_fi_y float
-#define T_fi_gap float
-#define T_ft_y float
-#define T_ft_gap float
-#define T_cost double
-#define T_crY double
-#define T_crD double
 
 #ifdef EPI_SPEC
 // dimensions and layout are compile-time constants; every access indexes the dynamic shared array itself,
@@ -114,11 +62,6 @@ extern __shared__ __align__(16) char cell_smem[];
 #define LO(arr, i, ln) (COLP(arr)[(i) * EPI_LW + (ln)])
 #define EV(arr, i) (ENVP(arr)[i])
 #define WT(arr, i) (COLP(arr)[i])  // warp-wide table
-
-template <class T> struct Pair { T x, y; };
-template <> struct __align__(8) Pair<float> { float x, y; };
-template <> struct __align__(16) Pair<double> { double x, y; };
-#define real2 Pair<real>
 
 struct Cx {
   int lane, slot, cell, j, u, lc, l0;  // l0: first lane of my env

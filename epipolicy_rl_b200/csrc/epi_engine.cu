@@ -20,6 +20,7 @@
 #include "../../include/epi_b200.h"
 #include "epi_kernels.cuh"
 #include "epi_cell.cuh"
+#include "epi_env.cuh"
 
 namespace {
 
@@ -58,6 +59,7 @@ struct epi_engine {
   DevState S{}, init{};
   std::vector<void*> allocs;
   char *big_scratch = nullptr, *small_scratch = nullptr;
+  double* cr_scratch = nullptr;
   int cta_mode = 0, threads = 128, wpb = 4, grid = 1;  // cta_mode: 0 warp team, 1 CTA team, 2 cell kernel
   int cellW = 32;                   // lanes per warp of the cell kernel (32 on the device; the host emulation shrinks it)
   size_t smem_bytes = 0, scratch_bytes = 0;
@@ -573,6 +575,44 @@ void build_cell_layout(epi_engine* h, int W) {
 }
 
 
+// layout of the env kernel (epi_env.cuh) for CTAs of `threads` threads
+void build_env_layout(epi_engine* h, int threads, int64_t smem_max) {
+  DevPlan& P = h->plan;
+  EnvLayout& Y = P.el;
+  const int64_t rs = (int64_t)h->real_size();
+  const int64_t C = P.C, G = P.G, F = P.F, n_lc = P.n_lc, NG = P.NG, nC = (int64_t)P.I * P.L, LG = P.LG;
+  Y = EnvLayout{};
+  Y.threads = threads;
+  int64_t o = 0;
+  auto take = [&](int64_t bytes) { int64_t r = o; o = align16(o + bytes); return r; };
+  const int64_t nS = P.has_src64 ? P.n_slot : 0;
+  Y.l_X = take(8 * C * LG); Y.l_ys = take(rs * C * LG); Y.l_K = take(rs * 7 * C * LG);
+  Y.l_fl = take(rs * P.NSRC * LG); Y.l_FBE = take(2 * rs * P.NSRC * LG); Y.l_accY = take(rs * (int64_t)P.n_acc * LG);
+  Y.l_mvY = take(4 * (int64_t)P.n_slot * LG); Y.l_mvD = take(4 * (int64_t)P.n_slot * LG);
+  Y.l_ysS = take(8 * nS * LG); Y.l_KS = take(8 * 7 * nS * LG);
+  Y.big_bytes = o;
+  o = 0;
+  Y.l_cmA = take(rs * (1 + NG) * LG); Y.l_cmB = take(rs * (1 + NG) * LG);
+  Y.comm_bytes = o;
+  o = 0;
+  Y.e_mult_y = take(4 * (int64_t)P.n_cls); Y.e_mult_d = take(4 * (int64_t)P.n_cls);
+  Y.e_cpv = take(4 * (int64_t)P.NCP); Y.e_act = take(P.I);
+  Y.e_expr = take(8 * (int64_t)P.n_expr); Y.e_sel = take(8 * (int64_t)P.n_sel);
+  Y.e_mpy = take(4 * n_lc * P.P * G); Y.e_mpg = take(4 * n_lc * P.P * G); Y.e_mpt0 = take(4 * n_lc * P.P * G);
+  Y.e_mpFy = take(4 * (int64_t)P.n_igp * n_lc * F * G); Y.e_mpFg = take(4 * (int64_t)P.n_igp * n_lc * F * G);
+  Y.e_coefS = take(rs * NG * n_lc * F * G); Y.e_Tnum = take(4 * n_lc * F * G * G);
+  Y.e_Tden = take(P.has_ft_ops ? rs * n_lc * F * G * G : 0);
+  Y.e_fi_y = take(4 * n_lc * F * G * G); Y.e_fi_gap = take(4 * n_lc * F * G * G);
+  Y.e_ft_y = take(4 * n_lc * F * G); Y.e_ft_gap = take(4 * n_lc * F * G);
+  Y.e_cost = Y.e_crY = Y.e_crD = o;  // the cost arrays of the env kernel live in global memory
+  Y.tab_bytes = o;
+  Y.red_bytes = align16(8 * (int64_t)threads);
+  int64_t used = Y.tab_bytes + Y.red_bytes;
+  Y.comm_in_smem = used + Y.comm_bytes <= smem_max;
+  if (Y.comm_in_smem) used += Y.comm_bytes;
+  Y.big_in_smem = Y.comm_in_smem && used + Y.big_bytes <= smem_max;
+}
+
 // ------------------------------------------------------------------------------------------
 // scenario-specialised code generator: the per-cell program of the cell kernel as straight-line CUDA
 // (same operations in the same order as the interpreted path of epi_cell.cuh)
@@ -591,7 +631,8 @@ std::string gen_spec(const epi_engine* h) {
     << ", NG = " << P.NG << ", NSRC = " << P.NSRC << ", n_acc = " << P.n_acc << ", n_slot = " << P.n_slot
     << ", has_ft_ops = " << P.has_ft_ops << ", has_src64 = " << P.has_src64
     << ", dense_mob = " << (P.mob_dense_csc ? 1 : 0) << ";\n";
-  {
+  o << "constexpr int big = " << (P.LG > 32 ? 1 : 0) << ";  // 1: env kernel (epi_env.cuh), 0: cell kernel (epi_cell.cuh)\n";
+  if (P.LG <= 32) {
     const CellLayout& Y = P.cl;  // built for 32-lane warps
     o << "constexpr int l_X = " << Y.l_X << ", l_ys = " << Y.l_ys << ", l_K = " << Y.l_K << ", l_fl = " << Y.l_fl << ", l_FBE = " << Y.l_FBE
       << ", l_accY = " << Y.l_accY << ", l_tdc = " << Y.l_tdc << ", LW = " << Y.lw << ", l_cmA = " << Y.l_cmA << ", l_cmB = " << Y.l_cmB << ", l_mvY = " << Y.l_mvY << ", l_mvD = " << Y.l_mvD
@@ -667,18 +708,25 @@ std::string gen_spec(const epi_engine* h) {
     for (int q = T.ag_off[a]; q < T.ag_off[a + 1]; q++) o << " out[" << a << "] += col[" << T.ag_src[q] << " * STRIDE] * " << hexf(T.ag_coef[q]) << ";";
     o << "\n";
   }
+  o << "}\n";
+  o << "__device__ __forceinline__ void acc_rt(const real* col, size_t stride, real* out) {\n";
+  for (int a = 0; a < P.n_acc; a++) {
+    o << "  out[" << a << "] = 0;";
+    for (int q = T.ag_off[a]; q < T.ag_off[a + 1]; q++) o << " out[" << a << "] += col[" << T.ag_src[q] << " * stride] * " << hexf(T.ag_coef[q]) << ";";
+    o << "\n";
+  }
   o << "}\n}}\n";
   std::string body = o.str();
   // key: FNV-1a of the body + the ABI of the structs passed by value
   uint64_t k = 1469598103934665603ull;
   auto mix = [&](const void* p, size_t n) { for (size_t i = 0; i < n; i++) { k ^= ((const unsigned char*)p)[i]; k *= 1099511628211ull; } };
   mix(body.data(), body.size());
-  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 5 /* generator revision */};
+  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 6 /* generator revision */};
   mix(abi, sizeof abi);
   char kb[32];
   snprintf(kb, sizeof kb, "%016llx", (unsigned long long)k);
   return std::string("// GENERATED by libepi_b200 (epi_engine.cu: gen_spec) - scenario-specialised per-cell program\n#define EPI_SPEC 1\n#define EPI_SPEC_KEY \"") +
-         kb + "\"\n" + body;
+         kb + "\"\n#define EPI_SPEC_BIG " + (P.LG > 32 ? "1" : "0") + "\n" + body;
 }
 
 void alloc_state(epi_engine* h, DevState& S, int N) {
@@ -722,6 +770,33 @@ void choose_launch(epi_engine* h) {
       h->scratch_bytes = 0;
       return;
     }
+  }
+  P.el.enabled = 0;
+  if (P.LG > 32 && !(force && (!strcmp(force, "warp") || !strcmp(force, "cta")))) {
+    // ENV kernel: one CTA per env, threads strided over the cells
+#ifdef EPI_HOST_EMU
+    int threads = P.LG < 24 ? P.LG : 24;  // host threads per emulated CTA
+#else
+    int threads = P.LG >= 256 ? 256 : ((P.LG + 31) / 32) * 32;
+#endif
+    build_env_layout(h, threads, smem_max);
+    P.el.enabled = 1;
+    h->cta_mode = 3; h->threads = threads; h->wpb = 1;
+    P.small_in_smem = 1; P.big_in_smem = P.el.big_in_smem;
+    h->smem_bytes = (size_t)(P.el.tab_bytes + P.el.red_bytes + (P.el.comm_in_smem ? P.el.comm_bytes : 0) +
+                             (P.el.big_in_smem ? P.el.big_bytes : 0));
+    int ctas_per_sm = (int)((prop.sharedMemPerMultiprocessor - 1024) / (h->smem_bytes + 1024));
+    int by_regs = 65536 / (threads * 128);  // __launch_bounds__(256): ptxas settles on <= 128 registers
+    if (by_regs < 1) by_regs = 1;
+    if (ctas_per_sm > by_regs) ctas_per_sm = by_regs;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    int cap = sms * ctas_per_sm;
+    h->grid = h->N < cap ? h->N : cap;
+    h->scratch_bytes = (size_t)h->grid * ((P.el.big_in_smem ? 0 : P.el.big_bytes) + (P.el.comm_in_smem ? 0 : P.el.comm_bytes));
+    if (!P.el.big_in_smem) h->big_scratch = h->dalloc<char>((size_t)P.el.big_bytes * h->grid, false);
+    if (!P.el.comm_in_smem) h->small_scratch = h->dalloc<char>((size_t)P.el.comm_bytes * h->grid, false);
+    h->cr_scratch = h->dalloc<double>((size_t)P.I * P.L * h->grid);
+    return;
   }
   if (force && !strcmp(force, "cta")) per_env = INT64_MAX / 16;
   if (per_env * 8 <= (int64_t)prop.sharedMemPerMultiprocessor - 8 * 1024 || per_env <= 28 * 1024) {
@@ -796,8 +871,38 @@ void launch_cell(epi_engine* h, const DevState& S, const epi::StepArgs& a, cudaS
   h->launches++;
 }
 
+template <class real>
+void launch_env(epi_engine* h, const DevState& S, const epi::StepArgs& a, cudaStream_t st) {
+  const int grid = a.N < h->grid ? a.N : h->grid;
+#ifdef EPI_HOST_EMU
+  (void)st;
+  emu::run_warps(grid, h->threads, h->smem_bytes, [&](char* smem, int tid, int cta) {
+    epi::env::Bx b = epi::env::bind(h->plan, a, smem, tid, h->threads, cta);
+    epi::env::step_cta<real>(h->plan, S, a, b, cta, grid);
+  });
+#else
+  if (h->spec_launch) {
+    int rc = h->spec_launch(&h->plan, &S, &a, grid, h->threads, h->smem_bytes, (void*)st);
+    if (rc != 0) throw CudaFail{std::string("specialised env kernel launch: ") + cudaGetErrorString((cudaError_t)rc)};
+  } else {
+    auto kern = epi::env::env_kernel<real>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    kern<<<grid, h->threads, h->smem_bytes, st>>>(h->plan, S, a);
+    CK(cudaGetLastError());
+  }
+#endif
+  h->launches++;
+}
+
 void launch(epi_engine* h, const DevState& S, epi::StepArgs a, cudaStream_t st) {
   a.dbg_attempts = (a.N == h->N) ? h->dbg_attempts : nullptr;
+  if (h->cta_mode == 3) {
+    a.big_scratch = h->big_scratch;
+    a.small_scratch = h->small_scratch;
+    a.cr_scratch = h->cr_scratch;
+    if (h->precision == EPI_FP64) launch_env<double>(h, S, a, st); else launch_env<float>(h, S, a, st);
+    return;
+  }
   if (h->cta_mode == 2) {
     if (h->precision == EPI_FP64) launch_cell<double>(h, S, a, st); else launch_cell<float>(h, S, a, st);
     return;
@@ -1099,7 +1204,7 @@ int64_t epi_launch_count(const epi_t* h) { return h ? h->launches : 0; }
 int epi_spec_source(epi_t* h, char* buf, size_t cap, size_t* need) {
   if (!h) return EPI_E_INVALID;
   return guarded(h, [&] {
-    if (h->cta_mode != 2) throw Unsupported{"scenario specialisation exists for the cell kernel only (L*G <= 32)"};
+    if (h->cta_mode < 2) throw Unsupported{"scenario specialisation exists for the cell and env kernels only"};
     std::string src = gen_spec(h);
     if (need) *need = src.size() + 1;
     if (buf && cap) {
@@ -1117,8 +1222,7 @@ int epi_spec_source_desc(const EpiDesc* desc, int precision, char* buf, size_t c
   int rc = guarded(nullptr, [&] {
     h->d = *desc;
     build_plan(h, *desc);
-    if (h->plan.LG > 32) throw Unsupported{"scenario specialisation exists for the cell kernel only (L*G <= 32)"};
-    build_cell_layout(h, 32);
+    if (h->plan.LG <= 32) build_cell_layout(h, 32);
     std::string src = gen_spec(h);
     if (need) *need = src.size() + 1;
     if (buf && cap) {
@@ -1135,7 +1239,7 @@ int epi_spec_source_desc(const EpiDesc* desc, int precision, char* buf, size_t c
 int epi_spec_attach(epi_t* h, const char* so_path) {
   if (!h || !so_path) return EPI_E_INVALID;
   return guarded(h, [&] {
-    if (h->cta_mode != 2) throw Unsupported{"scenario specialisation exists for the cell kernel only (L*G <= 32)"};
+    if (h->cta_mode < 2) throw Unsupported{"scenario specialisation exists for the cell and env kernels only"};
 #ifdef EPI_HOST_EMU
     throw Unsupported{"no specialised kernels in the host emulation"};
 #else

@@ -722,6 +722,7 @@ struct StepArgs {
   char* big_scratch;      // n_teams * big_bytes when !big_in_smem
   char* small_scratch;    // n_teams * small_bytes when !small_in_smem
   double* dbg_attempts;   // optional [N,64,2]: (h, error_norm) of each attempted RK step of the last day
+  double* cr_scratch;     // env kernel: n_ctas * I*L doubles (today's cost rate)
 };
 
 // one team, one env at a time: load state, prologue + RK45 for each day, store

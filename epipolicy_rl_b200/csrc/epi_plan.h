@@ -31,6 +31,17 @@ struct CellLayout {
   int64_t warp_bytes;
 };
 
+// layout of the env kernel (epi_env.cuh): byte offsets of the [word][cell] columns inside the "big" and "comm"
+// regions and of the per-env tables inside the table block; where each region lives.
+struct EnvLayout {
+  int enabled, threads, comm_in_smem, big_in_smem;
+  int64_t l_X, l_ys, l_K, l_fl, l_FBE, l_accY, l_mvY, l_mvD, l_ysS, l_KS;  // big region
+  int64_t l_cmA, l_cmB;                                                      // comm region
+  int64_t e_mult_y, e_mult_d, e_cpv, e_act, e_expr, e_sel, e_mpy, e_mpg, e_mpt0, e_mpFy, e_mpFg, e_coefS, e_Tnum,
+      e_Tden, e_fi_y, e_fi_gap, e_ft_y, e_ft_gap, e_cost, e_crY, e_crD;
+  int64_t tab_bytes, red_bytes, comm_bytes, big_bytes;
+};
+
 struct DevPlan {
   // ---- dimensions
   int C, L, G, F, P, I, A, NCP, LG, CLG, nnz, n_lc;
@@ -113,6 +124,7 @@ struct DevPlan {
   int64_t o_X, o_ys, o_K, o_accY, o_accB, o_accE, o_accF, o_accF2, o_flows, o_alive, o_Xw, o_Ag, o_Wg, o_s, o_r,
       o_mvY, o_mvD, o_cost, o_crY, o_crD, o_ysS, o_KS;   // big region (bytes)
   CellLayout cl;
+  EnvLayout el;
   int has_src64;  // fp32 mode with move slots: the slots' source compartments are carried in double
 };
 

@@ -3,13 +3,19 @@
 // The generated header (epi_spec_source, include/epi_b200.h) defines EPI_SPEC, EPI_SPEC_KEY and the
 // scenario's per-cell program in namespace epi::spec; epi_cell.cuh then compiles its specialised path.
 #include EPI_SPEC_HEADER
+#if EPI_SPEC_BIG
+#include "epi_env.cuh"
+#define EPI_SPEC_KERNEL epi::env::env_kernel<epi::spec::real>
+#else
 #include "epi_cell.cuh"
+#define EPI_SPEC_KERNEL epi::cell::cell_kernel<epi::spec::real>
+#endif
 
 extern "C" const char* epi_spec_key() { return EPI_SPEC_KEY; }
 
 extern "C" int epi_spec_launch(const DevPlan* P, const DevState* S, const epi::StepArgs* a, int grid, int threads,
                                size_t smem, void* stream) {
-  auto kern = epi::cell::cell_kernel<epi::spec::real>;
+  auto kern = EPI_SPEC_KERNEL;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   kern<<<grid, threads, smem, (cudaStream_t)stream>>>(*P, *S, *a);

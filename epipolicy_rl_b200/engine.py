@@ -43,7 +43,7 @@ class BatchedEpidemic:
         self.info = _lib.EpiInfo()
         self._ck(self.L.epi_info(self._h, ctypes.byref(self.info)))
         self.obs_dim, self.action_dim = self.info.obs_dim, self.info.action_dim
-        if self.info.team_kind == 2:
+        if self.info.team_kind in (2, 3):
             # scenario-specialised build of the cell kernel (spec.py); the interpreted kernel runs if absent
             from . import spec as _spec
             path = _spec.ensure(desc, self.precision)

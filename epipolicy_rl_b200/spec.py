@@ -48,7 +48,7 @@ def _src_hash() -> str:
     if _SRC_HASH is None:
         import hashlib
         h = hashlib.sha1()
-        for f in ("epi_cell.cuh", "epi_kernels.cuh", "epi_plan.h", "epi_spec_main.cu"):
+        for f in ("epi_cell.cuh", "epi_env.cuh", "epi_rk.cuh", "epi_kernels.cuh", "epi_plan.h", "epi_spec_main.cu"):
             with open(os.path.join(CSRC, f), "rb") as fh:
                 h.update(fh.read())
         h.update(" ".join(NVCC_FLAGS).encode())
@@ -87,7 +87,7 @@ def compile_spec(text: str, key: str) -> str | None:
 
 def ensure(desc, precision: int, compile_missing: bool = True) -> str | None:
     """Path of the specialised library for (desc, precision), building it if needed and possible."""
-    if os.environ.get("EPI_SPEC", "1") == "0" or desc.L * desc.G > 32:
+    if os.environ.get("EPI_SPEC", "1") == "0":
         return None
     text, key = source(desc, precision)
     out = so_path(key)

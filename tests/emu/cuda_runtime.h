@@ -44,8 +44,8 @@ static thread_local pthread_barrier_t* warp_barrier = nullptr;
 static thread_local int lane_id = 0;
 static thread_local int* vote_buf = nullptr;
 }  // namespace emu
-inline void __syncthreads() {}
 inline void __syncwarp() { if (emu::warp_barrier) pthread_barrier_wait(emu::warp_barrier); }
+inline void __syncthreads() { if (emu::warp_barrier) pthread_barrier_wait(emu::warp_barrier); }
 template <class T> inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
 inline int __any_sync(unsigned, int pred) {
   if (!emu::warp_barrier) return pred;

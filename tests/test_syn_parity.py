@@ -1,6 +1,7 @@
 """Synthetic COVID-like scenarios (BASELINE.json configs[3] and two smaller sizes; epipolicy_rl_b200/synth.py):
 the session is built in the reference's own schema, run through the UNMODIFIED reference (tools/gen_syn.py) and
-its per-day trajectory is the golden here. L*G > 32, so these exercise the CTA-team kernel."""
+its per-day trajectory is the golden here. L*G > 32, so these exercise the env kernel (epi_env.cuh: one CTA per env,
+threads strided over the cells) and, with EPI_TEAM=cta, the older CTA-team kernel."""
 import os
 import sys
 
@@ -26,15 +27,18 @@ def _run(eng, d, z, to_dev, n_weeks):
     return worst, worst_c, mism
 
 
+@pytest.mark.parametrize("kernel", ["env", "cta"])
 @pytest.mark.parametrize("prec", ["fp64", "fp32"])
 @pytest.mark.parametrize("name,weeks", [("syn_s", 2), ("syn_m", 1)])
-def test_emulated_team_kernel_vs_reference(name, weeks, prec):
+def test_emulated_kernels_vs_reference(name, weeks, prec, kernel, monkeypatch):
     from emu_engine import EmuEngine
     d, z = load(name)
+    if kernel == "cta":
+        monkeypatch.setenv("EPI_TEAM", "cta")
     eng = EmuEngine(d, 1, prec)
-    assert eng.info.team_kind == 1
+    assert eng.info.team_kind == (3 if kernel == "env" else 1)
     worst, worst_c, mism = _run(eng, d, z, lambda a: a, weeks)
-    print(f"{name} {prec} (emulated): X {worst:.2e} cost {worst_c:.2e} nfev mismatches {mism}")
+    print(f"{name} {prec} {kernel} (emulated): X {worst:.2e} cost {worst_c:.2e} nfev mismatches {mism}")
     assert worst <= TOL[prec] and worst_c <= TOL[prec]
     if prec == "fp64":
         assert mism == 0
