@@ -516,6 +516,15 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
   std::vector<uint8_t> dummy8(1, 0);
   P.alive_coef = h->up(vec(d.alive_coef, C)); P.X0 = h->up(vec(d.X0, (size_t)C * LG)); P.lclass = h->up(lclass);
   P.mp0 = h->up(mp0); P.ft0 = h->up(ft0); P.fi0 = h->up(fi0); P.mp_cls = h->up(mp_cls); P.ft_cls = h->up(ft_cls); P.fi_cls = h->up(fi_cls);
+  {
+    std::vector<float> tdT(tden.size());
+    std::vector<double> td64T(tden64.size());
+    for (int lv = 0; lv < n_lc * F; lv++) for (int u0 = 0; u0 < G; u0++) for (int u = 0; u < G; u++) {
+      tdT[((size_t)lv * G + u) * G + u0] = tden[((size_t)lv * G + u0) * G + u];
+      td64T[((size_t)lv * G + u) * G + u0] = tden64[((size_t)lv * G + u0) * G + u];
+    }
+    P.Tden_constT = h->up(tdT); P.Tden_const64T = h->up(td64T);
+  }
   P.Tden_const = h->up(tden); P.Tden_const64 = h->up(tden64); P.mx_csr = h->up(mx_csr); P.mx_csc = h->up(mx_csc);
   P.mob_dense_csc = dense_csc.empty() ? nullptr : h->up(dense_csc);
   P.mob_dense_csr = dense_csr.empty() ? nullptr : h->up(dense_csr);
@@ -721,7 +730,7 @@ std::string gen_spec(const epi_engine* h) {
   uint64_t k = 1469598103934665603ull;
   auto mix = [&](const void* p, size_t n) { for (size_t i = 0; i < n; i++) { k ^= ((const unsigned char*)p)[i]; k *= 1099511628211ull; } };
   mix(body.data(), body.size());
-  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 6 /* generator revision */};
+  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 7 /* generator revision */};
   mix(abi, sizeof abi);
   char kb[32];
   snprintf(kb, sizeof kb, "%016llx", (unsigned long long)k);

@@ -94,8 +94,11 @@ __device__ __forceinline__ void fill_tables(const DevPlan& P, const Bx& b, float
     float ft = lerp_rn(ET(ft_y, lv * G + u), ET(ft_gap, lv * G + u), tf);
     int a = (lv * G + u0) * G + u, bb = (lv * G + u) * G + u0;
     float fa = lerp_rn(ET(fi_y, a), ET(fi_gap, a), tf), fb = lerp_rn(ET(fi_y, bb), ET(fi_gap, bb), tf);
-    ET(Tnum, i) = __fmul_rn(__fmul_rn(ft, fa), fb);  // f32 product (core_optimize.py:114)
-    if (EDIM(has_ft_ops)) ET(Tden, i) = (real)ft * (real)__ldg(P.fi0 + a) * (real)__ldg(P.fi0 + bb);
+    // stored TRANSPOSED, [lv][u][u0]: the mixing pass reads T[.][u][u0] with u0 = the lane's group, so a
+    // locale's lanes hit consecutive words (no bank conflicts, coalesced)
+    const int it = (lv * G + u) * G + u0;
+    ET(Tnum, it) = __fmul_rn(__fmul_rn(ft, fa), fb);  // f32 product (core_optimize.py:114)
+    if (EDIM(has_ft_ops)) ET(Tden, it) = (real)ft * (real)__ldg(P.fi0 + a) * (real)__ldg(P.fi0 + bb);
   }
   const int FG = F * G, nFG = n_lc * FG;
   for (int i = b.tid; i < NG * nFG; i += b.nt) {
@@ -196,15 +199,29 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Bx& b, bool dyn, dou
 #pragma unroll
       for (int k = 0; k < EPI_MAX_NG; k++) sk[k] = 0;
       const int row = j * G;
+#ifdef EPI_SPEC
+      // the locale's gathered columns once, in registers (G is a compile-time constant)
+      real cb[1 + spec::NG][spec::G];
+#pragma unroll
+      for (int k = 0; k < 1 + spec::NG; k++)
+#pragma unroll
+        for (int u = 0; u < spec::G; u++) cb[k][u] = CM(cmB, k, row + u);
+#define CB(k, u) cb[k][u]
+#else
+#define CB(k, u) CM(cmB, k, row + (u))
+#endif
       for (int v = 0; v < F; v++) {
-        int tb = ((lc * F + v) * G + u0) * G;
+        const int tb = (lc * F + v) * G * G + u0;  // transposed tables: element (u0, u) at tb + u*G
         real den = 0;
         if (EDIM(has_ft_ops)) {
-          for (int u = 0; u < G; u++) den += CM(cmB, 0, row + u) * ET(Tden, tb + u);
+#pragma unroll
+          for (int u = 0; u < G; u++) den += CB(0, u) * ET(Tden, tb + u * G);
         } else if (sizeof(real) == 8) {
-          for (int u = 0; u < G; u++) den += CM(cmB, 0, row + u) * (real)__ldg(P.Tden_const64 + tb + u);
+#pragma unroll
+          for (int u = 0; u < G; u++) den += CB(0, u) * (real)__ldg(P.Tden_const64T + tb + u * G);
         } else {
-          for (int u = 0; u < G; u++) den += CM(cmB, 0, row + u) * (real)__ldg(P.Tden_const + tb + u);
+#pragma unroll
+          for (int u = 0; u < G; u++) den += CB(0, u) * (real)__ldg(P.Tden_constT + tb + u * G);
         }
         if (den <= (real)1e-15) den = 1;
         real inv = (real)1 / den;
@@ -212,11 +229,13 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Bx& b, bool dyn, dou
         for (int k = 0; k < EPI_MAX_NG; k++)
           if (k < NG) {
             real num = 0;
-            for (int u = 0; u < G; u++) num += CM(cmB, 1 + k, row + u) * (real)ET(Tnum, tb + u);
+#pragma unroll
+            for (int u = 0; u < G; u++) num += CB(1 + k, u) * (real)ET(Tnum, tb + u * G);
             real foi = sizeof(real) == 8 ? num / den : num * inv;
             sk[k] += ET(coefS, ((k * n_lc + lc) * F + v) * G + u0) * foi;
           }
       }
+#undef CB
 #pragma unroll
       for (int k = 0; k < EPI_MAX_NG; k++)
         if (k < NG) CM(cmA, 1 + k, cell) = sk[k];  // cmA[1..] is free again: pass 2 has been read out

@@ -67,6 +67,8 @@ struct DevPlan {
   const int* fi_cls;         // [n_lc,F,G,G]
   const float* Tden_const;   // [n_lc,F,G,G] ft*fi0*fi0^T with the default (normalised) ft, when !has_ft_ops
   const double* Tden_const64;
+  const float* Tden_constT;  // the same, transposed [n_lc,F,u,u0] (env kernel)
+  const double* Tden_const64T;
   const float* mx_csr;       // [G,nnz] combined mobility on the union pattern (core_optimize.py:69-92)
   const float* mx_csc;       // [G,nnz]
   const float *mob_dense_csc, *mob_dense_csr; // [LG,L] dense column / row of every cell when L <= 4 (else null)
