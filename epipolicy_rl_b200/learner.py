@@ -1,0 +1,166 @@
+"""Batched PPO over the GPU-resident environments (BASELINE.json configs[4]).
+
+The reference trains with SB3 PPO on ONE env through a DummyVecEnv (runner.py:62-155, hyper-parameters from
+configs/ppo_default.yaml); SB3 is not in this image and a host round trip per env step would undo the batched
+simulator. This is the in-repo learner the north_star asks for: policy/value MLP 256-256 ReLU as
+runner.py:116-119, Gaussian policy clipped to the Box(0,1) action space, GAE(gamma, lambda), clipped surrogate,
+value and entropy terms, gradient clipping (algorithm as in the reference's in-house optimizer/ppo.py:88-353;
+reward scaling as optimizer/env.py:19-36). Everything stays on the device.
+
+Multi-GPU (dist.py): every rank steps its own env shard with a policy replica; ONE all-gather per gym step
+delivers (obs | reward | done) of all shards to every rank, the learner rank (0) additionally receives the
+actions / log-probs / values through the same packed record, runs the PPO update and broadcasts the weights.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+
+class ActorCritic(nn.Module):
+    def __init__(self, obs_dim: int, act_dim: int, hidden=(256, 256), init_log_std: float = -1.0):
+        super().__init__()
+        def mlp(out):
+            layers, d = [], obs_dim
+            for h in hidden:
+                layers += [nn.Linear(d, h), nn.ReLU()]
+                d = h
+            return nn.Sequential(*layers, nn.Linear(d, out))
+        self.pi, self.v = mlp(act_dim), mlp(1)
+        self.log_std = nn.Parameter(torch.full((act_dim,), init_log_std))
+
+    def dist(self, obs):
+        return torch.distributions.Normal(torch.sigmoid(self.pi(obs)), self.log_std.exp())
+
+    @torch.no_grad()
+    def act(self, obs, deterministic: bool = False):
+        d = self.dist(obs)
+        a = d.mean if deterministic else d.sample()
+        return a, d.log_prob(a).sum(-1), self.v(obs).squeeze(-1)
+
+    def evaluate(self, obs, act):
+        d = self.dist(obs)
+        return d.log_prob(act).sum(-1), d.entropy().sum(-1), self.v(obs).squeeze(-1)
+
+
+def gae(rew, val, done, last_val, gamma: float, lam: float):
+    """rew/val/done: [T, N]; returns (advantages, returns) [T, N] (optimizer/ppo.py:60-86 restated for a batch)."""
+    T = rew.shape[0]
+    adv = torch.zeros_like(rew)
+    nxt, run = last_val, torch.zeros_like(last_val)
+    for t in reversed(range(T)):
+        nonterm = 1.0 - done[t]
+        delta = rew[t] + gamma * nxt * nonterm - val[t]
+        run = delta + gamma * lam * nonterm * run
+        adv[t] = run
+        nxt = val[t]
+    return adv, adv + val
+
+
+class BatchedPPO:
+    """PPO on a BatchedEpiEnv-like object: reset() -> obs [N, D]; step(a [N, A]) -> (obs, reward [N], done [N], _)."""
+
+    def __init__(self, env, obs_dim: int, act_dim: int, obs_scale, n_steps: int = 16, n_epochs: int = 4,
+                 minibatches: int = 4, gamma: float = 0.999, lam: float = 0.99, clip: float = 0.2,
+                 lr: float = 3e-4, vf_coef: float = 0.974, ent_coef: float = 5.3e-8, max_grad_norm: float = 2.0,
+                 reward_scale: float = 1e-7, device="cuda", seed: int = 10, gather=None):
+        torch.manual_seed(seed)
+        self.env, self.dev = env, torch.device(device)
+        self.ac = ActorCritic(obs_dim, act_dim).to(self.dev)
+        self.opt = torch.optim.Adam(self.ac.parameters(), lr=lr)
+        self.obs_scale = torch.as_tensor(obs_scale, dtype=torch.float32, device=self.dev)
+        self.n_steps, self.n_epochs, self.minibatches = n_steps, n_epochs, minibatches
+        self.gamma, self.lam, self.clip = gamma, lam, clip
+        self.vf_coef, self.ent_coef, self.max_grad_norm, self.reward_scale = vf_coef, ent_coef, max_grad_norm, reward_scale
+        self.gather = gather  # callable(local tensors...) -> gathered tensors on every rank, or None (single GPU)
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self._obs = None
+        self.ep_return = None
+        self.finished_returns = []
+
+    def _norm(self, obs):
+        return obs.to(torch.float32) / self.obs_scale
+
+    def _all(self, x):
+        """all-gather along the env axis (dim 0 of a [N_local, ...] tensor)"""
+        if self.world == 1:
+            return x
+        out = [torch.empty_like(x) for _ in range(self.world)]
+        dist.all_gather(out, x.contiguous())
+        return torch.cat(out, 0)
+
+    def collect(self):
+        """n_steps gym steps of every env; returns the rollout as [T, N_total, ...] tensors on every rank."""
+        if self._obs is None:
+            self._obs = self.env.reset().clone()
+            self.ep_return = torch.zeros(self._obs.shape[0], dtype=torch.float64, device=self.dev)
+        O, A, LP, V, R, D = [], [], [], [], [], []
+        for _ in range(self.n_steps):
+            o = self._norm(self._obs)
+            a, lp, v = self.ac.act(o)
+            obs, rew, done, _ = self.env.step(a.clamp(0.0, 1.0).contiguous())
+            self.ep_return += rew
+            d = done.to(torch.bool)
+            if d.any():
+                self.finished_returns += self.ep_return[d].tolist()
+                self.ep_return[d] = 0
+                self.env.reset(done)
+                obs = self.env.epi.obs
+            # one packed exchange per gym step: what the learner needs from every shard
+            rec = torch.cat([o, a, lp[:, None], v[:, None], (rew.to(torch.float32) * self.reward_scale)[:, None],
+                             d.to(torch.float32)[:, None]], 1)
+            rec = self._all(rec)
+            nd, na = o.shape[1], a.shape[1]
+            O.append(rec[:, :nd]); A.append(rec[:, nd:nd + na]); LP.append(rec[:, nd + na]); V.append(rec[:, nd + na + 1])
+            R.append(rec[:, nd + na + 2]); D.append(rec[:, nd + na + 3])
+            self._obs = obs.clone()
+        last_v = self._all(self.ac.act(self._norm(self._obs))[2])
+        return (torch.stack(O), torch.stack(A), torch.stack(LP), torch.stack(V), torch.stack(R), torch.stack(D), last_v)
+
+    def update(self, batch):
+        O, A, LP, V, R, D, last_v = batch
+        adv, ret = gae(R, V, D, last_v, self.gamma, self.lam)
+        O, A, LP, adv, ret = (x.reshape(-1, *x.shape[2:]) for x in (O, A, LP, adv, ret))
+        adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+        n = O.shape[0]
+        stats = {}
+        if self.rank == 0:
+            for _ in range(self.n_epochs):
+                perm = torch.randperm(n, device=self.dev)
+                for idx in perm.chunk(self.minibatches):
+                    lp, ent, v = self.ac.evaluate(O[idx], A[idx])
+                    ratio = (lp - LP[idx]).exp()
+                    pg = -torch.min(ratio * adv[idx], ratio.clamp(1 - self.clip, 1 + self.clip) * adv[idx]).mean()
+                    vl = ((v - ret[idx]) ** 2).mean()
+                    loss = pg + self.vf_coef * vl - self.ent_coef * ent.mean()
+                    self.opt.zero_grad(set_to_none=True)
+                    loss.backward()
+                    nn.utils.clip_grad_norm_(self.ac.parameters(), self.max_grad_norm)
+                    self.opt.step()
+            stats = {"pg_loss": float(pg.detach()), "v_loss": float(vl.detach()), "entropy": float(ent.mean().detach())}
+        if self.world > 1:  # the learner's weights go back to every shard's replica
+            flat = torch.cat([p.data.reshape(-1) for p in self.ac.parameters()])
+            dist.broadcast(flat, 0)
+            off = 0
+            for p in self.ac.parameters():
+                p.data.copy_(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+        return stats
+
+    def train(self, n_updates: int, log=None):
+        hist = []
+        for u in range(n_updates):
+            batch = self.collect()
+            st = self.update(batch)
+            mean_r = float(batch[4].sum(0).mean()) / self.reward_scale / self.n_steps
+            st.update(update=u, mean_step_reward=mean_r, episodes=len(self.finished_returns),
+                      mean_episode_return=(sum(self.finished_returns[-256:]) / max(1, len(self.finished_returns[-256:]))
+                                           if self.finished_returns else math.nan))
+            hist.append(st)
+            if log and self.rank == 0:
+                log(st)
+        return hist
