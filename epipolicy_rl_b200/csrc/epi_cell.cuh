@@ -46,8 +46,8 @@ using namespace rk;
 #define SLOT_C1(i) (spec::slot_c1[i])
 #define SLOT_C2(i) (spec::slot_c2[i])
 extern __shared__ __align__(16) char cell_smem[];
-#define COLP(arr) ((T_##arr*)(cell_smem + spec::l_##arr))
-#define ENVP(arr) ((T_##arr*)(cell_smem + (spec::e_base + spec::e_##arr) + c.ebase))
+#define COLP(arr) ((T_##arr*)(::epi::cell::cell_smem + spec::l_##arr))
+#define ENVP(arr) ((T_##arr*)(::epi::cell::cell_smem + (spec::e_base + spec::e_##arr) + c.ebase))
 #else
 #define DIM(x) (P.x)
 #define EPI_LW (P.cl.lw)

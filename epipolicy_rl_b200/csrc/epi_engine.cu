@@ -20,6 +20,7 @@
 #include "../../include/epi_b200.h"
 #include "epi_kernels.cuh"
 #include "epi_cell.cuh"
+#include "epi_cellteam.cuh"
 #include "epi_env.cuh"
 
 namespace {
@@ -46,6 +47,7 @@ struct HostTabs {
   std::vector<double> alive_coef, ig_w;
   std::vector<int> ig_c0, ig_w_off, ig_w_c2, ep_off, ep, xg_off, xg_src, ag_off, ag_src;
   std::vector<float> ep_coef, xg_coef, ag_coef;
+  std::vector<int> comp_role;
 };
 
 struct epi_engine {
@@ -478,6 +480,20 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
   for (auto& v : xg) { for (auto& pr : v) { xg_src.push_back(pr.first); xg_coef.push_back(pr.second); } xg_off.push_back((int)xg_src.size()); }
   for (auto& v : ag) { for (auto& pr : v) { ag_src.push_back(pr.first); ag_coef.push_back(pr.second); } ag_off.push_back((int)ag_src.size()); }
 
+  // roles of the cell-team kernel (epi_cellteam.cuh): R warps share one group of envs when there is enough
+  // per-cell work to split; the two compartments of a move slot stay together on role 0
+  {
+    int R = (d.E + NG + C) / 12;
+    R = R < 1 ? 1 : (R > 3 ? 3 : R);
+    if (const char* ov = getenv("EPI_ROLES")) { int v = atoi(ov); if (v >= 1 && v <= 4) R = v; }
+    if (LG > 32) R = 1;
+    P.cl.roles = R;
+    std::vector<int> comp_role(C);
+    for (int c = 0; c < C; c++) comp_role[c] = c % R;
+    for (int s = 0; s < n_slot; s++) comp_role[slots[s].first] = comp_role[slots[s].second] = 0;
+    h->tabs.comp_role = comp_role;
+    P.comp_role = h->up(comp_role);
+  }
   {
     HostTabs& T = h->tabs;
     T.alive_coef = vec(d.alive_coef, C); T.ig_w = ig_w; T.ig_c0 = ig_c0; T.ig_w_off = ig_w_off; T.ig_w_c2 = ig_w_c2;
@@ -555,7 +571,9 @@ void build_cell_layout(epi_engine* h, int W) {
   CellLayout& Y = P.cl;
   const int64_t rs = (int64_t)h->real_size();
   const int64_t C = P.C, G = P.G, F = P.F, n_lc = P.n_lc, NG = P.NG, nC = (int64_t)P.I * P.L;
+  const int roles = Y.roles > 0 ? Y.roles : 1;
   Y = CellLayout{};
+  Y.roles = roles;
   Y.epw = W / P.LG;
   Y.lw = W = Y.epw * P.LG;
   int64_t o = 0;
@@ -566,7 +584,7 @@ void build_cell_layout(epi_engine* h, int W) {
   Y.l_tdc = take(P.has_ft_ops ? 0 : rs * n_lc * F * G * G);
   Y.l_cmA = take(rs * (1 + NG) * W); Y.l_cmB = take(rs * (1 + NG) * W);
   Y.l_mvY = take(4 * (int64_t)P.n_slot * W); Y.l_mvD = take(4 * (int64_t)P.n_slot * W);
-  Y.l_ysS = take(8 * nS * W); Y.l_KS = take(8 * 7 * nS * W); Y.l_red = take(8 * W);
+  Y.l_ysS = take(8 * nS * W); Y.l_KS = take(8 * 7 * nS * W); Y.l_red = take(8 * (int64_t)W * roles);
   Y.e_base = o;
   o = 0;
   Y.e_mult_y = take(4 * (int64_t)P.n_cls); Y.e_mult_d = take(4 * (int64_t)P.n_cls);
@@ -583,6 +601,8 @@ void build_cell_layout(epi_engine* h, int W) {
   Y.warp_bytes = Y.e_base + Y.e_bytes * Y.epw;
 }
 
+
+int env_threads(int LG) { return LG >= 256 ? 256 : ((LG + 31) / 32) * 32; }
 
 // layout of the env kernel (epi_env.cuh) for CTAs of `threads` threads
 void build_env_layout(epi_engine* h, int threads, int64_t smem_max) {
@@ -639,7 +659,7 @@ std::string gen_spec(const epi_engine* h) {
     << ", LG = " << P.LG << ", CLG = " << P.CLG << ", nnz = " << P.nnz << ", n_lc = " << P.n_lc << ", E = " << P.E
     << ", NG = " << P.NG << ", NSRC = " << P.NSRC << ", n_acc = " << P.n_acc << ", n_slot = " << P.n_slot
     << ", has_ft_ops = " << P.has_ft_ops << ", has_src64 = " << P.has_src64
-    << ", dense_mob = " << (P.mob_dense_csc ? 1 : 0) << ";\n";
+    << ", dense_mob = " << (P.mob_dense_csc ? 1 : 0) << ", R = " << (P.cl.roles > 0 ? P.cl.roles : 1) << ";\n";
   o << "constexpr int big = " << (P.LG > 32 ? 1 : 0) << ";  // 1: env kernel (epi_env.cuh), 0: cell kernel (epi_cell.cuh)\n";
   if (P.LG <= 32) {
     const CellLayout& Y = P.cl;  // built for 32-lane warps
@@ -660,7 +680,7 @@ std::string gen_spec(const epi_engine* h) {
     o << "};\n";
   };
   std::vector<int> s1(P.slot_c1, P.slot_c1 + P.n_slot), s2(P.slot_c2, P.slot_c2 + P.n_slot);
-  arr("slot_c1", s1); arr("slot_c2", s2); arr("ig_c0", T.ig_c0);
+  arr("slot_c1", s1); arr("slot_c2", s2); arr("ig_c0", T.ig_c0); arr("comp_role", T.comp_role);
   // phase A
   o << "__device__ __forceinline__ void phaseA(const real* y, real& alive, real* xw) {\n  alive = 0;\n";
   for (int c = 0; c < P.C; c++)
@@ -718,6 +738,92 @@ std::string gen_spec(const epi_engine* h) {
     o << "\n";
   }
   o << "}\n";
+
+  // ---- per-role pieces of the cell-team kernel (epi_cellteam.cuh); columns are strided by LW
+  if (P.LG <= 32) {
+    const int R = P.cl.roles > 0 ? P.cl.roles : 1;
+    o << "__device__ __forceinline__ real phaseA_q(int q, const real* ys) {\n  real x = 0;\n  switch (q) {\n  case 0:\n";
+    for (int c = 0; c < P.C; c++)
+      if (T.alive_coef[c] != 0.0) o << "    x += ys[" << c << " * LW] * " << hexd(T.alive_coef[c]) << ";\n";
+    o << "    break;\n";
+    for (int k = 0; k < P.NG; k++) {
+      o << "  case " << k + 1 << ":\n";
+      for (int q = T.ig_w_off[k]; q < T.ig_w_off[k + 1]; q++) o << "    x += " << hexd(T.ig_w[q]) << " * ys[" << T.ig_w_c2[q] << " * LW];\n";
+      o << "    break;\n";
+    }
+    o << "  }\n  return x;\n}\n";
+    auto valr = [&](int fac) {
+      int kind = fac >> 24, idx = fac & 0xffffff;
+      std::ostringstream v;
+      if (kind == 0) v << "(real)mp[" << idx * P.G << "]";
+      else if (kind == 1) v << "alive";
+      else v << "y" << idx;
+      return v.str();
+    };
+    o << "__device__ __forceinline__ void flows_role(int role, const real* ys, real alive, const float* mp, real* fl) {\n  switch (role) {\n";
+    for (int r = 0; r < R; r++) {
+      o << "  case " << r << ": {\n";
+      std::vector<char> used(P.C, 0);
+      for (int e = r; e < P.E; e += R)
+        for (int k = T.ep_off[e]; k < T.ep_off[e + 1]; k++) {
+          // factor words are the only entries >= 1<<24 (kind 1, 2) or small parameter ids; walk the program properly
+        }
+      // collect the compartments this role's edges read
+      for (int e = r; e < P.E; e += R) {
+        const int* ep = T.ep.data() + T.ep_off[e];
+        int n = *ep++;
+        for (int q = 0; q < n; q++) { int f = *ep++; if ((f >> 24) == 2) used[f & 0xffffff] = 1; }
+        int ns = *ep++;
+        for (int sidx = 0; sidx < ns; sidx++) { ep++; int nf = *ep++; for (int q = 0; q < nf; q++) { int f = *ep++; if ((f >> 24) == 2) used[f & 0xffffff] = 1; } }
+      }
+      for (int c = 0; c < P.C; c++) if (used[c]) o << "    const real y" << c << " = ys[" << c << " * LW];\n";
+      for (int e = r; e < P.E; e += R) {
+        const int* ep = T.ep.data() + T.ep_off[e];
+        int n = *ep++;
+        o << "    { real n = (real)1";
+        for (int q = 0; q < n; q++) o << " * " << valr(*ep++);
+        o << ";";
+        int ns = *ep++;
+        if (ns == 0) {
+          o << " fl[" << e << " * LW] = n; }\n";
+        } else {
+          o << " real dn = 0;";
+          for (int sidx = 0; sidx < ns; sidx++) {
+            o << " dn += " << hexf(T.ep_coef[*ep++]);
+            int nf = *ep++;
+            for (int q = 0; q < nf; q++) o << " * " << valr(*ep++);
+            o << ";";
+          }
+          o << " fl[" << e << " * LW] = dn > 0 ? n / dn : n; }\n";
+        }
+      }
+      o << "  } break;\n";
+    }
+    o << "  }\n}\n";
+    o << "__device__ __forceinline__ void dx_role(int role, const real* fl, real* Kc) {\n  switch (role) {\n";
+    for (int r = 0; r < R; r++) {
+      o << "  case " << r << ":\n";
+      for (int c = 0; c < P.C; c++) {
+        if (T.comp_role[c] != r) continue;
+        o << "    { real d = 0;";
+        for (int q = T.xg_off[c]; q < T.xg_off[c + 1]; q++) o << " d += fl[" << T.xg_src[q] << " * LW] * " << hexf(T.xg_coef[q]) << ";";
+        o << " Kc[" << c << " * LW] = d; }\n";
+      }
+      o << "    break;\n";
+    }
+    o << "  }\n}\n";
+    o << "template <int STRIDE> __device__ __forceinline__ void acc_role(int role, const real* col, real* out) {\n  switch (role) {\n";
+    for (int r = 0; r < R; r++) {
+      o << "  case " << r << ":\n";
+      for (int a = r; a < P.n_acc; a += R) {
+        o << "    out[" << a / R << "] = 0;";
+        for (int q = T.ag_off[a]; q < T.ag_off[a + 1]; q++) o << " out[" << a / R << "] += col[" << T.ag_src[q] << " * STRIDE] * " << hexf(T.ag_coef[q]) << ";";
+        o << "\n";
+      }
+      o << "    break;\n";
+    }
+    o << "  }\n}\n";
+  }
   o << "__device__ __forceinline__ void acc_rt(const real* col, size_t stride, real* out) {\n";
   for (int a = 0; a < P.n_acc; a++) {
     o << "  out[" << a << "] = 0;";
@@ -730,12 +836,14 @@ std::string gen_spec(const epi_engine* h) {
   uint64_t k = 1469598103934665603ull;
   auto mix = [&](const void* p, size_t n) { for (size_t i = 0; i < n; i++) { k ^= ((const unsigned char*)p)[i]; k *= 1099511628211ull; } };
   mix(body.data(), body.size());
-  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 7 /* generator revision */};
+  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 9 /* generator revision */};
   mix(abi, sizeof abi);
   char kb[32];
   snprintf(kb, sizeof kb, "%016llx", (unsigned long long)k);
   return std::string("// GENERATED by libepi_b200 (epi_engine.cu: gen_spec) - scenario-specialised per-cell program\n#define EPI_SPEC 1\n#define EPI_SPEC_KEY \"") +
-         kb + "\"\n#define EPI_SPEC_BIG " + (P.LG > 32 ? "1" : "0") + "\n" + body;
+         kb + "\"\n#define EPI_SPEC_BIG " + (P.LG > 32 ? "1" : "0") + "\n" +
+         "#define EPI_SPEC_ROLES " + std::to_string(P.cl.roles > 0 ? P.cl.roles : 1) + "\n" +
+         (P.LG > 32 ? std::string("#define EPI_ENV_MINB ") + (P.el.big_in_smem ? "2" : "4") + "\n" : std::string()) + body;
 }
 
 void alloc_state(epi_engine* h, DevState& S, int N) {
@@ -773,7 +881,7 @@ void choose_launch(epi_engine* h) {
       P.cl.enabled = 1;
       h->cta_mode = 2; h->cellW = W;
       P.small_in_smem = P.big_in_smem = 1;
-      h->wpb = 1; h->threads = W;  // (the emulation runs LW host threads per warp)
+      h->wpb = P.cl.roles; h->threads = W * P.cl.roles;  // (the emulation runs LW host threads per warp)
       h->smem_bytes = (size_t)P.cl.warp_bytes;
       h->grid = (h->N + P.cl.epw - 1) / P.cl.epw;
       h->scratch_bytes = 0;
@@ -786,7 +894,7 @@ void choose_launch(epi_engine* h) {
 #ifdef EPI_HOST_EMU
     int threads = P.LG < 24 ? P.LG : 24;  // host threads per emulated CTA
 #else
-    int threads = P.LG >= 256 ? 256 : ((P.LG + 31) / 32) * 32;
+    int threads = env_threads(P.LG);
 #endif
     build_env_layout(h, threads, smem_max);
     P.el.enabled = 1;
@@ -795,8 +903,11 @@ void choose_launch(epi_engine* h) {
     h->smem_bytes = (size_t)(P.el.tab_bytes + P.el.red_bytes + (P.el.comm_in_smem ? P.el.comm_bytes : 0) +
                              (P.el.big_in_smem ? P.el.big_bytes : 0));
     int ctas_per_sm = (int)((prop.sharedMemPerMultiprocessor - 1024) / (h->smem_bytes + 1024));
-    int by_regs = 65536 / (threads * 128);  // __launch_bounds__(256): ptxas settles on <= 128 registers
+    // __launch_bounds__(256, EPI_ENV_MINB): 2 CTAs/SM (<= 128 registers) when the working set is in shared
+    // memory, 4 (<= 64 registers, more loads in flight) when it streams from the global workspace
+    int by_regs = 65536 / (threads * (P.el.big_in_smem ? 128 : 64));
     if (by_regs < 1) by_regs = 1;
+    if (const char* ov = getenv("EPI_ENV_CTAS")) by_regs = atoi(ov) > 0 ? atoi(ov) : by_regs;  // tuning aid
     if (ctas_per_sm > by_regs) ctas_per_sm = by_regs;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     int cap = sms * ctas_per_sm;
@@ -863,13 +974,23 @@ void launch_cell(epi_engine* h, const DevState& S, const epi::StepArgs& a, cudaS
   const int grid = (a.N + epw - 1) / epw;
 #ifdef EPI_HOST_EMU
   (void)st;
-  emu::run_warps(grid, h->cellW, (size_t)h->plan.cl.warp_bytes, [&](char* smem, int lane, int group) {
-    epi::cell::step_warp<real>(h->plan, S, a, smem, lane, group);
-  });
+  if (h->plan.cl.roles > 1)
+    emu::run_warps(grid, h->cellW * h->plan.cl.roles, (size_t)h->plan.cl.warp_bytes, [&](char* smem, int tid, int group) {
+      epi::cteam::step_cta<real>(h->plan, S, a, smem, tid, group);
+    });
+  else
+    emu::run_warps(grid, h->cellW, (size_t)h->plan.cl.warp_bytes, [&](char* smem, int lane, int group) {
+      epi::cell::step_warp<real>(h->plan, S, a, smem, lane, group);
+    });
 #else
   if (h->spec_launch) {
     int rc = h->spec_launch(&h->plan, &S, &a, grid, h->threads, h->smem_bytes, (void*)st);
     if (rc != 0) throw CudaFail{std::string("specialised cell kernel launch: ") + cudaGetErrorString((cudaError_t)rc)};
+  } else if (h->plan.cl.roles > 1) {
+    auto kern = epi::cteam::cell_team_kernel<real>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    kern<<<grid, h->threads, h->smem_bytes, st>>>(h->plan, S, a);
+    CK(cudaGetLastError());
   } else {
     auto kern = epi::cell::cell_kernel<real>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
@@ -1232,6 +1353,7 @@ int epi_spec_source_desc(const EpiDesc* desc, int precision, char* buf, size_t c
     h->d = *desc;
     build_plan(h, *desc);
     if (h->plan.LG <= 32) build_cell_layout(h, 32);
+    else build_env_layout(h, env_threads(h->plan.LG), 232448 - 1024);  // B200: 227 KB opt-in shared memory per CTA
     std::string src = gen_spec(h);
     if (need) *need = src.size() + 1;
     if (buf && cap) {

@@ -874,8 +874,11 @@ __device__ __forceinline__ Bx bind(const DevPlan& P, const StepArgs& a, char* sm
 }
 
 #ifndef EPI_HOST_EMU
+#ifndef EPI_ENV_MINB
+#define EPI_ENV_MINB 2  // CTAs per SM the register allocation aims at (256 threads -> <= 128 registers)
+#endif
 template <class real>
-__global__ void __launch_bounds__(256) env_kernel(const DevPlan P, const DevState S, const StepArgs a) {
+__global__ void __launch_bounds__(256, EPI_ENV_MINB) env_kernel(const DevPlan P, const DevState S, const StepArgs a) {
   extern __shared__ __align__(16) char env_smem[];
   Bx b = bind(P, a, env_smem, threadIdx.x, blockDim.x, blockIdx.x);
   step_cta<real>(P, S, a, b, blockIdx.x, gridDim.x);

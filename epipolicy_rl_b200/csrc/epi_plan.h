@@ -24,6 +24,7 @@
 struct CellLayout {
   int enabled, epw;  // envs per warp = 32 / (L*G)
   int lw;            // lanes that carry a cell = epw * L*G = width of a per-lane column
+  int roles;         // cooperating warps per CTA (epi_cellteam.cuh); 1 = the plain cell kernel
   int64_t l_X, l_ys, l_K, l_fl, l_FBE, l_accY, l_tdc, l_cmA, l_cmB, l_mvY, l_mvD, l_ysS, l_KS, l_red;
   int64_t e_base, e_bytes;
   int64_t e_mult_y, e_mult_d, e_cpv, e_act, e_expr, e_sel, e_mpy, e_mpg, e_mpt0, e_mpFy, e_mpFg, e_coefS, e_Tnum,
@@ -113,6 +114,7 @@ struct DevPlan {
   const int *ig_c0, *ig_p0, *ig_np_off, *ig_np, *ig_dp_off, *ig_dp, *ig_w_off, *ig_w_c2;
   const double* ig_w;
   int n_igp;                            // distinct parameters used by infectious groups
+  const int* comp_role;                 // [C] role owning a compartment in the cell-team kernel
   const int *igp, *ig_p0i, *ig_npi, *ig_dpi; // [n_igp] parameter ids; ig_p0 / ig_np / ig_dp as indices into igp
   // ---- gather lists
   const int *xg_off, *xg_src; const float* xg_coef;    // [C+1]

@@ -6,6 +6,9 @@
 #if EPI_SPEC_BIG
 #include "epi_env.cuh"
 #define EPI_SPEC_KERNEL epi::env::env_kernel<epi::spec::real>
+#elif EPI_SPEC_ROLES > 1
+#include "epi_cellteam.cuh"
+#define EPI_SPEC_KERNEL epi::cteam::cell_team_kernel<epi::spec::real>
 #else
 #include "epi_cell.cuh"
 #define EPI_SPEC_KERNEL epi::cell::cell_kernel<epi::spec::real>

@@ -42,16 +42,22 @@ def source(desc, precision: int, L=None) -> tuple[str, str]:
 _SRC_HASH = None
 
 
+def _extra_flags():
+    """tuning aids forwarded to the specialised build (part of the cache key)"""
+    mb = os.environ.get("EPI_ENV_MINB")
+    return [f"-DEPI_ENV_MINB={int(mb)}"] if mb else []
+
+
 def _src_hash() -> str:
     """hash of the kernel sources a specialised build compiles: a stale cache entry is never reused"""
     global _SRC_HASH
     if _SRC_HASH is None:
         import hashlib
         h = hashlib.sha1()
-        for f in ("epi_cell.cuh", "epi_env.cuh", "epi_rk.cuh", "epi_kernels.cuh", "epi_plan.h", "epi_spec_main.cu"):
+        for f in ("epi_cell.cuh", "epi_cellteam.cuh", "epi_env.cuh", "epi_rk.cuh", "epi_kernels.cuh", "epi_plan.h", "epi_spec_main.cu"):
             with open(os.path.join(CSRC, f), "rb") as fh:
                 h.update(fh.read())
-        h.update(" ".join(NVCC_FLAGS).encode())
+        h.update(" ".join(NVCC_FLAGS + _extra_flags()).encode())
         _SRC_HASH = h.hexdigest()[:10]
     return _SRC_HASH
 
@@ -79,7 +85,7 @@ def compile_spec(text: str, key: str) -> str | None:
         f.write(text)
     os.replace(hdr + f".{os.getpid()}", hdr)
     tmp = f"{out}.{os.getpid()}.tmp"
-    subprocess.check_call([nvcc, *NVCC_FLAGS, f'-DEPI_SPEC_HEADER="{hdr}"', "-I", CSRC, "-o", tmp,
+    subprocess.check_call([nvcc, *NVCC_FLAGS, *_extra_flags(), f'-DEPI_SPEC_HEADER="{hdr}"', "-I", CSRC, "-o", tmp,
                            os.path.join(CSRC, "epi_spec_main.cu")])
     os.replace(tmp, out)
     return out

@@ -56,6 +56,7 @@ inline int __any_sync(unsigned, int pred) {
   pthread_barrier_wait(emu::warp_barrier);
   return r;
 }
+inline int __syncthreads_or(int pred) { return __any_sync(0xffffffffu, pred); }
 namespace emu {
 // run `n_warps` warps one after the other, each as `width` lock-stepped host threads
 inline void run_warps(int n_warps, int width, size_t smem_bytes, const std::function<void(char*, int, int)>& body) {
