@@ -192,7 +192,7 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Tx& c, bool on, bool
         if (den <= (real)1e-15) den = 1;
         real num = 0;
         for (int u = 0; u < G; u++) num += LO(cmB, 1 + k, row + u) * (real)EV(Tnum, tb + u);
-        real foi = sizeof(real) == 8 ? num / den : num * ((real)1 / den);
+        real foi = fdiv(num, den);
         sk += EV(coefS, ((k * n_lc + c.lc) * F + v) * G + c.u) * foi;
       }
       LA(cmA, 1 + k) = sk;  // cmA[1..] is free again: phase B has been read out
@@ -241,7 +241,7 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Tx& c, bool on, bool
         for (int q = 0; q < nf; q++) sv *= val(__ldg(ep++));
         denom += sv;
       }
-      LA(fl, e) = denom > 0 ? numer / denom : numer;
+      LA(fl, e) = denom > 0 ? fdiv(numer, denom) : numer;
     }
 #endif
   }
@@ -530,7 +530,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Tx& c, bool on,
         for (int k = 0; k < C; k++)
           if (COMP_ROLE(k) == c.role) {
             real yv = (real)LA(X, k), sc = atolr + fabs(yv) * rtolr;
-            real a = yv / sc, b = LA(K, k) / sc;
+            real a = fdiv(yv, sc), b = fdiv(LA(K, k), sc);
             a0 += a * a; a1 += b * b;
           }
         {
@@ -539,7 +539,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Tx& c, bool on,
           for (int a_ = 0; a_ < n_acc; a_++)
             if (a_ % R == c.role) {
               real yv = LA(accY, a_), sc = atolr + fabs(yv) * rtolr;
-              real a = yv / sc, b = TACC_AT(g0, a_, COL_fl) / sc;
+              real a = fdiv(yv, sc), b = fdiv(TACC_AT(g0, a_, COL_fl), sc);
               a0 += a * a; a1 += b * b;
             }
         }
@@ -568,7 +568,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Tx& c, bool on,
 #pragma unroll
         for (int k = 0; k < C; k++)
           if (COMP_ROLE(k) == c.role) {
-            real sc = atolr + fabs((real)LA(X, k)) * rtolr, a = (LA(K, C + k) - LA(K, k)) / sc;
+            real sc = atolr + fabs((real)LA(X, k)) * rtolr, a = fdiv(LA(K, C + k) - LA(K, k), sc);
             a2 += a * a;
           }
         {
@@ -578,7 +578,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Tx& c, bool on,
           for (int a_ = 0; a_ < n_acc; a_++)
             if (a_ % R == c.role) {
               real sc = atolr + fabs(LA(accY, a_)) * rtolr;
-              real a = (TACC_AT(g1, a_, COL_fl) - TACC_AT(g0, a_, COL_FE)) / sc;
+              real a = fdiv(TACC_AT(g1, a_, COL_fl) - TACC_AT(g0, a_, COL_FE), sc);
               a2 += a * a;
             }
         }
@@ -599,7 +599,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Tx& c, bool on,
             LA(FBE, i) = p;
           }
       d2 = sqrt(d2 * inv_n) / h0;
-      double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / fmax(d1, d2), 0.2);
+      double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : ctrl_pow(real(0), 0.01 / fmax(d1, d2), 0.2);
       h_abs = fmin(fmin(100 * h0, h1), 1.0);
       nfev++;
       phase = __syncthreads_or(run) ? 2 : -1;
@@ -618,7 +618,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Tx& c, bool on,
             real e = 0;
 #pragma unroll
             for (int j = 0; j < 7; j++) e += LA(K, j * C + k) * rkE(real(0), j);
-            real a = e * (real)h / sc;
+            real a = fdiv(e * (real)h, sc);
             ae += a * a;
           }
         {
@@ -628,7 +628,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Tx& c, bool on,
           for (int a_ = 0; a_ < n_acc; a_++)
             if (a_ % R == c.role) {
               real yv = LA(accY, a_), yn = yv + (real)h * TACC_AT(gB, a_, COL_FB);
-              real sc = atolr + fmax(fabs(yv), fabs(yn)) * rtolr, a = TACC_AT(gE, a_, COL_FE) * (real)h / sc;
+              real sc = atolr + fmax(fabs(yv), fabs(yn)) * rtolr, a = fdiv(TACC_AT(gE, a_, COL_FE) * (real)h, sc);
               ae += a * a;
             }
         }
@@ -657,12 +657,12 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Tx& c, bool on,
         if (dbg && c.tl == 0 && n_att < 64) { dbg[2 * n_att] = h; dbg[2 * n_att + 1] = err; }
         n_att++;
         if (err < 1) {
-          double factor = err == 0 ? 10.0 : fmin(10.0, 0.9 * pow(err, -0.2));
+          double factor = err == 0 ? 10.0 : fmin(10.0, 0.9 * ctrl_pow(real(0), err, -0.2));
           if (rejected) factor = fmin(1.0, factor);
           h_abs *= factor;
           accepted = true;
         } else {
-          h_abs *= fmax(0.2, 0.9 * pow(err, -0.2));
+          h_abs *= fmax(0.2, 0.9 * ctrl_pow(real(0), err, -0.2));
           rejected = true;
           nrej++;
         }

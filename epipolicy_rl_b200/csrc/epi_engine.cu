@@ -483,8 +483,10 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
   // roles of the cell-team kernel (epi_cellteam.cuh): R warps share one group of envs when there is enough
   // per-cell work to split; the two compartments of a move slot stay together on role 0
   {
-    int R = (d.E + NG + C) / 12;
-    R = R < 1 ? 1 : (R > 3 ? 3 : R);
+    // Measured on B200 (COVID_C x 4096, fp32): R = 2/3/4 -> 2.28/2.12/2.11 ms per gym step against 1.24 ms for
+    // R = 1: the barrier-separated role phases have too little ILP each and the per-warp control overhead does
+    // not divide by R. The role split therefore stays an experiment behind EPI_ROLES; default is the cell kernel.
+    int R = 1;
     if (const char* ov = getenv("EPI_ROLES")) { int v = atoi(ov); if (v >= 1 && v <= 4) R = v; }
     if (LG > 32) R = 1;
     P.cl.roles = R;
@@ -653,7 +655,7 @@ std::string gen_spec(const epi_engine* h) {
   const DevPlan& P = h->plan;
   const HostTabs& T = h->tabs;
   std::ostringstream o;
-  o << "namespace epi { namespace spec {\n";
+  o << "#include \"epi_fdiv.cuh\"\nnamespace epi { namespace spec {\n";
   o << "typedef " << (h->precision == EPI_FP64 ? "double" : "float") << " real;\n";
   o << "constexpr int C = " << P.C << ", L = " << P.L << ", G = " << P.G << ", F = " << P.F << ", P = " << P.P << ", I = " << P.I
     << ", LG = " << P.LG << ", CLG = " << P.CLG << ", nnz = " << P.nnz << ", n_lc = " << P.n_lc << ", E = " << P.E
@@ -718,7 +720,7 @@ std::string gen_spec(const epi_engine* h) {
         for (int q = 0; q < nf; q++) o << " * " << val(*ep++);
         o << ";";
       }
-      o << " f[" << e << "] = dn > 0 ? n / dn : n; }\n";
+      o << " f[" << e << "] = dn > 0 ? fdiv(n, dn) : n; }\n";
     }
   }
   o << "}\n";
@@ -740,8 +742,8 @@ std::string gen_spec(const epi_engine* h) {
   o << "}\n";
 
   // ---- per-role pieces of the cell-team kernel (epi_cellteam.cuh); columns are strided by LW
-  if (P.LG <= 32) {
-    const int R = P.cl.roles > 0 ? P.cl.roles : 1;
+  if (P.LG <= 32 && P.cl.roles > 1) {
+    const int R = P.cl.roles;
     o << "__device__ __forceinline__ real phaseA_q(int q, const real* ys) {\n  real x = 0;\n  switch (q) {\n  case 0:\n";
     for (int c = 0; c < P.C; c++)
       if (T.alive_coef[c] != 0.0) o << "    x += ys[" << c << " * LW] * " << hexd(T.alive_coef[c]) << ";\n";
@@ -794,7 +796,7 @@ std::string gen_spec(const epi_engine* h) {
             for (int q = 0; q < nf; q++) o << " * " << valr(*ep++);
             o << ";";
           }
-          o << " fl[" << e << " * LW] = dn > 0 ? n / dn : n; }\n";
+          o << " fl[" << e << " * LW] = dn > 0 ? fdiv(n, dn) : n; }\n";
         }
       }
       o << "  } break;\n";
@@ -836,7 +838,7 @@ std::string gen_spec(const epi_engine* h) {
   uint64_t k = 1469598103934665603ull;
   auto mix = [&](const void* p, size_t n) { for (size_t i = 0; i < n; i++) { k ^= ((const unsigned char*)p)[i]; k *= 1099511628211ull; } };
   mix(body.data(), body.size());
-  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 9 /* generator revision */};
+  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 10 /* generator revision */};
   mix(abi, sizeof abi);
   char kb[32];
   snprintf(kb, sizeof kb, "%016llx", (unsigned long long)k);

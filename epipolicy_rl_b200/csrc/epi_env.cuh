@@ -224,14 +224,13 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Bx& b, bool dyn, dou
           for (int u = 0; u < G; u++) den += CB(0, u) * (real)__ldg(P.Tden_constT + tb + u * G);
         }
         if (den <= (real)1e-15) den = 1;
-        real inv = (real)1 / den;
-#pragma unroll
+  #pragma unroll
         for (int k = 0; k < EPI_MAX_NG; k++)
           if (k < NG) {
             real num = 0;
 #pragma unroll
             for (int u = 0; u < G; u++) num += CB(1 + k, u) * (real)ET(Tnum, tb + u * G);
-            real foi = sizeof(real) == 8 ? num / den : num * inv;
+            real foi = fdiv(num, den);
             sk[k] += ET(coefS, ((k * n_lc + lc) * F + v) * G + u0) * foi;
           }
       }
@@ -334,7 +333,7 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Bx& b, bool dyn, dou
         for (int q = 0; q < nf; q++) sv *= val(__ldg(ep++));
         denom += sv;
       }
-      BA(fl, e) = denom > 0 ? numer / denom : numer;
+      BA(fl, e) = denom > 0 ? fdiv(numer, denom) : numer;
     }
     for (int k = 0; k < C; k++) {
       real d = 0;
@@ -605,7 +604,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
 #pragma unroll
         for (int k = 0; k < C; k++) {
           real yv = (real)BA(X, k), sc = atolr + fabs(yv) * rtolr;
-          real a = yv / sc, bq = BA(K, k) / sc;
+          real a = fdiv(yv, sc), bq = fdiv(BA(K, k), sc);
           a0 += a * a; a1 += bq * bq;
         }
         {
@@ -613,7 +612,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
 #pragma unroll
           for (int a_ = 0; a_ < n_acc; a_++) {
             real yv = BA(accY, a_), sc = atolr + fabs(yv) * rtolr;
-            real a = yv / sc, bq = EACC_AT(g0, a_, ECOL_fl) / sc;
+            real a = fdiv(yv, sc), bq = fdiv(EACC_AT(g0, a_, ECOL_fl), sc);
             a0 += a * a; a1 += bq * bq;
           }
         }
@@ -637,7 +636,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
         real a2 = 0;
 #pragma unroll
         for (int k = 0; k < C; k++) {
-          real sc = atolr + fabs((real)BA(X, k)) * rtolr, a = (BA(K, C + k) - BA(K, k)) / sc;
+          real sc = atolr + fabs((real)BA(X, k)) * rtolr, a = fdiv(BA(K, C + k) - BA(K, k), sc);
           a2 += a * a;
         }
         {
@@ -646,7 +645,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
 #pragma unroll
           for (int a_ = 0; a_ < n_acc; a_++) {
             real sc = atolr + fabs(BA(accY, a_)) * rtolr;
-            real a = (EACC_AT(g1, a_, ECOL_fl) - EACC_AT(g0, a_, ECOL_FE)) / sc;
+            real a = fdiv(EACC_AT(g1, a_, ECOL_fl) - EACC_AT(g0, a_, ECOL_FE), sc);
             a2 += a * a;
           }
         }
@@ -664,7 +663,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
         s2 += a * a;
       }
       double d2 = sqrt(block_sum(b, s2) * inv_n) / h0;
-      double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / fmax(d1, d2), 0.2);
+      double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : ctrl_pow(real(0), 0.01 / fmax(d1, d2), 0.2);
       h_abs = fmin(fmin(100 * h0, h1), 1.0);
       nfev++;
       phase = 2;
@@ -682,7 +681,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
           real e = 0;
 #pragma unroll
           for (int j = 0; j < 7; j++) e += BA(K, j * C + k) * rkE(real(0), j);
-          real a = e * (real)h / sc;
+          real a = fdiv(e * (real)h, sc);
           ae += a * a;
         }
         {
@@ -691,7 +690,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
 #pragma unroll
           for (int a_ = 0; a_ < n_acc; a_++) {
             real yv = BA(accY, a_), yn = yv + (real)h * EACC_AT(gB, a_, ECOL_FB);
-            real sc = atolr + fmax(fabs(yv), fabs(yn)) * rtolr, a = EACC_AT(gE, a_, ECOL_FE) * (real)h / sc;
+            real sc = atolr + fmax(fabs(yv), fabs(yn)) * rtolr, a = fdiv(EACC_AT(gE, a_, ECOL_FE) * (real)h, sc);
             ae += a * a;
           }
         }
@@ -717,12 +716,12 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
       n_att++;
       bool accepted = false;
       if (err < 1) {
-        double factor = err == 0 ? 10.0 : fmin(10.0, 0.9 * pow(err, -0.2));
+        double factor = err == 0 ? 10.0 : fmin(10.0, 0.9 * ctrl_pow(real(0), err, -0.2));
         if (rejected) factor = fmin(1.0, factor);
         h_abs *= factor;
         accepted = true;
       } else {
-        h_abs *= fmax(0.2, 0.9 * pow(err, -0.2));
+        h_abs *= fmax(0.2, 0.9 * ctrl_pow(real(0), err, -0.2));
         rejected = true;
         nrej++;
       }

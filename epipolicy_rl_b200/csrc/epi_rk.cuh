@@ -2,6 +2,7 @@
 // Dormand-Prince tableau, element types of the working-set columns / per-env tables, a 2-vector.
 #pragma once
 #include "epi_kernels.cuh"
+#include "epi_fdiv.cuh"
 
 namespace epi {
 namespace rk {
