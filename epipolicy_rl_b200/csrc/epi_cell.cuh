@@ -450,13 +450,13 @@ __device__ __forceinline__ int prologue(const DevPlan& P, const Cx& c, bool on, 
   for (int s = 0; s < P.n_sel; s++) {
     double part = 0;
     if (on && P.sel_l[s * L + c.j] && P.sel_g[s * G + c.u]) {
-      int mode = P.sel_mode[s];
-      for (int k = 0; k < C; k++)
-        if (P.sel_c[s * C + k]) {
-          if (mode == 0) part += LA(X, k);
-          else if (mode == 1) part += P.X0[k * LG + c.cell];
-          else part += LA(X, k) - Xprev_g[P.chg_slot_of_comp[k] * LG + c.cell];
-        }
+      const int mode = __ldg(P.sel_mode + s);
+      for (int q = __ldg(P.selc_off + s); q < __ldg(P.selc_off + s + 1); q++) {  // the select's compartments
+        const int k = __ldg(P.selc + q);
+        if (mode == 0) part += LA(X, k);
+        else if (mode == 1) part += P.X0[k * LG + c.cell];
+        else part += LA(X, k) - Xprev_g[P.chg_slot_of_comp[k] * LG + c.cell];
+      }
     }
     double tot;
     TEAM_SUM(tot, part, on);
@@ -471,9 +471,7 @@ __device__ __forceinline__ int prologue(const DevPlan& P, const Cx& c, bool on, 
     }
     // 2. expressions
     for (int e = c.cell; e < P.n_expr; e += LG) {
-      int itv = P.expr_itv[e];
-      bool live = EV(act, itv) && P.expr_prog[e] == (variant ? P.prog_init[itv] : P.prog_step[itv]);
-      EV(expr, e) = live ? eval_expr(P, e, &EV(cpv, 0), &EV(sel, 0)) : 0.0;
+      EV(expr, e) = EV(elive, e) ? eval_expr(P, e, &EV(cpv, 0), &EV(sel, 0)) : 0.0;
     }
   }
   __syncwarp();
@@ -483,7 +481,7 @@ __device__ __forceinline__ int prologue(const DevPlan& P, const Cx& c, bool on, 
       float m = 1.0f;
       for (int q = P.cls_off[k]; q < P.cls_off[k + 1]; q++) {
         int o = P.cls_op[q];
-        if (op_live(P, &EV(act, 0), variant, o)) m = __fmul_rn(m, (float)EV(expr, P.op_expr[o]));
+        if (EV(live, o)) m = __fmul_rn(m, (float)EV(expr, P.op_expr[o]));
       }
       EV(mult_d, k) = m;
     }
@@ -559,7 +557,7 @@ __device__ __forceinline__ int prologue(const DevPlan& P, const Cx& c, bool on, 
   }
   for (int mo = 0; mo < P.n_mv_op; mo++) {
     int o = P.mv_op[mo];
-    bool live = on && op_live(P, &EV(act, 0), variant, o);
+    bool live = on && EV(live, o);
     int nc1 = P.mv_c1_off[mo + 1] - P.mv_c1_off[mo], nc2 = P.mv_c2_off[mo + 1] - P.mv_c2_off[mo];
     const int* c1s = P.mv_c1 + P.mv_c1_off[mo];
     const int* c2s = P.mv_c2 + P.mv_c2_off[mo];
@@ -592,12 +590,10 @@ __device__ __forceinline__ int prologue(const DevPlan& P, const Cx& c, bool on, 
   if (on) {
     // 6. cost rates of today (nb_add, executor.py:236-243)
     for (int it = c.cell; it < P.I * L; it += LG) {
-      int i = it / L, l = it % L;
       double cr = 0;
-      for (int ao = 0; ao < P.n_add_op; ao++) {
-        int o = P.add_op[ao];
-        if (P.add_i[ao * P.I + i] && P.add_l[ao * L + l] && op_live(P, &EV(act, 0), variant, o))
-          cr += EV(expr, P.op_expr[o]) / (double)P.add_parts[ao];
+      for (int q = __ldg(P.cr_off + it); q < __ldg(P.cr_off + it + 1); q++) {  // the ADD ops covering (i, l), in op order
+        const int ao = __ldg(P.cr_ops + q), o = __ldg(P.add_op + ao);
+        if (EV(live, o)) cr += EV(expr, __ldg(P.op_expr + o)) / (double)__ldg(P.add_parts + ao);
       }
       EV(crD, it) = cr;
     }
@@ -923,6 +919,16 @@ __device__ __forceinline__ void step_warp(const DevPlan& P, const DevState& S, c
       EV(act, i) = a.active ? a.active[e * P.I + i] : (a.init_only ? P.init_active[i] : 1);
   }
   int t_day = on0 ? meta[0] : 0, ex_y = on0 ? meta[1] : 0;
+  __syncwarp();
+  if (on0) {
+    // which ops / expressions are live for this launch: the intervention is active and the op belongs to the
+    // program variant in use (fixed over the launch's days)
+    for (int o = c.cell; o < P.n_op; o += LG) EV(live, o) = (uint8_t)op_live(P, &EV(act, 0), a.variant, o);
+    for (int x = c.cell; x < P.n_expr; x += LG) {
+      int itv = P.expr_itv[x];
+      EV(elive, x) = (uint8_t)(EV(act, itv) && P.expr_prog[x] == (a.variant ? P.prog_init[itv] : P.prog_step[itv]));
+    }
+  }
   __syncwarp();
 
   double reward = 0;

@@ -12,6 +12,7 @@
 
 #include <dlfcn.h>
 
+#include <functional>
 #include <map>
 #include <sstream>
 #include <string>
@@ -365,6 +366,17 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
     add_l.insert(add_l.end(), ml.begin(), ml.end());
   }
   P.n_add_op = (int)add_op.size();
+  // per cost cell (i, l): the ADD ops that cover it; per select: its compartments
+  std::vector<int> cr_off{0}, cr_ops, selc_off{0}, selc;
+  for (int i = 0; i < I; i++) for (int l = 0; l < L; l++) {
+    for (size_t ao = 0; ao < add_op.size(); ao++)
+      if (add_i[ao * I + i] && add_l[ao * L + l]) cr_ops.push_back((int)ao);
+    cr_off.push_back((int)cr_ops.size());
+  }
+  for (int s = 0; s < d.NSEL; s++) {
+    for (int c = 0; c < C; c++) if (sel_c[(size_t)s * C + c]) selc.push_back(c);
+    selc_off.push_back((int)selc.size());
+  }
 
   // ---- control-parameter expansion (epipolicy_environment.py:24-31,:40-47)
   std::vector<int> cp_src(d.NCP, -1);
@@ -557,6 +569,7 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
   P.sel_c = h->up(sel_c); P.sel_l = h->up(sel_l); P.sel_g = h->up(sel_g); P.sel_mode = h->up(sel_mode); P.chg_slot_of_comp = h->up(chg_slot);
   P.mv_op = h->up(mv_op); P.mv_g = h->up(mv_g); P.mv_l1 = h->up(mv_l1); P.mv_c1_off = h->up(mv_c1_off); P.mv_c1 = h->up(mv_c1);
   P.mv_c2_off = h->up(mv_c2_off); P.mv_c2 = h->up(mv_c2); P.slot_of_pair = h->up(slot_of_pair); P.slot_cover = h->up(slot_cover);
+  P.cr_off = h->up(cr_off); P.cr_ops = h->up(cr_ops); P.selc_off = h->up(selc_off); P.selc = h->up(selc);
   P.add_op = h->up(add_op); P.add_i = h->up(add_i); P.add_l = h->up(add_l); P.add_parts = h->up(add_parts);
   P.cp_src = h->up(cp_src); P.cp_fixed = h->up(cp_fixed); P.init_cpv = h->up(vec(d.init_cpv, d.NCP)); P.init_active = h->up(init_active);
   P.ep_off = h->up(ep_off); P.ep = h->up(ep); P.ep_coef = h->up(vec(d.sum_coef, d.NS));
@@ -591,6 +604,7 @@ void build_cell_layout(epi_engine* h, int W) {
   o = 0;
   Y.e_mult_y = take(4 * (int64_t)P.n_cls); Y.e_mult_d = take(4 * (int64_t)P.n_cls);
   Y.e_cpv = take(4 * (int64_t)P.NCP); Y.e_act = take(P.I);
+  Y.e_live = take(P.n_op); Y.e_elive = take(P.n_expr);
   Y.e_expr = take(8 * (int64_t)P.n_expr); Y.e_sel = take(8 * (int64_t)P.n_sel);
   Y.e_mpy = take(4 * n_lc * P.P * G); Y.e_mpg = take(4 * n_lc * P.P * G); Y.e_mpt0 = take(4 * n_lc * P.P * G);
   Y.e_mpFy = take(4 * (int64_t)P.n_igp * n_lc * F * G); Y.e_mpFg = take(4 * (int64_t)P.n_igp * n_lc * F * G);
@@ -669,7 +683,7 @@ std::string gen_spec(const epi_engine* h) {
       << ", l_accY = " << Y.l_accY << ", l_tdc = " << Y.l_tdc << ", LW = " << Y.lw << ", l_cmA = " << Y.l_cmA << ", l_cmB = " << Y.l_cmB << ", l_mvY = " << Y.l_mvY << ", l_mvD = " << Y.l_mvD
       << ", l_ysS = " << Y.l_ysS << ", l_KS = " << Y.l_KS << ", l_red = " << Y.l_red << ";\n";
     o << "constexpr int e_base = " << Y.e_base << ", e_bytes = " << Y.e_bytes << ", e_mult_y = " << Y.e_mult_y << ", e_mult_d = " << Y.e_mult_d
-      << ", e_cpv = " << Y.e_cpv << ", e_act = " << Y.e_act << ", e_expr = " << Y.e_expr << ", e_sel = " << Y.e_sel << ", e_mpy = " << Y.e_mpy
+      << ", e_cpv = " << Y.e_cpv << ", e_act = " << Y.e_act << ", e_live = " << Y.e_live << ", e_elive = " << Y.e_elive << ", e_expr = " << Y.e_expr << ", e_sel = " << Y.e_sel << ", e_mpy = " << Y.e_mpy
       << ", e_mpg = " << Y.e_mpg << ", e_mpt0 = " << Y.e_mpt0 << ", e_mpFy = " << Y.e_mpFy << ", e_mpFg = " << Y.e_mpFg
       << ", e_coefS = " << Y.e_coefS << ", e_Tnum = " << Y.e_Tnum << ", e_Tden = " << Y.e_Tden << ", e_fi_y = " << Y.e_fi_y
       << ", e_fi_gap = " << Y.e_fi_gap << ", e_ft_y = " << Y.e_ft_y << ", e_ft_gap = " << Y.e_ft_gap << ", e_cost = " << Y.e_cost
@@ -693,6 +707,38 @@ std::string gen_spec(const epi_engine* h) {
       o << "  xw[" << k << "] += " << hexd(T.ig_w[q]) << " * y[" << T.ig_w_c2[q] << "];\n";
   }
   o << "}\n";
+
+  // denominator of a regular edge: `dn > 0 ? n / dn : n` (compute_fraction, core_optimize.py:55-65). A denominator
+  // made of constants only is folded here (the usual case is the single summant "1").
+  auto emit_denominator = [&](std::ostringstream& out, const int*& ep, const std::function<std::string(int)>& valfn,
+                              const std::string& target) {
+    int ns = *ep++;
+    if (ns == 0) { out << " " << target << " = n; }\n"; return; }
+    bool all_const = true;
+    double csum = 0;
+    {
+      const int* q = ep;
+      for (int sidx = 0; sidx < ns; sidx++) { float cf = T.ep_coef[*q++]; int nf = *q++; if (nf) all_const = false; q += nf; csum += (double)cf; }
+    }
+    if (all_const) {
+      for (int sidx = 0; sidx < ns; sidx++) { ep++; ep++; }
+      float c = 0.0f;  // summed in f32 like `denom += sv` on real=float; exact for the single-summant case
+      { const int* q = ep - 2 * ns; for (int sidx = 0; sidx < ns; sidx++) { c += T.ep_coef[*q]; q += 2; } }
+      (void)csum;
+      if (c == 1.0f) out << " " << target << " = n; }\n";
+      else if (c > 0) out << " " << target << " = fdiv(n, " << hexf(c) << "); }\n";
+      else out << " " << target << " = n; }\n";
+      return;
+    }
+    out << " real dn = 0;";
+    for (int sidx = 0; sidx < ns; sidx++) {
+      out << " dn += " << hexf(T.ep_coef[*ep++]);
+      int nf = *ep++;
+      for (int q = 0; q < nf; q++) out << " * " << valfn(*ep++);
+      out << ";";
+    }
+    out << " " << target << " = dn > 0 ? fdiv(n, dn) : n; }\n";
+  };
   // regular edges
   o << "__device__ __forceinline__ void flows(const real* y, real alive, const float* mp, real* f) {\n";
   auto val = [&](int fac) {
@@ -709,19 +755,7 @@ std::string gen_spec(const epi_engine* h) {
     o << "  { real n = (real)1";
     for (int q = 0; q < n; q++) o << " * " << val(*ep++);
     o << ";";
-    int ns = *ep++;
-    if (ns == 0) {
-      o << " f[" << e << "] = n; }\n";
-    } else {
-      o << " real dn = 0;";
-      for (int sidx = 0; sidx < ns; sidx++) {
-        o << " dn += " << hexf(T.ep_coef[*ep++]);
-        int nf = *ep++;
-        for (int q = 0; q < nf; q++) o << " * " << val(*ep++);
-        o << ";";
-      }
-      o << " f[" << e << "] = dn > 0 ? fdiv(n, dn) : n; }\n";
-    }
+    emit_denominator(o, ep, val, "f[" + std::to_string(e) + "]");
   }
   o << "}\n";
   // scatter into dX
@@ -785,19 +819,7 @@ std::string gen_spec(const epi_engine* h) {
         o << "    { real n = (real)1";
         for (int q = 0; q < n; q++) o << " * " << valr(*ep++);
         o << ";";
-        int ns = *ep++;
-        if (ns == 0) {
-          o << " fl[" << e << " * LW] = n; }\n";
-        } else {
-          o << " real dn = 0;";
-          for (int sidx = 0; sidx < ns; sidx++) {
-            o << " dn += " << hexf(T.ep_coef[*ep++]);
-            int nf = *ep++;
-            for (int q = 0; q < nf; q++) o << " * " << valr(*ep++);
-            o << ";";
-          }
-          o << " fl[" << e << " * LW] = dn > 0 ? fdiv(n, dn) : n; }\n";
-        }
+        emit_denominator(o, ep, valr, "fl[" + std::to_string(e) + " * LW]");
       }
       o << "  } break;\n";
     }
@@ -838,7 +860,7 @@ std::string gen_spec(const epi_engine* h) {
   uint64_t k = 1469598103934665603ull;
   auto mix = [&](const void* p, size_t n) { for (size_t i = 0; i < n; i++) { k ^= ((const unsigned char*)p)[i]; k *= 1099511628211ull; } };
   mix(body.data(), body.size());
-  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 10 /* generator revision */};
+  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 12 /* generator revision */};
   mix(abi, sizeof abi);
   char kb[32];
   snprintf(kb, sizeof kb, "%016llx", (unsigned long long)k);

@@ -27,7 +27,7 @@ struct CellLayout {
   int roles;         // cooperating warps per CTA (epi_cellteam.cuh); 1 = the plain cell kernel
   int64_t l_X, l_ys, l_K, l_fl, l_FBE, l_accY, l_tdc, l_cmA, l_cmB, l_mvY, l_mvD, l_ysS, l_KS, l_red;
   int64_t e_base, e_bytes;
-  int64_t e_mult_y, e_mult_d, e_cpv, e_act, e_expr, e_sel, e_mpy, e_mpg, e_mpt0, e_mpFy, e_mpFg, e_coefS, e_Tnum,
+  int64_t e_mult_y, e_mult_d, e_cpv, e_act, e_live, e_elive, e_expr, e_sel, e_mpy, e_mpg, e_mpt0, e_mpFy, e_mpFg, e_coefS, e_Tnum,
       e_Tden, e_fi_y, e_fi_gap, e_ft_y, e_ft_gap, e_cost, e_crY, e_crD;
   int64_t warp_bytes;
 };
@@ -87,6 +87,8 @@ struct DevPlan {
   // selects: byte masks
   const uint8_t *sel_c, *sel_l, *sel_g; // [n_sel,C] [n_sel,L] [n_sel,G]
   const int* sel_mode;                  // [n_sel]
+  const int *selc_off, *selc;           // [n_sel+1], compartments of each select (the set bits of sel_c)
+  const int *cr_off, *cr_ops;           // [I*L+1], ADD ops (indices into add_op) covering cost cell (i, l), in op order
   const int* chg_slot_of_comp;          // [C] index into Xprev rows or -1
   // MOVE ops (case "different compartment, same locale", executor.py:201-212)
   int n_mv_op;

@@ -43,6 +43,8 @@ __device__ __forceinline__ double rkE(double, int j) { return RK_E[j]; }
 #define T_mult_d float
 #define T_cpv float
 #define T_act uint8_t
+#define T_live uint8_t
+#define T_elive uint8_t
 #define T_expr double
 #define T_sel double
 #define T_mpy float
