@@ -1086,6 +1086,18 @@ void do_reset(epi_engine* h, const uint8_t* mask, void* obs_out, cudaStream_t st
   h->launches++;
 }
 
+// pinned host staging + device mirrors of the host-buffer path
+void ensure_host_buffers(epi_engine* h) {
+  if (h->h_act) return;
+  const size_t N = h->N, A = h->plan.A ? h->plan.A : 1, rs = h->real_size(), CLG = h->plan.CLG;
+  CK(cudaMallocHost(&h->h_act, N * A * 4)); h->d_act = h->dalloc<float>(N * A);
+  CK(cudaMallocHost(&h->h_obs, N * CLG * rs)); h->d_obs = h->dalloc<char>(N * CLG * rs);
+  CK(cudaMallocHost(&h->h_rew, N * 8)); h->d_rew = h->dalloc<double>(N);
+  CK(cudaMallocHost(&h->h_done, N)); h->d_done = h->dalloc<uint8_t>(N);
+  // dalloc's cudaMemset runs on the legacy default stream, which h->stream (non-blocking) does not wait for
+  CK(cudaDeviceSynchronize());
+}
+
 template <class F>
 int guarded(const epi_engine* h, F&& f) {
   try {
@@ -1241,17 +1253,10 @@ int epi_step_host(epi_t* h, const float* actions_host, int n_days, void* obs_out
     if (!actions_host && h->plan.A > 0) throw Invalid{"actions_host is NULL"};
     if (n_days < 1) throw Invalid{"n_days < 1"};
     CK(cudaSetDevice(h->device));
-    const size_t N = h->N, A = h->plan.A ? h->plan.A : 1, rs = h->real_size(), CLG = h->plan.CLG;
-    if (!h->h_act) {
-      CK(cudaMallocHost(&h->h_act, N * A * 4)); h->d_act = h->dalloc<float>(N * A);
-      CK(cudaMallocHost(&h->h_obs, N * CLG * rs)); h->d_obs = h->dalloc<char>(N * CLG * rs);
-      CK(cudaMallocHost(&h->h_rew, N * 8)); h->d_rew = h->dalloc<double>(N);
-      CK(cudaMallocHost(&h->h_done, N)); h->d_done = h->dalloc<uint8_t>(N);
-      // dalloc's cudaMemset runs on the legacy default stream, which h->stream (non-blocking) does not wait for
-      CK(cudaDeviceSynchronize());
-    }
+    const size_t N = h->N, rs = h->real_size(), CLG = h->plan.CLG;
+    ensure_host_buffers(h);
     if (h->plan.A > 0) {
-      memcpy(h->h_act, actions_host, N * h->plan.A * 4);
+      if (actions_host != h->h_act) memcpy(h->h_act, actions_host, N * h->plan.A * 4);
       CK(cudaMemcpyAsync(h->d_act, h->h_act, N * h->plan.A * 4, cudaMemcpyHostToDevice, h->stream));
     }
     epi::StepArgs a{};
@@ -1262,9 +1267,22 @@ int epi_step_host(epi_t* h, const float* actions_host, int n_days, void* obs_out
     CK(cudaMemcpyAsync(h->h_rew, h->d_rew, N * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(h->h_done, h->d_done, N, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    if (obs_out_host) memcpy(obs_out_host, h->h_obs, N * CLG * rs);
-    if (reward_out_host) memcpy(reward_out_host, h->h_rew, N * 8);
-    if (done_out_host) memcpy(done_out_host, h->h_done, N);
+    // callers that use the library's own pinned buffers (epi_host_buffers) read the results in place
+    if (obs_out_host && obs_out_host != h->h_obs) memcpy(obs_out_host, h->h_obs, N * CLG * rs);
+    if (reward_out_host && reward_out_host != h->h_rew) memcpy(reward_out_host, h->h_rew, N * 8);
+    if (done_out_host && done_out_host != h->h_done) memcpy(done_out_host, h->h_done, N);
+  });
+}
+
+int epi_host_buffers(epi_t* h, float** actions, void** obs, double** reward, uint8_t** done) {
+  if (!h) return EPI_E_INVALID;
+  return guarded(h, [&] {
+    CK(cudaSetDevice(h->device));
+    ensure_host_buffers(h);
+    if (actions) *actions = h->h_act;
+    if (obs) *obs = h->h_obs;
+    if (reward) *reward = h->h_rew;
+    if (done) *done = h->h_done;
   });
 }
 

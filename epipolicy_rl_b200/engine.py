@@ -118,10 +118,21 @@ class BatchedEpidemic:
         if a.shape != (self.n_envs, self.action_dim):
             raise ValueError(f"actions must have shape {(self.n_envs, self.action_dim)}")
         if not hasattr(self, "_h_obs"):
-            self._h_obs = np.empty((self.n_envs, self.obs_dim), self.np_dtype)
-            self._h_rew = np.empty(self.n_envs, np.float64)
-            self._h_done = np.empty(self.n_envs, np.uint8)
-        self._ck(self.L.epi_step_host(self._h, a.ctypes.data, int(n_days), self._h_obs.ctypes.data,
+            # numpy views of the library's pinned staging buffers: results are read in place (no extra copies);
+            # they are overwritten by the next step_host call
+            pa, po, pr, pd = (ctypes.c_void_p() for _ in range(4))
+            self._ck(self.L.epi_host_buffers(self._h, ctypes.byref(pa), ctypes.byref(po), ctypes.byref(pr), ctypes.byref(pd)))
+
+            def view(ptr, shape, dtype):
+                n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+                return np.frombuffer((ctypes.c_char * n).from_address(ptr.value), dtype=dtype).reshape(shape)
+            self._h_act = view(pa, (self.n_envs, max(self.action_dim, 1)), np.float32)
+            self._h_obs = view(po, (self.n_envs, self.obs_dim), self.np_dtype)
+            self._h_rew = view(pr, (self.n_envs,), np.float64)
+            self._h_done = view(pd, (self.n_envs,), np.uint8)
+        if self.action_dim:
+            np.copyto(self._h_act[:, :self.action_dim], a)
+        self._ck(self.L.epi_step_host(self._h, self._h_act.ctypes.data, int(n_days), self._h_obs.ctypes.data,
                                       self._h_rew.ctypes.data, self._h_done.ctypes.data))
         return self._h_obs, self._h_rew, self._h_done
 

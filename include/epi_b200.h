@@ -75,6 +75,12 @@ int epi_step_plan(epi_t* h, const float* cpv_dev, const uint8_t* active_dev, int
 int epi_step_host(epi_t* h, const float* actions_host, int n_days, void* obs_out_host, double* reward_out_host,
                   uint8_t* done_out_host);
 
+/* The library's own pinned host buffers of the host path: actions float32 [n_envs, action_dim], obs real
+ * [n_envs, obs_dim], reward double [n_envs], done uint8 [n_envs]. A caller that fills `*actions` and passes these
+ * very pointers to epi_step_host gets the results in place, without the staging copies. Valid until epi_destroy;
+ * overwritten by the next epi_step_host. */
+int epi_host_buffers(epi_t* h, float** actions, void** obs, double** reward, uint8_t** done);
+
 /* State access for checkpoint/resume and parity injection. `what`:
  *   0 X [n_envs, obs_dim] double        1 cumulative_cost [n_envs, I*L] double
  *   2 day counter [n_envs] int32        3 reference-layout flat observable [n_envs, n_flat] double (get only)
