@@ -631,11 +631,30 @@ void build_env_layout(epi_engine* h, int threads, int64_t smem_max) {
   int64_t o = 0;
   auto take = [&](int64_t bytes) { int64_t r = o; o = align16(o + bytes); return r; };
   const int64_t nS = P.has_src64 ? P.n_slot : 0;
-  Y.l_X = take(8 * C * LG); Y.l_ys = take(rs * C * LG); Y.l_K = take(rs * 7 * C * LG);
-  Y.l_fl = take(rs * P.NSRC * LG); Y.l_FBE = take(2 * rs * P.NSRC * LG); Y.l_accY = take(rs * (int64_t)P.n_acc * LG);
-  Y.l_mvY = take(4 * (int64_t)P.n_slot * LG); Y.l_mvD = take(4 * (int64_t)P.n_slot * LG);
-  Y.l_ysS = take(8 * nS * LG); Y.l_KS = take(8 * 7 * nS * LG);
-  Y.big_bytes = o;
+  // first with the flow sums (fl + packed FB/FE): does the env fit in shared memory? if not, the global-workspace
+  // regime stores the 7 stages' flows instead (less traffic per evaluation, more workspace)
+  for (int pass = 0; pass < 2; pass++) {
+    o = 0;
+    Y.l_X = take(8 * C * LG); Y.l_ys = take(rs * C * LG); Y.l_K = take(rs * 7 * C * LG);
+    if (Y.flow_slots) {
+      Y.l_fls = take(rs * 7 * P.NSRC * LG); Y.l_accYn = take(rs * (int64_t)P.n_acc * LG);
+      Y.l_fl = Y.l_FBE = Y.l_fls;
+    } else {
+      Y.l_fl = take(rs * P.NSRC * LG); Y.l_FBE = take(2 * rs * P.NSRC * LG);
+      Y.l_fls = Y.l_accYn = Y.l_fl;
+    }
+    Y.l_accY = take(rs * (int64_t)P.n_acc * LG);
+    Y.l_mvY = take(4 * (int64_t)P.n_slot * LG); Y.l_mvD = take(4 * (int64_t)P.n_slot * LG);
+    Y.l_ysS = take(8 * nS * LG); Y.l_KS = take(8 * 7 * nS * LG);
+    Y.big_bytes = o;
+    if (pass == 0) {
+      // (tables + reduction scratch + comm columns are laid out below; a conservative bound decides the regime)
+      int64_t small = 48 * 1024;
+      if (getenv("EPI_ENV_FLOWSLOTS")) Y.flow_slots = atoi(getenv("EPI_ENV_FLOWSLOTS")) != 0;
+      else Y.flow_slots = Y.big_bytes + small > smem_max;
+      if (!Y.flow_slots) break;
+    }
+  }
   o = 0;
   Y.l_cmA = take(rs * (1 + NG) * LG); Y.l_cmB = take(rs * (1 + NG) * LG);
   Y.comm_bytes = o;
@@ -675,7 +694,7 @@ std::string gen_spec(const epi_engine* h) {
     << ", LG = " << P.LG << ", CLG = " << P.CLG << ", nnz = " << P.nnz << ", n_lc = " << P.n_lc << ", E = " << P.E
     << ", NG = " << P.NG << ", NSRC = " << P.NSRC << ", n_acc = " << P.n_acc << ", n_slot = " << P.n_slot
     << ", has_ft_ops = " << P.has_ft_ops << ", has_src64 = " << P.has_src64
-    << ", dense_mob = " << (P.mob_dense_csc ? 1 : 0) << ", R = " << (P.cl.roles > 0 ? P.cl.roles : 1) << ";\n";
+    << ", dense_mob = " << (P.mob_dense_csc ? 1 : 0) << ", flow_slots = " << (P.LG > 32 ? P.el.flow_slots : 0) << ", R = " << (P.cl.roles > 0 ? P.cl.roles : 1) << ";\n";
   o << "constexpr int big = " << (P.LG > 32 ? 1 : 0) << ";  // 1: env kernel (epi_env.cuh), 0: cell kernel (epi_cell.cuh)\n";
   if (P.LG <= 32) {
     const CellLayout& Y = P.cl;  // built for 32-lane warps
@@ -860,7 +879,7 @@ std::string gen_spec(const epi_engine* h) {
   uint64_t k = 1469598103934665603ull;
   auto mix = [&](const void* p, size_t n) { for (size_t i = 0; i < n; i++) { k ^= ((const unsigned char*)p)[i]; k *= 1099511628211ull; } };
   mix(body.data(), body.size());
-  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 12 /* generator revision */};
+  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 13 /* generator revision */};
   mix(abi, sizeof abi);
   char kb[32];
   snprintf(kb, sizeof kb, "%016llx", (unsigned long long)k);
@@ -893,7 +912,7 @@ void choose_launch(epi_engine* h) {
   int64_t per_env = P.small_bytes + P.big_bytes;
   const char* force = getenv("EPI_TEAM");  // debugging aid: "warp" / "cta" force the team kernels
   P.cl.enabled = 0;
-  if (P.LG <= 32 && !(force && (!strcmp(force, "warp") || !strcmp(force, "cta")))) {
+  if (P.LG <= 32 && !(force && (!strcmp(force, "warp") || !strcmp(force, "cta") || !strcmp(force, "env")))) {
 #ifdef EPI_HOST_EMU
     int W = P.LG * (h->N < 32 / P.LG ? h->N : 32 / P.LG);  // as many lanes as the test's envs need
 #else
@@ -913,7 +932,7 @@ void choose_launch(epi_engine* h) {
     }
   }
   P.el.enabled = 0;
-  if (P.LG > 32 && !(force && (!strcmp(force, "warp") || !strcmp(force, "cta")))) {
+  if ((P.LG > 32 || (force && !strcmp(force, "env"))) && !(force && (!strcmp(force, "warp") || !strcmp(force, "cta")))) {
     // ENV kernel: one CTA per env, threads strided over the cells
 #ifdef EPI_HOST_EMU
     int threads = P.LG < 24 ? P.LG : 24;  // host threads per emulated CTA

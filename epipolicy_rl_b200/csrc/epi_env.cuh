@@ -81,6 +81,15 @@ __device__ __forceinline__ real acc_gather(const DevPlan& P, const real* col, si
   return d;
 }
 #endif
+// flow-slot mode (global-workspace regime): the 7 stages' flows are stored (one 35-word write per evaluation)
+// and combined once per attempt, instead of read-modify-writing the packed flow sums in every evaluation
+#ifdef EPI_SPEC
+#define EFS (spec::flow_slots)
+#else
+#define EFS (P.el.flow_slots)
+#endif
+#define FLW(i) (*(EFS ? &BA(fls, (size_t)fslot * EDIM(NSRC) + (i)) : &BA(fl, i)))
+#define ECOL_slot(ps) (&BA(fls, (size_t)(ps) * EDIM(NSRC))), (size_t)EDIM(LG)
 #define ECOL_fl (&BA(fl, 0)), (size_t)EDIM(LG)
 #define ECOL_FB (&BA(FBE, 0).x), (size_t)2 * EDIM(LG)
 #define ECOL_FE (&BA(FBE, 0).y), (size_t)2 * EDIM(LG)
@@ -126,7 +135,7 @@ __device__ __forceinline__ void fill_tables(const DevPlan& P, const Bx& b, float
 template <class real>
 __device__ __forceinline__ void rhs(const DevPlan& P, const Bx& b, bool dyn, double t, int ex_bits, int kslot, real bw,
                                     real ew, int acc_mode, bool keep_fl, double hh, int nj, const real (&co)[6],
-                                    const double (&coS)[6]) {
+                                    const double (&coS)[6], int fslot) {
   const int G = EDIM(G), F = EDIM(F), LG = EDIM(LG), nnz = EDIM(nnz), NG = EDIM(NG), n_lc = EDIM(n_lc), PP = EDIM(P),
             C = EDIM(C), nE = EDIM(E), nS = EDIM(has_src64) ? EDIM(n_slot) : 0;
   const float tf = (float)t;
@@ -290,29 +299,34 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Bx& b, bool dyn, dou
     }
 #pragma unroll
     for (int k = 0; k < C; k++) BA(K, k0 + k) = d[k];
-    if (acc_mode == 1) {
+    if (EFS) {
 #pragma unroll
-      for (int i = 0; i < spec::NSRC; i++) {
-        real2 p = BA(FBE, i);
-        p.x += bw * f[i];
-        p.y += ew * f[i];
-        BA(FBE, i) = p;
+      for (int i = 0; i < spec::NSRC; i++) BA(fls, (size_t)fslot * spec::NSRC + i) = f[i];
+    } else {
+      if (acc_mode == 1) {
+#pragma unroll
+        for (int i = 0; i < spec::NSRC; i++) {
+          real2 p = BA(FBE, i);
+          p.x += bw * f[i];
+          p.y += ew * f[i];
+          BA(FBE, i) = p;
+        }
+      } else if (acc_mode == 2) {
+#pragma unroll
+        for (int i = 0; i < spec::NSRC; i++) {
+          real2 p;
+          p.x = bw * f[i];
+          p.y = ew * f[i];
+          BA(FBE, i) = p;
+        }
       }
-    } else if (acc_mode == 2) {
+      if (keep_fl) {
 #pragma unroll
-      for (int i = 0; i < spec::NSRC; i++) {
-        real2 p;
-        p.x = bw * f[i];
-        p.y = ew * f[i];
-        BA(FBE, i) = p;
+        for (int i = 0; i < spec::NSRC; i++) BA(fl, i) = f[i];
       }
-    }
-    if (keep_fl) {
-#pragma unroll
-      for (int i = 0; i < spec::NSRC; i++) BA(fl, i) = f[i];
     }
 #else
-    for (int k = 0; k < NG; k++) BA(fl, nE + k) = BA(ys, __ldg(P.ig_c0 + k)) * rs[k];
+    for (int k = 0; k < NG; k++) FLW(nE + k) = BA(ys, __ldg(P.ig_c0 + k)) * rs[k];
     // regular edges (compute_fraction, :43-65)
     const int* ep = P.ep;
     for (int e = 0; e < nE; e++) {
@@ -333,12 +347,12 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Bx& b, bool dyn, dou
         for (int q = 0; q < nf; q++) sv *= val(__ldg(ep++));
         denom += sv;
       }
-      BA(fl, e) = denom > 0 ? fdiv(numer, denom) : numer;
+      FLW(e) = denom > 0 ? fdiv(numer, denom) : numer;
     }
     for (int k = 0; k < C; k++) {
       real d = 0;
       for (int q = __ldg(P.xg_off + k); q < __ldg(P.xg_off + k + 1); q++)
-        d += BA(fl, __ldg(P.xg_src + q)) * (real)__ldg(P.xg_coef + q);
+        d += FLW(__ldg(P.xg_src + q)) * (real)__ldg(P.xg_coef + q);
       BA(K, k0 + k) = d;
     }
     // clamped moves, slots in op order (core_optimize.py:196-208), double round trip as in epi_cell.cuh
@@ -360,9 +374,10 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Bx& b, bool dyn, dou
       } else if (P.has_src64) {
         BA(KS, kslot * P.n_slot + sl) = (double)BA(K, k0 + c1);
       }
-      BA(fl, nE + NG + sl) = nv;
+      FLW(nE + NG + sl) = nv;
     }
-    if (acc_mode == 1) {
+    if (EFS) {
+    } else if (acc_mode == 1) {
       for (int i = 0; i < P.NSRC; i++) {
         real f = BA(fl, i);
         real2 p = BA(FBE, i);
@@ -561,6 +576,8 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
   double last_err = 0, t = 0.0, h_abs = 0, h = 0, t_new = 0, h0 = 0, d0 = 0, d1 = 0;
   bool run = true, rejected = false;
   auto qd = [](double tt) { return (double)(float)((-3.0 * tt + 4.0) * tt); };
+  int rot = 0;  // flow-slot mode: stage s of the current attempt lives in slot (s + rot) % 7
+  auto ps = [&](int st) { int v = st + rot; return v >= 7 ? v - 7 : v; };
 
   int phase = 0;
   while (phase >= 0) {
@@ -595,7 +612,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
       coS[j] = phase == 7 ? RK_B[j] : (phase == 1 ? 1.0 : RK_A[stage < 6 ? stage : 0][j < 5 ? j : 4]);
     }
     rhs<real>(P, b, dyn, t_eval, ex_bits, stage, bw, ew, phase <= 1 ? 0 : (phase == 8 ? 2 : 1), phase <= 1 || phase == 7,
-              hh, nj, co, coS);
+              hh, nj, co, coS, ps(stage));
     if (phase == 0) {
       // select_initial_step (common.py:68-134), first half
       double s0 = 0, s1 = 0;
@@ -607,7 +624,15 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
           real a = fdiv(yv, sc), bq = fdiv(BA(K, k), sc);
           a0 += a * a; a1 += bq * bq;
         }
-        {
+        if (EFS) {
+          EACC_DECL(g0, ECOL_slot(ps(0)));
+#pragma unroll
+          for (int a_ = 0; a_ < n_acc; a_++) {
+            real yv = BA(accY, a_), sc = atolr + fabs(yv) * rtolr;
+            real a = fdiv(yv, sc), bq = fdiv(EACC_AT(g0, a_, ECOL_slot(ps(0))), sc);
+            a0 += a * a; a1 += bq * bq;
+          }
+        } else {
           EACC_DECL(g0, ECOL_fl);
 #pragma unroll
           for (int a_ = 0; a_ < n_acc; a_++) {
@@ -617,7 +642,8 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
           }
         }
         s0 += (double)a0; s1 += (double)a1;
-        for (int i = 0; i < NSRC; i++) BA(FBE, i).y = BA(fl, i);  // stage-0 flows, needed once more in phase 1
+        if (!EFS)
+          for (int i = 0; i < NSRC; i++) BA(FBE, i).y = BA(fl, i);  // stage-0 flows, needed once more in phase 1
       }
       for (int i = b.tid; i < nC; i += b.nt) {
         double yv = b.cost[i], sc = atol + fabs(yv) * rtol;
@@ -639,7 +665,16 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
           real sc = atolr + fabs((real)BA(X, k)) * rtolr, a = fdiv(BA(K, C + k) - BA(K, k), sc);
           a2 += a * a;
         }
-        {
+        if (EFS) {
+          EACC_DECL(g1, ECOL_slot(ps(1)));
+          EACC_DECL(g0, ECOL_slot(ps(0)));
+#pragma unroll
+          for (int a_ = 0; a_ < n_acc; a_++) {
+            real sc = atolr + fabs(BA(accY, a_)) * rtolr;
+            real a = fdiv(EACC_AT(g1, a_, ECOL_slot(ps(1))) - EACC_AT(g0, a_, ECOL_slot(ps(0))), sc);
+            a2 += a * a;
+          }
+        } else {
           EACC_DECL(g1, ECOL_fl);
           EACC_DECL(g0, ECOL_FE);
 #pragma unroll
@@ -650,6 +685,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
           }
         }
         s2 += (double)a2;
+        if (!EFS)
         for (int i = 0; i < NSRC; i++) {  // stage-0 contributions of the first attempt
           real f = BA(FBE, i).y;
           real2 p;
@@ -684,7 +720,51 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
           real a = fdiv(e * (real)h, sc);
           ae += a * a;
         }
-        {
+        if (EFS) {
+          // combine the 7 stored stage flows once: FB = sum_s B_s f_s, FE = sum_s E_s f_s, then the accumulator
+          // gathers; the candidate y_new of the accumulators is kept for the commit
+#ifdef EPI_SPEC
+          real fb[spec::NSRC], fe[spec::NSRC];
+#pragma unroll
+          for (int i = 0; i < spec::NSRC; i++) { fb[i] = 0; fe[i] = 0; }
+#pragma unroll
+          for (int st = 0; st < 7; st++) {
+            const size_t o = (size_t)ps(st) * spec::NSRC;
+#pragma unroll
+            for (int i = 0; i < spec::NSRC; i++) {
+              real f = BA(fls, o + i);
+              fb[i] += rkB(real(0), st) * f;
+              fe[i] += rkE(real(0), st) * f;
+            }
+          }
+          real gB[spec::n_acc > 0 ? spec::n_acc : 1], gE[spec::n_acc > 0 ? spec::n_acc : 1];
+          spec::acc_rt(fb, 1, gB);
+          spec::acc_rt(fe, 1, gE);
+#endif
+#pragma unroll
+          for (int a_ = 0; a_ < n_acc; a_++) {
+#ifdef EPI_SPEC
+            const real vB = gB[a_], vE = gE[a_];
+#else
+            real vB = 0, vE = 0;
+            for (int q = __ldg(P.ag_off + a_); q < __ldg(P.ag_off + a_ + 1); q++) {
+              const int src = __ldg(P.ag_src + q);
+              real sb = 0, se = 0;
+              for (int st = 0; st < 7; st++) {
+                real f = BA(fls, (size_t)ps(st) * NSRC + src);
+                sb += rkB(real(0), st) * f;
+                se += rkE(real(0), st) * f;
+              }
+              vB += sb * (real)__ldg(P.ag_coef + q);
+              vE += se * (real)__ldg(P.ag_coef + q);
+            }
+#endif
+            real yv = BA(accY, a_), yn = yv + (real)h * vB;
+            real sc = atolr + fmax(fabs(yv), fabs(yn)) * rtolr, a = fdiv(vE * (real)h, sc);
+            ae += a * a;
+            BA(accYn, a_) = yn;
+          }
+        } else {
           EACC_DECL(gB, ECOL_FB);
           EACC_DECL(gE, ECOL_FE);
 #pragma unroll
@@ -741,11 +821,15 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
             BA(X, ESLOT_C1(q)) = BA(ysS, q);  // = X + h * sum_j B_j KS_j in double
             BA(KS, q) = BA(KS, 6 * nS + q);
           }
-          {
+          if (EFS) {
+#pragma unroll
+            for (int a_ = 0; a_ < n_acc; a_++) BA(accY, a_) = BA(accYn, a_);
+          } else {
             EACC_DECL(gB, ECOL_FB);
 #pragma unroll
             for (int a_ = 0; a_ < n_acc; a_++) BA(accY, a_) += hr * EACC_AT(gB, a_, ECOL_FB);
           }
+          if (!EFS)
           for (int i = 0; i < NSRC; i++) {  // the last stage's flows open the next attempt (FSAL)
             real f = BA(fl, i);
             real2 p;
@@ -764,10 +848,13 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
         t = t_new;
         rejected = false;
         if (!(t < 1.0)) run = false;
+        if (EFS) rot = ps(6);  // FSAL: the slot of stage 6 becomes the slot of stage 0
         __syncthreads();
         phase = run ? 2 : -1;
       } else {
-        phase = 8;  // restore the stage-0 flow sums by re-evaluating f(t, y); not counted in nfev
+        // flow sums: restore the stage-0 terms by re-evaluating f(t, y) (not counted in nfev);
+        // flow slots: slot 0 still holds them
+        phase = EFS ? 2 : 8;
       }
     } else {
       phase = 2;

@@ -31,6 +31,8 @@ __device__ __forceinline__ double rkE(double, int j) { return RK_E[j]; }
 #define T_fl real
 #define T_FBE real2
 #define T_accY real
+#define T_accYn real
+#define T_fls real
 #define T_tdc real
 #define T_cmA real
 #define T_cmB real
