@@ -867,6 +867,41 @@ std::string gen_spec(const epi_engine* h) {
     }
     o << "  }\n}\n";
   }
+
+  // ---- streaming form for the env kernel's flow-slot regime: every flow is stored as soon as it is known and
+  // scattered into dX on the fly (few live registers: y, d), instead of materialising all flows first
+  if (P.LG > 32) {
+    std::vector<std::vector<std::pair<int, float>>> sc_of(P.NSRC);  // source -> (compartment, coef), in gather order
+    for (int c = 0; c < P.C; c++)
+      for (int q = T.xg_off[c]; q < T.xg_off[c + 1]; q++) sc_of[T.xg_src[q]].push_back({c, T.xg_coef[q]});
+    auto scatter = [&](int src) {
+      for (auto& pr : sc_of[src]) o << " d[" << pr.first << "] += f * " << hexf(pr.second) << ";";
+    };
+    o << "__device__ __forceinline__ void flows_scatter(const real* y, real alive, const float* mp, const real* rs, real* out, size_t stride, real* d) {\n";
+    for (int c = 0; c < P.C; c++) o << "  d[" << c << "] = 0;\n";
+    for (int k = 0; k < P.NG; k++) {
+      o << "  { real f = y[" << T.ig_c0[k] << "] * rs[" << k << "]; out[" << P.E + k << " * stride] = f;";
+      scatter(P.E + k);
+      o << " }\n";
+    }
+    for (int e = 0; e < P.E; e++) {
+      const int* ep = T.ep.data() + T.ep_off[e];
+      int n = *ep++;
+      o << "  { real f; { real n = (real)1";
+      for (int q = 0; q < n; q++) o << " * " << val(*ep++);
+      o << ";";
+      emit_denominator(o, ep, val, "f");
+      o << "    out[" << e << " * stride] = f;";
+      scatter(e);
+      o << " }\n";
+    }
+    o << "}\n";
+    arr("ag_off", T.ag_off); arr("ag_src", T.ag_src);
+    o << "__device__ constexpr float ag_coef[" << (T.ag_coef.empty() ? 1 : T.ag_coef.size()) << "] = {";
+    if (T.ag_coef.empty()) o << "0";
+    for (size_t i = 0; i < T.ag_coef.size(); i++) { char b[64]; snprintf(b, sizeof b, "%af", (double)T.ag_coef[i]); o << (i ? ", " : "") << b; }
+    o << "};\n";
+  }
   o << "__device__ __forceinline__ void acc_rt(const real* col, size_t stride, real* out) {\n";
   for (int a = 0; a < P.n_acc; a++) {
     o << "  out[" << a << "] = 0;";
@@ -879,7 +914,7 @@ std::string gen_spec(const epi_engine* h) {
   uint64_t k = 1469598103934665603ull;
   auto mix = [&](const void* p, size_t n) { for (size_t i = 0; i < n; i++) { k ^= ((const unsigned char*)p)[i]; k *= 1099511628211ull; } };
   mix(body.data(), body.size());
-  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 13 /* generator revision */};
+  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 14 /* generator revision */};
   mix(abi, sizeof abi);
   char kb[32];
   snprintf(kb, sizeof kb, "%016llx", (unsigned long long)k);

@@ -269,6 +269,38 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Bx& b, bool dyn, dou
     const float* mp = &ET(mpt0, lc * PP * G + u);  // parameters from facility 0 only (:48)
     const int k0 = kslot * C;
 #ifdef EPI_SPEC
+    if (EFS) {
+      // streaming form: flows go straight to their slot and into dX (see gen_spec: flows_scatter)
+      real y[spec::C], d[spec::C];
+#pragma unroll
+      for (int k = 0; k < C; k++) y[k] = BA(ys, k);
+      real* out = &BA(fls, (size_t)fslot * spec::NSRC);
+      spec::flows_scatter(y, alive, mp, rs, out, (size_t)LG, d);
+#pragma unroll
+      for (int sl = 0; sl < spec::n_slot; sl++) {
+        real nv = 0;
+        const int c1 = spec::slot_c1[sl], c2 = spec::slot_c2[sl];
+        if (__ldg(P.slot_cover + (size_t)sl * LG + cell) && ((ex_bits >> sl) & 0x10001)) {
+          float my = ((ex_bits >> sl) & 1) ? BA(mvY, sl) : 0.0f;
+          float md = ((ex_bits >> (16 + sl)) & 1) ? BA(mvD, sl) : 0.0f;
+          float v = __fadd_rn(__fmul_rn(__fsub_rn(md, my), qf), my);  // coo.py scale/add in f32
+          double y1 = spec::has_src64 ? BA(ysS, sl) : (double)y[c1], y2 = (double)y[c2];
+          double n1 = y1 + (double)d[c1], n2 = y2 + (double)d[c2];
+          double nvd = (double)v < n1 ? (double)v : n1;
+          double k1 = (n1 - nvd) - y1;
+          d[c1] = (real)k1;
+          d[c2] = (real)((n2 + nvd) - y2);
+          nv = (real)nvd;
+          if (spec::has_src64) BA(KS, kslot * spec::n_slot + sl) = k1;
+        } else if (spec::has_src64) {
+          BA(KS, kslot * spec::n_slot + sl) = (double)d[c1];
+        }
+        out[(size_t)(nE + NG + sl) * LG] = nv;
+      }
+#pragma unroll
+      for (int k = 0; k < C; k++) BA(K, k0 + k) = d[k];
+      continue;
+    }
     real y[spec::C], f[spec::NSRC], d[spec::C];
 #pragma unroll
     for (int k = 0; k < C; k++) y[k] = BA(ys, k);
@@ -723,35 +755,32 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
         if (EFS) {
           // combine the 7 stored stage flows once: FB = sum_s B_s f_s, FE = sum_s E_s f_s, then the accumulator
           // gathers; the candidate y_new of the accumulators is kept for the commit
-#ifdef EPI_SPEC
-          real fb[spec::NSRC], fe[spec::NSRC];
+          size_t so[7];
 #pragma unroll
-          for (int i = 0; i < spec::NSRC; i++) { fb[i] = 0; fe[i] = 0; }
-#pragma unroll
-          for (int st = 0; st < 7; st++) {
-            const size_t o = (size_t)ps(st) * spec::NSRC;
-#pragma unroll
-            for (int i = 0; i < spec::NSRC; i++) {
-              real f = BA(fls, o + i);
-              fb[i] += rkB(real(0), st) * f;
-              fe[i] += rkE(real(0), st) * f;
-            }
-          }
-          real gB[spec::n_acc > 0 ? spec::n_acc : 1], gE[spec::n_acc > 0 ? spec::n_acc : 1];
-          spec::acc_rt(fb, 1, gB);
-          spec::acc_rt(fe, 1, gE);
-#endif
+          for (int st = 0; st < 7; st++) so[st] = (size_t)ps(st) * NSRC;
 #pragma unroll
           for (int a_ = 0; a_ < n_acc; a_++) {
-#ifdef EPI_SPEC
-            const real vB = gB[a_], vE = gE[a_];
-#else
             real vB = 0, vE = 0;
+#ifdef EPI_SPEC
+#pragma unroll
+            for (int q = spec::ag_off[a_]; q < spec::ag_off[a_ + 1]; q++) {
+              const int src = spec::ag_src[q];
+              real sb = 0, se = 0;
+#pragma unroll
+              for (int st = 0; st < 7; st++) {
+                real f = BA(fls, so[st] + src);
+                sb += rkB(real(0), st) * f;
+                se += rkE(real(0), st) * f;
+              }
+              vB += sb * (real)spec::ag_coef[q];
+              vE += se * (real)spec::ag_coef[q];
+            }
+#else
             for (int q = __ldg(P.ag_off + a_); q < __ldg(P.ag_off + a_ + 1); q++) {
               const int src = __ldg(P.ag_src + q);
               real sb = 0, se = 0;
               for (int st = 0; st < 7; st++) {
-                real f = BA(fls, (size_t)ps(st) * NSRC + src);
+                real f = BA(fls, so[st] + src);
                 sb += rkB(real(0), st) * f;
                 se += rkE(real(0), st) * f;
               }
