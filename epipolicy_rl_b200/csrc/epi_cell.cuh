@@ -270,12 +270,13 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Cx& c, bool on, bool
         for (int u = 0; u < G; u++) den += LO(cmB, 0, row + u) * WT(tdc, tb + u);
       }
       if (den <= (real)1e-15) den = 1;
+      const real inv = sizeof(real) == 8 ? (real)0 : frcp(den);  // fp32 mode: one reciprocal for the NG quotients
 #pragma unroll
       for (int k = 0; k < EPI_MAX_NG; k++)
         if (k < NG) {
           real num = 0;
           for (int u = 0; u < G; u++) num += LO(cmB, 1 + k, row + u) * (real)EV(Tnum, tb + u);
-          real foi = fdiv(num, den);
+          real foi = sizeof(real) == 8 ? num / den : num * inv;
           sk[k] += EV(coefS, ((k * n_lc + c.lc) * F + v) * G + c.u) * foi;
         }
     }

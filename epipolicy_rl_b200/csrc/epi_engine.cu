@@ -729,6 +729,7 @@ std::string gen_spec(const epi_engine* h) {
 
   // denominator of a regular edge: `dn > 0 ? n / dn : n` (compute_fraction, core_optimize.py:55-65). A denominator
   // made of constants only is folded here (the usual case is the single summant "1").
+  const std::map<std::string, std::string>* rcp_of = nullptr;
   auto emit_denominator = [&](std::ostringstream& out, const int*& ep, const std::function<std::string(int)>& valfn,
                               const std::string& target) {
     int ns = *ep++;
@@ -749,15 +750,47 @@ std::string gen_spec(const epi_engine* h) {
       else out << " " << target << " = n; }\n";
       return;
     }
-    out << " real dn = 0;";
+    std::ostringstream dn;
     for (int sidx = 0; sidx < ns; sidx++) {
-      out << " dn += " << hexf(T.ep_coef[*ep++]);
+      dn << " dn += " << hexf(T.ep_coef[*ep++]);
       int nf = *ep++;
-      for (int q = 0; q < nf; q++) out << " * " << valfn(*ep++);
-      out << ";";
+      for (int q = 0; q < nf; q++) dn << " * " << valfn(*ep++);
+      dn << ";";
+    }
+    out << " real dn = 0;" << dn.str();
+    if (h->precision == EPI_FP32 && rcp_of) {
+      // fp32 mode: edges sharing a denominator share its reciprocal (declared by the caller from rcp_of)
+      auto it = rcp_of->find(dn.str());
+      if (it != rcp_of->end()) { out << " " << target << " = dn > 0 ? n * " << it->second << " : n; }\n"; return; }
     }
     out << " " << target << " = dn > 0 ? fdiv(n, dn) : n; }\n";
   };
+  // denominators (as generated text) that occur in more than one regular edge -> a shared reciprocal variable
+  auto shared_denominators = [&](const std::function<std::string(int)>& valfn, std::vector<std::pair<std::string, std::string>>& decl) {
+    std::map<std::string, int> count;
+    std::vector<std::string> order;
+    for (int e = 0; e < P.E; e++) {
+      const int* ep = T.ep.data() + T.ep_off[e];
+      int n = *ep++; ep += n;
+      int ns = *ep++;
+      bool all_const = true;
+      std::ostringstream dn;
+      for (int sidx = 0; sidx < ns; sidx++) {
+        dn << " dn += " << hexf(T.ep_coef[*ep++]);
+        int nf = *ep++;
+        if (nf) all_const = false;
+        for (int q = 0; q < nf; q++) dn << " * " << valfn(*ep++);
+        dn << ";";
+      }
+      if (ns == 0 || all_const) continue;
+      if (!count[dn.str()]++) order.push_back(dn.str());
+    }
+    std::map<std::string, std::string> m;
+    for (auto& k : order)
+      if (count[k] > 1) { std::string v = "rcp" + std::to_string(m.size()); m[k] = v; decl.push_back({v, k}); }
+    return m;
+  };
+
   // regular edges
   o << "__device__ __forceinline__ void flows(const real* y, real alive, const float* mp, real* f) {\n";
   auto val = [&](int fac) {
@@ -768,6 +801,13 @@ std::string gen_spec(const epi_engine* h) {
     else v << "y[" << idx << "]";
     return v.str();
   };
+  std::vector<std::pair<std::string, std::string>> rdecl;
+  std::map<std::string, std::string> rmap;
+  if (h->precision == EPI_FP32) {
+    rmap = shared_denominators(val, rdecl);
+    for (auto& dc : rdecl) o << "  real " << dc.first << "; { real dn = 0;" << dc.second << " " << dc.first << " = frcp(dn); }\n";
+    rcp_of = &rmap;
+  }
   for (int e = 0; e < P.E; e++) {
     const int* ep = T.ep.data() + T.ep_off[e];
     int n = *ep++;
@@ -776,6 +816,7 @@ std::string gen_spec(const epi_engine* h) {
     o << ";";
     emit_denominator(o, ep, val, "f[" + std::to_string(e) + "]");
   }
+  rcp_of = nullptr;
   o << "}\n";
   // scatter into dX
   o << "__device__ __forceinline__ void dx(const real* f, real* d) {\n";
@@ -879,6 +920,10 @@ std::string gen_spec(const epi_engine* h) {
     };
     o << "__device__ __forceinline__ void flows_scatter(const real* y, real alive, const float* mp, const real* rs, real* out, size_t stride, real* d) {\n";
     for (int c = 0; c < P.C; c++) o << "  d[" << c << "] = 0;\n";
+    if (h->precision == EPI_FP32) {
+      for (auto& dc : rdecl) o << "  real " << dc.first << "; { real dn = 0;" << dc.second << " " << dc.first << " = frcp(dn); }\n";
+      rcp_of = &rmap;
+    }
     for (int k = 0; k < P.NG; k++) {
       o << "  { real f = y[" << T.ig_c0[k] << "] * rs[" << k << "]; out[" << P.E + k << " * stride] = f;";
       scatter(P.E + k);
@@ -895,6 +940,7 @@ std::string gen_spec(const epi_engine* h) {
       scatter(e);
       o << " }\n";
     }
+    rcp_of = nullptr;
     o << "}\n";
     arr("ag_off", T.ag_off); arr("ag_src", T.ag_src);
     o << "__device__ constexpr float ag_coef[" << (T.ag_coef.empty() ? 1 : T.ag_coef.size()) << "] = {";
@@ -914,7 +960,7 @@ std::string gen_spec(const epi_engine* h) {
   uint64_t k = 1469598103934665603ull;
   auto mix = [&](const void* p, size_t n) { for (size_t i = 0; i < n; i++) { k ^= ((const unsigned char*)p)[i]; k *= 1099511628211ull; } };
   mix(body.data(), body.size());
-  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 14 /* generator revision */};
+  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 15 /* generator revision */};
   mix(abi, sizeof abi);
   char kb[32];
   snprintf(kb, sizeof kb, "%016llx", (unsigned long long)k);

@@ -6,10 +6,15 @@
 namespace epi {
 __device__ __forceinline__ double fdiv(double a, double b) { return a / b; }
 __device__ __forceinline__ double ctrl_pow(double, double x, double p) { return pow(x, p); }
+// reciprocal shared by several quotients with one denominator: fp32 mode only (the fp64 mode divides, like the
+// reference); callers test `sizeof(real) == 8`
+__device__ __forceinline__ double frcp(double x) { return 1.0 / x; }
 #ifdef EPI_HOST_EMU
+__device__ __forceinline__ float frcp(float x) { return 1.0f / x; }
 __device__ __forceinline__ float fdiv(float a, float b) { return a / b; }
 __device__ __forceinline__ double ctrl_pow(float, double x, double p) { return (double)powf((float)x, (float)p); }
 #else
+__device__ __forceinline__ float frcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
 __device__ __forceinline__ double ctrl_pow(float, double x, double p) { return (double)__powf((float)x, (float)p); }
 #endif
