@@ -132,6 +132,11 @@ def run_reference(args):
     desc = load_desc(args.workload)
     cores = len(os.sched_getaffinity(0))
     per_core = args.ref_envs_per_core
+    # bounded sample: about 2 s of CPU work per core and step
+    t0 = time.perf_counter()
+    _ref_worker((args.workload, 1, 1, 7))
+    one = time.perf_counter() - t0
+    per_core = max(1, min(per_core, int(2.0 / max(one, 1e-6))))
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
         job = [(args.workload, per_core, 1, 100 + i) for i in range(cores)]
