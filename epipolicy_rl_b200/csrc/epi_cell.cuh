@@ -448,6 +448,28 @@ __device__ __forceinline__ int prologue(const DevPlan& P, const Cx& c, bool on, 
                                         int ex_y_bits, bool& dyn, bool& tabs_current) {
   const int LG = DIM(LG), G = DIM(G), L = DIM(L), C = DIM(C), F = DIM(F), PP = DIM(P);
   // 1. select sums (executor.py:346-359, ['Value'].sum())
+#if defined(EPI_SPEC) && EPI_SPEC_PROLOGUE
+  // generated per-cell partial sums of every distinct select, ONE exchange through shared memory (the stage
+  // derivative column K is free between days), each total reduced in lane order by one lane of the env
+  {
+    double* scr = (double*)COLP(K);
+    if (on) {
+      double part[spec::n_sel > 0 ? spec::n_sel : 1];
+      spec::sel_partials(c.j, c.u, &LA(X, 0), P.X0 + c.cell, Xprev_g + c.cell, part);
+#pragma unroll
+      for (int s = 0; s < spec::n_sel; s++)
+        if (spec::sel_rep[s] == s) scr[s * EPI_LW + c.lane] = part[s];
+    }
+    __syncwarp();
+    if (on)
+      for (int s = c.cell; s < spec::n_sel; s += LG) {
+        const int r = spec::sel_rep[s];
+        double tot = 0;
+        for (int i = 0; i < LG; i++) tot += scr[r * EPI_LW + c.l0 + i];
+        EV(sel, s) = tot;
+      }
+  }
+#else
   for (int s = 0; s < P.n_sel; s++) {
     double part = 0;
     if (on && P.sel_l[s * L + c.j] && P.sel_g[s * G + c.u]) {
@@ -463,6 +485,7 @@ __device__ __forceinline__ int prologue(const DevPlan& P, const Cx& c, bool on, 
     TEAM_SUM(tot, part, on);
     if (on && c.cell == 0) EV(sel, s) = tot;
   }
+#endif
   __syncwarp();
   if (on) {
     // the previous state for tomorrow's 'change' selects is today's start state (epidemic.py:96-99)
@@ -472,19 +495,27 @@ __device__ __forceinline__ int prologue(const DevPlan& P, const Cx& c, bool on, 
     }
     // 2. expressions
     for (int e = c.cell; e < P.n_expr; e += LG) {
+#if defined(EPI_SPEC) && EPI_SPEC_PROLOGUE
+      EV(expr, e) = EV(elive, e) ? spec::expr_eval(e, &EV(cpv, 0), &EV(sel, 0)) : 0.0;
+#else
       EV(expr, e) = EV(elive, e) ? eval_expr(P, e, &EV(cpv, 0), &EV(sel, 0)) : 0.0;
+#endif
     }
   }
   __syncwarp();
   if (on) {
     // 3. class multipliers: sequential f32 products in op order (nb_apply, executor.py:116-164)
     for (int k = c.cell; k < P.n_cls; k += LG) {
+#if defined(EPI_SPEC) && EPI_SPEC_PROLOGUE
+      EV(mult_d, k) = spec::cls_mult(k, &EV(live, 0), &EV(expr, 0));
+#else
       float m = 1.0f;
       for (int q = P.cls_off[k]; q < P.cls_off[k + 1]; q++) {
         int o = P.cls_op[q];
         if (EV(live, o)) m = __fmul_rn(m, (float)EV(expr, P.op_expr[o]));
       }
       EV(mult_d, k) = m;
+#endif
     }
   }
   __syncwarp();

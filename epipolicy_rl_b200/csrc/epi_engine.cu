@@ -49,6 +49,10 @@ struct HostTabs {
   std::vector<int> ig_c0, ig_w_off, ig_w_c2, ep_off, ep, xg_off, xg_src, ag_off, ag_src;
   std::vector<float> ep_coef, xg_coef, ag_coef;
   std::vector<int> comp_role;
+  // prologue tables for the generator
+  std::vector<uint8_t> sel_c, sel_l, sel_g;
+  std::vector<int> sel_mode, chg_slot, selc_off, selc, cls_off, cls_op, op_expr, expr_off, tok_op, tok_arg, tok_f32;
+  std::vector<double> tok_val;
 };
 
 struct epi_engine {
@@ -513,6 +517,11 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
     T.alive_coef = vec(d.alive_coef, C); T.ig_w = ig_w; T.ig_c0 = ig_c0; T.ig_w_off = ig_w_off; T.ig_w_c2 = ig_w_c2;
     T.ep_off = ep_off; T.ep = ep; T.ep_coef = vec(d.sum_coef, d.NS);
     T.xg_off = xg_off; T.xg_src = xg_src; T.xg_coef = xg_coef; T.ag_off = ag_off; T.ag_src = ag_src; T.ag_coef = ag_coef;
+    T.sel_c = sel_c; T.sel_l = sel_l; T.sel_g = sel_g; T.sel_mode = sel_mode; T.chg_slot = chg_slot;
+    T.selc_off = selc_off; T.selc = selc; T.cls_off = cls_off; T.cls_op = cls_op;
+    T.op_expr = vec(d.op_expr, d.NOP); T.expr_off = vec(d.expr_off, d.NEXPR + 1);
+    T.tok_op = vec(d.tok_op, d.NTOK); T.tok_arg = vec(d.tok_arg, d.NTOK); T.tok_f32 = vec(d.tok_f32, d.NTOK);
+    T.tok_val = vec(d.tok_val, d.NTOK);
   }
 
   // ---- workspace layout
@@ -948,6 +957,76 @@ std::string gen_spec(const epi_engine* h) {
     for (size_t i = 0; i < T.ag_coef.size(); i++) { char b[64]; snprintf(b, sizeof b, "%af", (double)T.ag_coef[i]); o << (i ? ", " : "") << b; }
     o << "};\n";
   }
+
+  // ---- day prologue pieces of the cell kernel: per-cell partial sums of the distinct selects, the expression
+  // programs and the class-multiplier products as straight-line code (executor.py:116-164, :346-359)
+  bool spec_prologue = false;
+  if (P.LG <= 32 && (int64_t)P.n_sel * 8 <= (int64_t)7 * P.C * (int64_t)h->real_size() && P.L <= 32 && P.G <= 32) {
+    spec_prologue = true;
+    const int NS = P.n_sel;
+    std::vector<int> rep(NS);
+    for (int s = 0; s < NS; s++) {
+      rep[s] = s;
+      for (int r = 0; r < s; r++) {
+        bool same = T.sel_mode[r] == T.sel_mode[s];
+        for (int c = 0; c < P.C && same; c++) same = T.sel_c[(size_t)r * P.C + c] == T.sel_c[(size_t)s * P.C + c];
+        for (int l = 0; l < P.L && same; l++) same = T.sel_l[(size_t)r * P.L + l] == T.sel_l[(size_t)s * P.L + l];
+        for (int g = 0; g < P.G && same; g++) same = T.sel_g[(size_t)r * P.G + g] == T.sel_g[(size_t)s * P.G + g];
+        if (same) { rep[s] = rep[r]; break; }
+      }
+    }
+    o << "constexpr int n_sel = " << NS << ";\n";
+    arr("sel_rep", rep);
+    o << "__device__ __forceinline__ void sel_partials(int j, int u, const double* X, const double* X0c, const double* Xpc, double* part) {\n";
+    for (int s = 0; s < NS; s++) {
+      if (rep[s] != s) continue;
+      unsigned lm = 0, gm = 0;
+      for (int l = 0; l < P.L; l++) if (T.sel_l[(size_t)s * P.L + l]) lm |= 1u << l;
+      for (int g = 0; g < P.G; g++) if (T.sel_g[(size_t)s * P.G + g]) gm |= 1u << g;
+      o << "  part[" << s << "] = 0; if (((" << lm << "u >> j) & 1u) && ((" << gm << "u >> u) & 1u)) {";
+      for (int q = T.selc_off[s]; q < T.selc_off[s + 1]; q++) {
+        int k = T.selc[q];
+        if (T.sel_mode[s] == 0) o << " part[" << s << "] += X[" << k << " * LW];";
+        else if (T.sel_mode[s] == 1) o << " part[" << s << "] += X0c[" << k << " * LG];";
+        else o << " part[" << s << "] += X[" << k << " * LW] - Xpc[" << T.chg_slot[k] << " * LG];";
+      }
+      o << " }\n";
+    }
+    o << "}\n";
+    o << "__device__ __forceinline__ double expr_eval(int e, const float* cpv, const double* sel) {\n  switch (e) {\n";
+    for (int e = 0; e < P.n_expr; e++) {
+      std::vector<std::string> st;
+      for (int k = T.expr_off[e]; k < T.expr_off[e + 1]; k++) {
+        int op = T.tok_op[k];
+        std::string r;
+        char b[64];
+        if (op == 0) { snprintf(b, sizeof b, "%a", T.tok_val[k]); r = b; }
+        else if (op == 1) r = "(double)cpv[" + std::to_string(T.tok_arg[k]) + "]";
+        else if (op == 2) r = "sel[" + std::to_string(T.tok_arg[k]) + "]";
+        else if (op == 7) { std::string a = st.back(); st.pop_back(); r = "(-" + a + ")"; }
+        else {
+          std::string bb = st.back(); st.pop_back();
+          std::string a = st.back(); st.pop_back();
+          r = op == 3 ? "__dadd_rn(" + a + ", " + bb + ")" : op == 4 ? "__dsub_rn(" + a + ", " + bb + ")"
+            : op == 5 ? "__dmul_rn(" + a + ", " + bb + ")" : "(" + a + " / " + bb + ")";
+        }
+        if (T.tok_f32[k]) r = "(double)(float)(" + r + ")";
+        st.push_back(r);
+      }
+      o << "  case " << e << ": return " << (st.empty() ? std::string("0.0") : st[0]) << ";\n";
+    }
+    o << "  }\n  return 0.0;\n}\n";
+    o << "__device__ __forceinline__ float cls_mult(int k, const unsigned char* live, const double* expr) {\n  float m = 1.0f;\n  switch (k) {\n";
+    for (int k = 0; k < P.n_cls; k++) {
+      o << "  case " << k << ":";
+      for (int q = T.cls_off[k]; q < T.cls_off[k + 1]; q++) {
+        int op = T.cls_op[q];
+        o << " if (live[" << op << "]) m = __fmul_rn(m, (float)expr[" << T.op_expr[op] << "]);";
+      }
+      o << " break;\n";
+    }
+    o << "  }\n  return m;\n}\n";
+  }
   o << "__device__ __forceinline__ void acc_rt(const real* col, size_t stride, real* out) {\n";
   for (int a = 0; a < P.n_acc; a++) {
     o << "  out[" << a << "] = 0;";
@@ -960,12 +1039,13 @@ std::string gen_spec(const epi_engine* h) {
   uint64_t k = 1469598103934665603ull;
   auto mix = [&](const void* p, size_t n) { for (size_t i = 0; i < n; i++) { k ^= ((const unsigned char*)p)[i]; k *= 1099511628211ull; } };
   mix(body.data(), body.size());
-  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 15 /* generator revision */};
+  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 17 /* generator revision */};
   mix(abi, sizeof abi);
   char kb[32];
   snprintf(kb, sizeof kb, "%016llx", (unsigned long long)k);
   return std::string("// GENERATED by libepi_b200 (epi_engine.cu: gen_spec) - scenario-specialised per-cell program\n#define EPI_SPEC 1\n#define EPI_SPEC_KEY \"") +
          kb + "\"\n#define EPI_SPEC_BIG " + (P.LG > 32 ? "1" : "0") + "\n" +
+         "#define EPI_SPEC_PROLOGUE " + (spec_prologue ? "1" : "0") + "\n" +
          "#define EPI_SPEC_ROLES " + std::to_string(P.cl.roles > 0 ? P.cl.roles : 1) + "\n" +
          (P.LG > 32 ? std::string("#define EPI_ENV_MINB ") + (P.el.big_in_smem ? "2" : "4") + "\n" : std::string()) + body;
 }
