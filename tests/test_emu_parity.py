@@ -91,3 +91,32 @@ def test_unsupported_programs_are_refused_not_approximated():
     with pytest.raises(lib.EpiError) as ei:
         EmuEngine(d, 1, "fp64")
     assert ei.value.code == -2
+
+
+@pytest.mark.parametrize("knobs", [{"EPI_ROLES": "2"}, {"EPI_ROLES": "3"}, {"EPI_TEAM": "env", "EPI_ENV_FLOWSLOTS": "0"},
+                                   {"EPI_TEAM": "env", "EPI_ENV_FLOWSLOTS": "1"}, {"EPI_TEAM": "warp"}],
+                         ids=["roles2", "roles3", "env-flowsums", "env-flowslots", "warp-team"])
+def test_alternative_kernels_on_covid_c(knobs, monkeypatch):
+    """The other kernels of the library on a shipped scenario whose episode includes rejected RK45 attempts:
+    the cell-team kernel (R cooperating warps), the env kernel in both flow regimes, the warp-team kernel."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    d, z = load("COVID_C")
+    eng = EmuEngine(d, 2, "fp64")
+    acts = np.stack([z["rnd_actions"], z["lax_actions"]], 1)
+    X = np.stack([z["rnd_X"], z["lax_X"]], 1)
+    nf = np.stack([z["rnd_nfev"], z["lax_nfev"]], 1)
+    day, worst, mism, rej = 0, 0.0, 0, 0
+    for a in acts:
+        for _ in range(7):
+            if day >= d.horizon:
+                break
+            eng.step(a, 1)
+            tr = eng.get_state("trace")
+            worst = max(worst, x_err(eng.get_state("X"), X[day], d))
+            mism += int(np.any(tr[:, 0] != nf[day]))
+            rej += int(tr[:, 2].sum())
+            day += 1
+    assert worst <= 1e-9 and mism == 0
+    assert rej > 0  # the trajectory exercised the reject path
+    eng.close()
