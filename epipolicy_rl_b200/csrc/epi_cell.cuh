@@ -61,6 +61,9 @@ extern __shared__ __align__(16) char cell_smem[];
 #define LA(arr, i) (COLP(arr)[(i) * EPI_LW + c.lane])
 #define LO(arr, i, ln) (COLP(arr)[(i) * EPI_LW + (ln)])
 #define EV(arr, i) (ENVP(arr)[i])
+// the stage derivatives: element (stage j, compartment k) of my lane. The 8 stage slots of one compartment are
+// two 4-vectors per lane ([k][j/4][lane][j%4]), so the fp32 build reads them with two 128-bit loads
+#define KA(j, k) (COLP(K)[((((k) * 2 + ((j) >> 2)) * EPI_LW + c.lane) << 2) + ((j) & 3)])
 #define WT(arr, i) (COLP(arr)[i])  // warp-wide table
 
 struct Cx {
@@ -312,7 +315,6 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Cx& c, bool on, bool
       }
     }
     const float* mp = &EV(mpt0, c.lc * PP * G + c.u);  // parameters from facility 0 only (:48)
-    const int k0 = kslot * C;
 #ifdef EPI_SPEC
     // ---- phases E-G on registers: flows, scatter into dX, clamped moves
     real f[spec::NSRC], d[spec::C];
@@ -342,7 +344,7 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Cx& c, bool on, bool
       f[nE + NG + sl] = nv;
     }
 #pragma unroll
-    for (int k = 0; k < C; k++) LA(K, k0 + k) = d[k];
+    for (int k = 0; k < C; k++) KA(kslot, k) = d[k];
     if (acc_mode == 1) {
 #pragma unroll
       for (int i = 0; i < spec::NSRC; i++) {
@@ -393,7 +395,7 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Cx& c, bool on, bool
       real d = 0;
       for (int q = __ldg(P.xg_off + k); q < __ldg(P.xg_off + k + 1); q++)
         d += LA(fl, __ldg(P.xg_src + q)) * (real)__ldg(P.xg_coef + q);
-      LA(K, k0 + k) = d;
+      KA(kslot, k) = d;
     }
     // ---- phase G: clamped moves, slots in op order. next = X + dX, clamp, dX = next - X in double in BOTH
     // modes: a clamped move must give dX[c1] = -X[c1] to full relative precision (core_optimize.py:196-208)
@@ -405,15 +407,15 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Cx& c, bool on, bool
         float md = ((ex_bits >> (16 + sl)) & 1) ? LA(mvD, sl) : 0.0f;
         float v = __fadd_rn(__fmul_rn(__fsub_rn(md, my), qf), my);  // coo.py scale/add in f32
         double y1 = P.has_src64 ? LA(ysS, sl) : (double)LA(ys, c1), y2 = (double)LA(ys, c2);
-        double n1 = y1 + (double)LA(K, k0 + c1), n2 = y2 + (double)LA(K, k0 + c2);
+        double n1 = y1 + (double)KA(kslot, c1), n2 = y2 + (double)KA(kslot, c2);
         double nvd = (double)v < n1 ? (double)v : n1;
         double k1 = (n1 - nvd) - y1;
-        LA(K, k0 + c1) = (real)k1;
-        LA(K, k0 + c2) = (real)((n2 + nvd) - y2);
+        KA(kslot, c1) = (real)k1;
+        KA(kslot, c2) = (real)((n2 + nvd) - y2);
         nv = (real)nvd;
         if (P.has_src64) LA(KS, kslot * P.n_slot + sl) = k1;
       } else if (P.has_src64) {
-        LA(KS, kslot * P.n_slot + sl) = (double)LA(K, k0 + c1);
+        LA(KS, kslot * P.n_slot + sl) = (double)KA(kslot, c1);
       }
       LA(fl, nE + NG + sl) = nv;
     }
@@ -449,10 +451,11 @@ __device__ __forceinline__ int prologue(const DevPlan& P, const Cx& c, bool on, 
   const int LG = DIM(LG), G = DIM(G), L = DIM(L), C = DIM(C), F = DIM(F), PP = DIM(P);
   // 1. select sums (executor.py:346-359, ['Value'].sum())
 #if defined(EPI_SPEC) && EPI_SPEC_PROLOGUE
-  // generated per-cell partial sums of every distinct select, ONE exchange through shared memory (the stage
-  // derivative column K is free between days), each total reduced in lane order by one lane of the env
+  // generated per-cell partial sums of every distinct select, ONE exchange through shared memory (the flow-sum
+  // column FBE is free between days and fully rewritten before it is read), each total reduced in lane order by
+  // one lane of the env
   {
-    double* scr = (double*)COLP(K);
+    double* scr = (double*)COLP(FBE);
     if (on) {
       double part[spec::n_sel > 0 ? spec::n_sel : 1];
       spec::sel_partials(c.j, c.u, &LA(X, 0), P.X0 + c.cell, Xprev_g + c.cell, part);
@@ -695,13 +698,24 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on,
     if (ev) {
       real co[6];
 #pragma unroll
-      for (int j = 0; j < 6; j++) co[j] = phase == 7 ? rkB(real(0), j) : (phase == 1 ? (real)1 : rkA(real(0), stage < 6 ? stage : 0, j < 5 ? j : 4));
+      for (int j = 0; j < 6; j++)
+        co[j] = j >= nj ? (real)0 : (phase == 7 ? rkB(real(0), j) : (phase == 1 ? (real)1 : rkA(real(0), stage < 6 ? stage : 0, j < 5 ? j : 4)));
 #pragma unroll
       for (int k = 0; k < C; k++) {
         real dy = 0;
+#ifndef EPI_HOST_EMU
+        if (sizeof(real) == 4) {
+          // co[j] is zero beyond the stages that exist and K is finite (zeroed at launch): no predicates
+          const float4 lo = *(const float4*)&KA(0, k), hi = *(const float4*)&KA(4, k);
+          dy += (real)lo.x * co[0]; dy += (real)lo.y * co[1]; dy += (real)lo.z * co[2]; dy += (real)lo.w * co[3];
+          dy += (real)hi.x * co[4]; dy += (real)hi.y * co[5];
+        } else
+#endif
+        {
 #pragma unroll
-        for (int j = 0; j < 6; j++)
-          if (j < nj) dy += LA(K, j * C + k) * co[j];
+          for (int j = 0; j < 6; j++)
+            if (j < nj) dy += KA(j, k) * co[j];
+        }
         YV(k) = (real)(LA(X, k) + (double)dy * hh);
       }
       for (int q = 0; q < nS; q++) {
@@ -727,7 +741,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on,
 #pragma unroll
         for (int k = 0; k < C; k++) {
           real yv = (real)LA(X, k), sc = atolr + fabs(yv) * rtolr;
-          real a = fdiv(yv, sc), b = fdiv(LA(K, k), sc);
+          real a = fdiv(yv, sc), b = fdiv(KA(0, k), sc);
           a0 += a * a; a1 += b * b;
         }
         {
@@ -761,7 +775,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on,
       if (on) {
 #pragma unroll
         for (int k = 0; k < C; k++) {
-          real sc = atolr + fabs((real)LA(X, k)) * rtolr, a = fdiv(LA(K, C + k) - LA(K, k), sc);
+          real sc = atolr + fabs((real)LA(X, k)) * rtolr, a = fdiv(KA(1, k) - KA(0, k), sc);
           a2 += a * a;
         }
         {
@@ -806,8 +820,18 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on,
         for (int k = 0; k < C; k++) {
           real sc = atolr + fmax(fabs((real)LA(X, k)), fabs(YV(k))) * rtolr;
           real e = 0;
+#ifndef EPI_HOST_EMU
+          if (sizeof(real) == 4) {
+            const float4 lo = *(const float4*)&KA(0, k), hi = *(const float4*)&KA(4, k);
+            e += (real)lo.x * rkE(real(0), 0); e += (real)lo.y * rkE(real(0), 1); e += (real)lo.z * rkE(real(0), 2);
+            e += (real)lo.w * rkE(real(0), 3); e += (real)hi.x * rkE(real(0), 4); e += (real)hi.y * rkE(real(0), 5);
+            e += (real)hi.z * rkE(real(0), 6);
+          } else
+#endif
+          {
 #pragma unroll
-          for (int j = 0; j < 7; j++) e += LA(K, j * C + k) * rkE(real(0), j);
+            for (int j = 0; j < 7; j++) e += KA(j, k) * rkE(real(0), j);
+          }
           real a = fdiv(e * (real)h, sc);
           ae += a * a;
         }
@@ -864,10 +888,20 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on,
 #pragma unroll
         for (int k = 0; k < C; k++) {
           real dy = 0;
+#ifndef EPI_HOST_EMU
+          if (sizeof(real) == 4) {
+            const float4 lo = *(const float4*)&KA(0, k), hi = *(const float4*)&KA(4, k);
+            dy += (real)lo.x * rkB(real(0), 0); dy += (real)lo.y * rkB(real(0), 1); dy += (real)lo.z * rkB(real(0), 2);
+            dy += (real)lo.w * rkB(real(0), 3); dy += (real)hi.x * rkB(real(0), 4); dy += (real)hi.y * rkB(real(0), 5);
+            KA(0, k) = (real)hi.z;
+          } else
+#endif
+          {
 #pragma unroll
-          for (int j = 0; j < 6; j++) dy += LA(K, j * C + k) * rkB(real(0), j);
+            for (int j = 0; j < 6; j++) dy += KA(j, k) * rkB(real(0), j);
+            KA(0, k) = KA(6, k);
+          }
           LA(X, k) = LA(X, k) + h * (double)dy;
-          LA(K, k) = LA(K, 6 * C + k);
         }
         for (int q = 0; q < nS; q++) {
           LA(X, SLOT_C1(q)) = LA(ysS, q);  // = X + h * sum_j B_j KS_j in double
@@ -925,6 +959,9 @@ __device__ __forceinline__ void step_warp(const DevPlan& P, const DevState& S, c
   if (!DIM(has_ft_ops) && c.lane < EPI_LW)
     for (int i = c.lane; i < DIM(n_lc) * DIM(F) * DIM(G) * DIM(G); i += EPI_LW)
       WT(tdc, i) = sizeof(real) == 8 ? (real)__ldg(P.Tden_const64 + i) : (real)__ldg(P.Tden_const + i);
+  // the stage-derivative column starts finite (its unused slots are multiplied by zero coefficients)
+  if (c.lane < EPI_LW)
+    for (int i = c.lane; i < 8 * C * EPI_LW; i += EPI_LW) COLP(K)[i] = 0;
   // ---- load the env's persistent state
   double* gX = S.X + e * CLG;
   real* gAcc = (real*)S.acc + e * nA + c.cell;

@@ -603,7 +603,7 @@ void build_cell_layout(epi_engine* h, int W) {
   int64_t o = 0;
   auto take = [&](int64_t bytes) { int64_t r = o; o = align16(o + bytes); return r; };
   const int64_t nS = P.has_src64 ? P.n_slot : 0;
-  Y.l_X = take(8 * C * W); Y.l_ys = take(rs * C * W); Y.l_K = take(rs * 7 * C * W);
+  Y.l_X = take(8 * C * W); Y.l_ys = take(rs * C * W); Y.l_K = take(rs * 8 * C * W);  // 8 stage slots: two 4-vectors
   Y.l_fl = take(rs * P.NSRC * W); Y.l_FBE = take(2 * rs * P.NSRC * W); Y.l_accY = take(rs * (int64_t)P.n_acc * W);
   Y.l_tdc = take(P.has_ft_ops ? 0 : rs * n_lc * F * G * G);
   Y.l_cmA = take(rs * (1 + NG) * W); Y.l_cmB = take(rs * (1 + NG) * W);
@@ -961,7 +961,7 @@ std::string gen_spec(const epi_engine* h) {
   // ---- day prologue pieces of the cell kernel: per-cell partial sums of the distinct selects, the expression
   // programs and the class-multiplier products as straight-line code (executor.py:116-164, :346-359)
   bool spec_prologue = false;
-  if (P.LG <= 32 && (int64_t)P.n_sel * 8 <= (int64_t)7 * P.C * (int64_t)h->real_size() && P.L <= 32 && P.G <= 32) {
+  if (P.LG <= 32 && (int64_t)P.n_sel * 8 <= (int64_t)2 * P.NSRC * (int64_t)h->real_size() && P.L <= 32 && P.G <= 32) {
     spec_prologue = true;
     const int NS = P.n_sel;
     std::vector<int> rep(NS);
@@ -1039,7 +1039,7 @@ std::string gen_spec(const epi_engine* h) {
   uint64_t k = 1469598103934665603ull;
   auto mix = [&](const void* p, size_t n) { for (size_t i = 0; i < n; i++) { k ^= ((const unsigned char*)p)[i]; k *= 1099511628211ull; } };
   mix(body.data(), body.size());
-  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 17 /* generator revision */};
+  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 19 /* generator revision */};
   mix(abi, sizeof abi);
   char kb[32];
   snprintf(kb, sizeof kb, "%016llx", (unsigned long long)k);
