@@ -698,8 +698,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on,
     if (ev) {
       real co[6];
 #pragma unroll
-      for (int j = 0; j < 6; j++)
-        co[j] = j >= nj ? (real)0 : (phase == 7 ? rkB(real(0), j) : (phase == 1 ? (real)1 : rkA(real(0), stage < 6 ? stage : 0, j < 5 ? j : 4)));
+      for (int j = 0; j < 6; j++) co[j] = rkCO(real(0), phase, j);  // zero beyond the stages that exist
 #pragma unroll
       for (int k = 0; k < C; k++) {
         real dy = 0;
@@ -722,7 +721,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on,
         double dy = 0;
 #pragma unroll
         for (int j = 0; j < 6; j++)
-          if (j < nj) dy += LA(KS, j * nS + q) * (phase == 7 ? RK_B[j] : (phase == 1 ? 1.0 : RK_A[stage < 6 ? stage : 0][j < 5 ? j : 4]));
+          if (j < nj) dy += LA(KS, j * nS + q) * RK_CO64[phase][j];
         LA(ysS, q) = LA(X, SLOT_C1(q)) + dy * hh;
       }
     }

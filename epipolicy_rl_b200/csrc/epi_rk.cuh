@@ -24,6 +24,23 @@ __device__ __forceinline__ double rkB(double, int j) { return RK_B[j]; }
 __device__ __forceinline__ float rkE(float, int j) { return RK_E32[j]; }
 __device__ __forceinline__ double rkE(double, int j) { return RK_E[j]; }
 
+// stage-input coefficients by phase of the RK45 state machine (epi_cell.cuh: rk45_day): y = X + hh * sum_j CO[phase][j] K_j.
+// phase 0 / 8: y = X; phase 1: X + h0 K_0; phases 2..6: row `phase - 1` of A; phase 7: B.
+#define EPI_CO_ROWS(T)                                                                                             \
+  {{0, 0, 0, 0, 0, 0},                                                                                             \
+   {1, 0, 0, 0, 0, 0},                                                                                             \
+   {(T)(1.0 / 5), 0, 0, 0, 0, 0},                                                                                  \
+   {(T)(3.0 / 40), (T)(9.0 / 40), 0, 0, 0, 0},                                                                     \
+   {(T)(44.0 / 45), (T)(-56.0 / 15), (T)(32.0 / 9), 0, 0, 0},                                                      \
+   {(T)(19372.0 / 6561), (T)(-25360.0 / 2187), (T)(64448.0 / 6561), (T)(-212.0 / 729), 0, 0},                      \
+   {(T)(9017.0 / 3168), (T)(-355.0 / 33), (T)(46732.0 / 5247), (T)(49.0 / 176), (T)(-5103.0 / 18656), 0},          \
+   {(T)(35.0 / 384), 0, (T)(500.0 / 1113), (T)(125.0 / 192), (T)(-2187.0 / 6784), (T)(11.0 / 84)},                 \
+   {0, 0, 0, 0, 0, 0}}
+__constant__ float RK_CO32[9][6] = EPI_CO_ROWS(float);
+__constant__ double RK_CO64[9][6] = EPI_CO_ROWS(double);
+__device__ __forceinline__ float rkCO(float, int ph, int j) { return RK_CO32[ph][j]; }
+__device__ __forceinline__ double rkCO(double, int ph, int j) { return RK_CO64[ph][j]; }
+
 // per-lane columns and per-env tables: element types
 #define T_X double
 #define T_ys real
