@@ -669,7 +669,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on,
   int phase = 0;
   while (phase >= 0) {
     // ---- who evaluates, where, and what is done with the flows
-    const int stage = phase <= 1 ? phase : (phase == 8 ? 0 : phase - 1);  // K slot written
+    const int stage = PH_STAGE[phase];  // K slot written
     if (phase == 2 && run) {
       // a new attempt (rk.py:111-128)
       double min_step = 10 * fabs(__longlong_as_double(__double_as_longlong(t) + 1) - t);  // nextafter(t, inf), t >= 0
@@ -687,13 +687,11 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on,
       }
     }
     const bool ev = phase <= 1 ? on : (phase == 8 ? redo : run);
-    double t_eval = 0, hh = 0;
-    int nj = 0;
-    real bw = 0, ew = 0;
-    if (phase == 1) { t_eval = h0; hh = h0; nj = 1; }
-    else if (phase >= 2 && phase <= 6) { t_eval = t + RK_C[stage] * h; hh = h; nj = stage; bw = rkB(real(0), stage); ew = rkE(real(0), stage); }
-    else if (phase == 7) { t_eval = t + h; hh = h; nj = 6; ew = rkE(real(0), 6); }
-    else if (phase == 8) { t_eval = t; bw = rkB(real(0), 0); ew = rkE(real(0), 0); }
+    // per-phase scalars from constant tables (epi_rk.cuh): no branch chains on the single warp's critical path
+    const int nj = PH_NJ[phase];
+    const double hh = phase <= 1 ? h0 : h;
+    const double t_eval = t + PH_TC[phase] * hh;
+    const real bw = phBW(real(0), phase), ew = phEW(real(0), phase);
     // ---- stage input: y = X + hh * sum_{j<nj} coef_j K_j   (coef = 1 | A[stage][:] | B[:])
     if (ev) {
       real co[6];
@@ -725,8 +723,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on,
         LA(ysS, q) = LA(X, SLOT_C1(q)) + dy * hh;
       }
     }
-    rhs<real>(P, c, ev, dyn, t_eval, ex_bits, stage, bw, ew, phase <= 1 ? 0 : (phase == 8 ? 2 : 1),
-              phase <= 1 || phase == 7
+    rhs<real>(P, c, ev, dyn, t_eval, ex_bits, stage, bw, ew, PH_ACC[phase], PH_KEEP[phase] != 0
 #ifdef EPI_SPEC
               , y
 #endif

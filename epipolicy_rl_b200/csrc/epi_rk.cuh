@@ -38,6 +38,23 @@ __device__ __forceinline__ double rkE(double, int j) { return RK_E[j]; }
    {0, 0, 0, 0, 0, 0}}
 __constant__ float RK_CO32[9][6] = EPI_CO_ROWS(float);
 __constant__ double RK_CO64[9][6] = EPI_CO_ROWS(double);
+// per-phase scalars: K slot written, number of stage terms, t_eval = t + PH_TC * hh, weights of the evaluation's
+// flows in the B / E sums, how the flow sums are updated (0 none, 1 add, 2 set), whether the flow column is kept
+__constant__ int PH_STAGE[9] = {0, 1, 1, 2, 3, 4, 5, 6, 0};
+__constant__ int PH_NJ[9] = {0, 1, 1, 2, 3, 4, 5, 6, 0};
+__constant__ double PH_TC[9] = {0, 1, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1, 1, 0};
+__constant__ int PH_ACC[9] = {0, 0, 1, 1, 1, 1, 1, 1, 2};
+__constant__ int PH_KEEP[9] = {1, 1, 0, 0, 0, 0, 0, 1, 0};
+#define EPI_PH_BW(T) {0, 0, (T)0, (T)(500.0 / 1113), (T)(125.0 / 192), (T)(-2187.0 / 6784), (T)(11.0 / 84), 0, (T)(35.0 / 384)}
+#define EPI_PH_EW(T) {0, 0, (T)0, (T)(71.0 / 16695), (T)(-71.0 / 1920), (T)(17253.0 / 339200), (T)(-22.0 / 525), (T)(1.0 / 40), (T)(-71.0 / 57600)}
+__constant__ float PH_BW32[9] = EPI_PH_BW(float);
+__constant__ double PH_BW64[9] = EPI_PH_BW(double);
+__constant__ float PH_EW32[9] = EPI_PH_EW(float);
+__constant__ double PH_EW64[9] = EPI_PH_EW(double);
+__device__ __forceinline__ float phBW(float, int ph) { return PH_BW32[ph]; }
+__device__ __forceinline__ double phBW(double, int ph) { return PH_BW64[ph]; }
+__device__ __forceinline__ float phEW(float, int ph) { return PH_EW32[ph]; }
+__device__ __forceinline__ double phEW(double, int ph) { return PH_EW64[ph]; }
 __device__ __forceinline__ float rkCO(float, int ph, int j) { return RK_CO32[ph][j]; }
 __device__ __forceinline__ double rkCO(double, int ph, int j) { return RK_CO64[ph][j]; }
 
