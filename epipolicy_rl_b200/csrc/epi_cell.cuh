@@ -144,9 +144,15 @@ __device__ __forceinline__ real acc_gather(const DevPlan& P, const real* col, in
 #ifdef EPI_SPEC
 #define Y_DECL real y[spec::C]
 #define YV(k) (y[k])
+// fp32 specialised build: the (otherwise unused) ys column holds a float copy of the state for the stage inputs,
+// y = fma(dy, h, float(X)); the state itself stays double
+#define EPI_XF (sizeof(real) == 4)
+#define XF(k) LA(ys, k)
 #else
 #define Y_DECL
 #define YV(k) LA(ys, k)
+#define EPI_XF 0
+#define XF(k) LA(ys, k)
 #endif
 
 // ------------------------------------------------------------------------------------------
@@ -713,7 +719,8 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on,
           for (int j = 0; j < 6; j++)
             if (j < nj) dy += KA(j, k) * co[j];
         }
-        YV(k) = (real)(LA(X, k) + (double)dy * hh);
+        if (EPI_XF) YV(k) = dy * (real)hh + XF(k);
+        else YV(k) = (real)(LA(X, k) + (double)dy * hh);
       }
       for (int q = 0; q < nS; q++) {
         double dy = 0;
@@ -897,10 +904,15 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on,
             for (int j = 0; j < 6; j++) dy += KA(j, k) * rkB(real(0), j);
             KA(0, k) = KA(6, k);
           }
-          LA(X, k) = LA(X, k) + h * (double)dy;
+          {
+            const double xn = LA(X, k) + h * (double)dy;
+            LA(X, k) = xn;
+            if (EPI_XF) XF(k) = (real)xn;
+          }
         }
         for (int q = 0; q < nS; q++) {
           LA(X, SLOT_C1(q)) = LA(ysS, q);  // = X + h * sum_j B_j KS_j in double
+          if (EPI_XF) XF(SLOT_C1(q)) = (real)LA(ysS, q);
           LA(KS, q) = LA(KS, 6 * nS + q);
         }
         {
@@ -964,7 +976,11 @@ __device__ __forceinline__ void step_warp(const DevPlan& P, const DevState& S, c
   double* gXprev = S.Xprev + e * P.n_chg * LG;
   int* meta = S.meta + e * 8;
   if (on0) {
-    for (int k = 0; k < C; k++) LA(X, k) = gX[k * LG + c.cell];
+    for (int k = 0; k < C; k++) {
+      const double x = gX[k * LG + c.cell];
+      LA(X, k) = x;
+      if (EPI_XF) XF(k) = (real)x;
+    }
     for (int s = 0; s < DIM(n_slot); s++) LA(mvY, s) = S.mvY[e * nM + s * LG + c.cell];
     for (int a_ = 0; a_ < DIM(n_acc); a_++) LA(accY, a_) = gAcc[a_ * LG];
     for (int i = c.cell; i < nC; i += LG) {
