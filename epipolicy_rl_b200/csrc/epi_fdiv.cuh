@@ -15,7 +15,7 @@ __device__ __forceinline__ float fdiv(float a, float b) { return a / b; }
 __device__ __forceinline__ double ctrl_pow(float, double x, double p) { return (double)powf((float)x, (float)p); }
 #else
 __device__ __forceinline__ float frcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return a * frcp(b); }  // MUFU.RCP + FMUL, ~2 ulp
 __device__ __forceinline__ double ctrl_pow(float, double x, double p) { return (double)__powf((float)x, (float)p); }
 #endif
 }  // namespace epi
