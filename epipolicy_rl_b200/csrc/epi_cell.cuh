@@ -759,15 +759,15 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on,
         s0 = (double)a0; s1 = (double)a1;
         for (int i = c.cell; i < nC; i += LG) {
           double yv = EV(cost, i), sc = atol + fabs(yv) * rtol;
-          double a = yv / sc, b = EV(crY, i) / sc;  // q(0) = 0
+          double a = norm_term(real(0), yv, sc), b = norm_term(real(0), EV(crY, i), sc);  // q(0) = 0
           s0 += a * a; s1 += b * b;
         }
         for (int i = 0; i < NSRC; i++) LA(FBE, i).y = LA(fl, i);  // stage-0 flows, needed once more in phase 1
       }
       TEAM_SUM(d0, s0, on);
       TEAM_SUM(d1, s1, on);
-      d0 = sqrt(d0 * inv_n);
-      d1 = sqrt(d1 * inv_n);
+      d0 = ctrl_sqrt(real(0), d0 * inv_n);
+      d1 = ctrl_sqrt(real(0), d1 * inv_n);
       h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
       h0 = fmin(h0, 1.0);
       nfev++;
@@ -793,7 +793,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on,
         }
         s2 = (double)a2;
         for (int i = c.cell; i < nC; i += LG) {
-          double sc = atol + fabs(EV(cost, i)) * rtol, a = ((EV(crD, i) - EV(crY, i)) * q0) / sc;
+          double sc = atol + fabs(EV(cost, i)) * rtol, a = norm_term(real(0), (EV(crD, i) - EV(crY, i)) * q0, sc);
           s2 += a * a;
         }
         // stage-0 contributions of the first attempt
@@ -806,7 +806,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on,
         }
       }
       TEAM_SUM(d2, s2, on);
-      d2 = sqrt(d2 * inv_n) / h0;
+      d2 = ctrl_sqrt(real(0), d2 * inv_n) / h0;
       double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : ctrl_pow(real(0), 0.01 / fmax(d1, d2), 0.2);
       h_abs = fmin(fmin(100 * h0, h1), 1.0);
       nfev++;
@@ -860,13 +860,13 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on,
             se += k * RK_E[j];
           }
           double yv = EV(cost, i), yn = yv + h * sb;
-          double sc = atol + fmax(fabs(yv), fabs(yn)) * rtol, a = se * h / sc;
+          double sc = atol + fmax(fabs(yv), fabs(yn)) * rtol, a = norm_term(real(0), se * h, sc);
           e2 += a * a;
         }
       }
       double err;
       TEAM_SUM(err, e2, run);
-      err = sqrt(err * inv_n);
+      err = ctrl_sqrt(real(0), err * inv_n);
       bool accepted = false;
       if (run) {
         last_err = err;
