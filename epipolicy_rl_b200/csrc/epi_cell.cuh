@@ -723,11 +723,15 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on,
         else YV(k) = (real)(LA(X, k) + (double)dy * hh);
       }
       for (int q = 0; q < nS; q++) {
-        double dy = 0;
+        // (fp32 mode only) the double-carried move sources: coefficients are zero beyond the stages that exist
+        // and the slots are finite (zeroed at launch), so no predicates; two partial sums halve the DFMA chain
+        double dy0 = 0, dy1 = 0;
 #pragma unroll
-        for (int j = 0; j < 6; j++)
-          if (j < nj) dy += LA(KS, j * nS + q) * RK_CO64[phase][j];
-        LA(ysS, q) = LA(X, SLOT_C1(q)) + dy * hh;
+        for (int j = 0; j < 6; j += 2) {
+          dy0 += LA(KS, j * nS + q) * RK_CO64[phase][j];
+          dy1 += LA(KS, (j + 1) * nS + q) * RK_CO64[phase][j + 1];
+        }
+        LA(ysS, q) = LA(X, SLOT_C1(q)) + (dy0 + dy1) * hh;
       }
     }
     rhs<real>(P, c, ev, dyn, t_eval, ex_bits, stage, bw, ew, PH_ACC[phase], PH_KEEP[phase] != 0
@@ -968,8 +972,11 @@ __device__ __forceinline__ void step_warp(const DevPlan& P, const DevState& S, c
     for (int i = c.lane; i < DIM(n_lc) * DIM(F) * DIM(G) * DIM(G); i += EPI_LW)
       WT(tdc, i) = sizeof(real) == 8 ? (real)__ldg(P.Tden_const64 + i) : (real)__ldg(P.Tden_const + i);
   // the stage-derivative column starts finite (its unused slots are multiplied by zero coefficients)
-  if (c.lane < EPI_LW)
+  if (c.lane < EPI_LW) {
     for (int i = c.lane; i < 8 * C * EPI_LW; i += EPI_LW) COLP(K)[i] = 0;
+    if (DIM(has_src64))
+      for (int i = c.lane; i < 7 * DIM(n_slot) * EPI_LW; i += EPI_LW) COLP(KS)[i] = 0;
+  }
   // ---- load the env's persistent state
   double* gX = S.X + e * CLG;
   real* gAcc = (real*)S.acc + e * nA + c.cell;
