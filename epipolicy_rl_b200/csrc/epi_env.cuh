@@ -613,7 +613,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
 
   int phase = 0;
   while (phase >= 0) {
-    const int stage = phase <= 1 ? phase : (phase == 8 ? 0 : phase - 1);  // K slot written
+    const int stage = PH_STAGE[phase];  // K slot written
     if (phase == 2) {
       // a new attempt (rk.py:111-128)
       double min_step = 10 * fabs(__longlong_as_double(__double_as_longlong(t) + 1) - t);  // nextafter(t, inf), t >= 0
@@ -629,21 +629,19 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
       h = t_new - t;
       h_abs = fabs(h);
     }
-    double t_eval = 0, hh = 0;
-    int nj = 0;
-    real bw = 0, ew = 0;
-    if (phase == 1) { t_eval = h0; hh = h0; nj = 1; }
-    else if (phase >= 2 && phase <= 6) { t_eval = t + RK_C[stage] * h; hh = h; nj = stage; bw = rkB(real(0), stage); ew = rkE(real(0), stage); }
-    else if (phase == 7) { t_eval = t + h; hh = h; nj = 6; ew = rkE(real(0), 6); }
-    else if (phase == 8) { t_eval = t; bw = rkB(real(0), 0); ew = rkE(real(0), 0); }
+    // per-phase scalars and stage-input coefficients from constant tables (epi_rk.cuh)
+    const int nj = PH_NJ[phase];
+    const double hh = phase <= 1 ? h0 : h;
+    const double t_eval = t + PH_TC[phase] * hh;
+    const real bw = phBW(real(0), phase), ew = phEW(real(0), phase);
     real co[6];
     double coS[6];
 #pragma unroll
     for (int j = 0; j < 6; j++) {
-      co[j] = phase == 7 ? rkB(real(0), j) : (phase == 1 ? (real)1 : rkA(real(0), stage < 6 ? stage : 0, j < 5 ? j : 4));
-      coS[j] = phase == 7 ? RK_B[j] : (phase == 1 ? 1.0 : RK_A[stage < 6 ? stage : 0][j < 5 ? j : 4]);
+      co[j] = rkCO(real(0), phase, j);
+      coS[j] = RK_CO64[phase][j];
     }
-    rhs<real>(P, b, dyn, t_eval, ex_bits, stage, bw, ew, phase <= 1 ? 0 : (phase == 8 ? 2 : 1), phase <= 1 || phase == 7,
+    rhs<real>(P, b, dyn, t_eval, ex_bits, stage, bw, ew, PH_ACC[phase], PH_KEEP[phase] != 0,
               hh, nj, co, coS, ps(stage));
     if (phase == 0) {
       // select_initial_step (common.py:68-134), first half
@@ -679,11 +677,11 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
       }
       for (int i = b.tid; i < nC; i += b.nt) {
         double yv = b.cost[i], sc = atol + fabs(yv) * rtol;
-        double a = yv / sc, bq = b.crY[i] / sc;  // q(0) = 0
+        double a = norm_term(real(0), yv, sc), bq = norm_term(real(0), b.crY[i], sc);  // q(0) = 0
         s0 += a * a; s1 += bq * bq;
       }
-      d0 = sqrt(block_sum(b, s0) * inv_n);
-      d1 = sqrt(block_sum(b, s1) * inv_n);
+      d0 = ctrl_sqrt(real(0), block_sum(b, s0) * inv_n);
+      d1 = ctrl_sqrt(real(0), block_sum(b, s1) * inv_n);
       h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
       h0 = fmin(h0, 1.0);
       nfev++;
@@ -727,10 +725,10 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
         }
       }
       for (int i = b.tid; i < nC; i += b.nt) {
-        double sc = atol + fabs(b.cost[i]) * rtol, a = ((b.crD[i] - b.crY[i]) * q0) / sc;
+        double sc = atol + fabs(b.cost[i]) * rtol, a = norm_term(real(0), (b.crD[i] - b.crY[i]) * q0, sc);
         s2 += a * a;
       }
-      double d2 = sqrt(block_sum(b, s2) * inv_n) / h0;
+      double d2 = ctrl_sqrt(real(0), block_sum(b, s2) * inv_n) / h0;
       double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : ctrl_pow(real(0), 0.01 / fmax(d1, d2), 0.2);
       h_abs = fmin(fmin(100 * h0, h1), 1.0);
       nfev++;
@@ -816,10 +814,10 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
           se += k * RK_E[j];
         }
         double yv = b.cost[i], yn = yv + h * sb;
-        double sc = atol + fmax(fabs(yv), fabs(yn)) * rtol, a = se * h / sc;
+        double sc = atol + fmax(fabs(yv), fabs(yn)) * rtol, a = norm_term(real(0), se * h, sc);
         e2 += a * a;
       }
-      double err = sqrt(block_sum(b, e2) * inv_n);
+      double err = ctrl_sqrt(real(0), block_sum(b, e2) * inv_n);
       last_err = err;
       if (dbg && b.tid == 0 && n_att < 64) { dbg[2 * n_att] = h; dbg[2 * n_att + 1] = err; }
       n_att++;
