@@ -226,3 +226,17 @@ def test_specialised_kernel_equals_interpreted_kernel(prec, monkeypatch):
     assert np.allclose(r1.cpu().numpy(), r2.cpu().numpy(), rtol=tol)
     es.close()
     eg.close()
+
+
+def test_batched_ppo_runs_on_device():
+    """The in-repo learner (learner.py) on GPU-resident envs: two PPO updates on COVID_A, everything on the device."""
+    from epipolicy_rl_b200.env import BatchedEpiEnv
+    from epipolicy_rl_b200.learner import BatchedPPO
+    d, _ = load("COVID_A")
+    env = BatchedEpiEnv(d, 256, device=0, precision="fp32", auto_reset=False)
+    pop = np.broadcast_to(d.pop.reshape(1, d.L, d.G), (d.C, d.L, d.G)).reshape(-1)
+    ppo = BatchedPPO(env, env.epi.obs_dim, d.A, obs_scale=pop, n_steps=8, n_epochs=2, device="cuda:0")
+    hist = ppo.train(2)
+    assert len(hist) == 2 and all(np.isfinite(h["mean_step_reward"]) and h["mean_step_reward"] < 0 for h in hist)
+    assert np.isfinite(hist[-1]["v_loss"])
+    env.close()
