@@ -43,7 +43,8 @@ __constant__ double RK_CO64[9][6] = EPI_CO_ROWS(double);
 __constant__ int PH_STAGE[9] = {0, 1, 1, 2, 3, 4, 5, 6, 0};
 __constant__ int PH_NJ[9] = {0, 1, 1, 2, 3, 4, 5, 6, 0};
 __constant__ double PH_TC[9] = {0, 1, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1, 1, 0};
-__constant__ int PH_ACC[9] = {0, 0, 1, 1, 1, 1, 1, 1, 2};
+// (stage 1 has B = E = 0: its flows enter neither sum)
+__constant__ int PH_ACC[9] = {0, 0, 0, 1, 1, 1, 1, 1, 2};
 __constant__ int PH_KEEP[9] = {1, 1, 0, 0, 0, 0, 0, 1, 0};
 #define EPI_PH_BW(T) {0, 0, (T)0, (T)(500.0 / 1113), (T)(125.0 / 192), (T)(-2187.0 / 6784), (T)(11.0 / 84), 0, (T)(35.0 / 384)}
 #define EPI_PH_EW(T) {0, 0, (T)0, (T)(71.0 / 16695), (T)(-71.0 / 1920), (T)(17253.0 / 339200), (T)(-22.0 / 525), (T)(1.0 / 40), (T)(-71.0 / 57600)}
