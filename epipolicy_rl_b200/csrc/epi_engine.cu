@@ -927,14 +927,14 @@ std::string gen_spec(const epi_engine* h) {
     auto scatter = [&](int src) {
       for (auto& pr : sc_of[src]) o << " d[" << pr.first << "] += f * " << hexf(pr.second) << ";";
     };
-    o << "__device__ __forceinline__ void flows_scatter(const real* y, real alive, const float* mp, const real* rs, real* out, size_t stride, real* d) {\n";
+    o << "__device__ __forceinline__ void flows_scatter(const real* y, real alive, const float* mp, const real* rs, real* out, size_t stride, real* d, bool st) {\n";
     for (int c = 0; c < P.C; c++) o << "  d[" << c << "] = 0;\n";
     if (h->precision == EPI_FP32) {
       for (auto& dc : rdecl) o << "  real " << dc.first << "; { real dn = 0;" << dc.second << " " << dc.first << " = frcp(dn); }\n";
       rcp_of = &rmap;
     }
     for (int k = 0; k < P.NG; k++) {
-      o << "  { real f = y[" << T.ig_c0[k] << "] * rs[" << k << "]; out[" << P.E + k << " * stride] = f;";
+      o << "  { real f = y[" << T.ig_c0[k] << "] * rs[" << k << "]; if (st) out[" << P.E + k << " * stride] = f;";
       scatter(P.E + k);
       o << " }\n";
     }
@@ -945,7 +945,7 @@ std::string gen_spec(const epi_engine* h) {
       for (int q = 0; q < n; q++) o << " * " << val(*ep++);
       o << ";";
       emit_denominator(o, ep, val, "f");
-      o << "    out[" << e << " * stride] = f;";
+      o << "    if (st) out[" << e << " * stride] = f;";
       scatter(e);
       o << " }\n";
     }
@@ -1039,7 +1039,7 @@ std::string gen_spec(const epi_engine* h) {
   uint64_t k = 1469598103934665603ull;
   auto mix = [&](const void* p, size_t n) { for (size_t i = 0; i < n; i++) { k ^= ((const unsigned char*)p)[i]; k *= 1099511628211ull; } };
   mix(body.data(), body.size());
-  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 19 /* generator revision */};
+  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 21 /* generator revision */};
   mix(abi, sizeof abi);
   char kb[32];
   snprintf(kb, sizeof kb, "%016llx", (unsigned long long)k);

@@ -275,7 +275,8 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Bx& b, bool dyn, dou
 #pragma unroll
       for (int k = 0; k < C; k++) y[k] = BA(ys, k);
       real* out = &BA(fls, (size_t)fslot * spec::NSRC);
-      spec::flows_scatter(y, alive, mp, rs, out, (size_t)LG, d);
+      const bool st = keep_fl || kslot != 1;  // stage 1 of an attempt has B = E = 0: its flows are never combined
+      spec::flows_scatter(y, alive, mp, rs, out, (size_t)LG, d, st);
 #pragma unroll
       for (int sl = 0; sl < spec::n_slot; sl++) {
         real nv = 0;
@@ -295,7 +296,7 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Bx& b, bool dyn, dou
         } else if (spec::has_src64) {
           BA(KS, kslot * spec::n_slot + sl) = (double)d[c1];
         }
-        out[(size_t)(nE + NG + sl) * LG] = nv;
+        if (st) out[(size_t)(nE + NG + sl) * LG] = nv;
       }
 #pragma unroll
       for (int k = 0; k < C; k++) BA(K, k0 + k) = d[k];
@@ -766,6 +767,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
               real sb = 0, se = 0;
 #pragma unroll
               for (int st = 0; st < 7; st++) {
+                if (st == 1) continue;  // B[1] = E[1] = 0 (and the slot is not written)
                 real f = BA(fls, so[st] + src);
                 sb += rkB(real(0), st) * f;
                 se += rkE(real(0), st) * f;
@@ -778,6 +780,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
               const int src = __ldg(P.ag_src + q);
               real sb = 0, se = 0;
               for (int st = 0; st < 7; st++) {
+                if (st == 1) continue;  // B[1] = E[1] = 0
                 real f = BA(fls, so[st] + src);
                 sb += rkB(real(0), st) * f;
                 se += rkE(real(0), st) * f;
