@@ -627,7 +627,10 @@ void build_cell_layout(epi_engine* h, int W) {
 }
 
 
-int env_threads(int LG) { return LG >= 256 ? 256 : ((LG + 31) / 32) * 32; }
+int env_threads(int LG) {
+  if (const char* ov = getenv("EPI_ENV_THREADS")) { int v = atoi(ov); if (v >= 32 && v <= 256 && v % 32 == 0) return v; }  // tuning aid
+  return LG >= 256 ? 256 : ((LG + 31) / 32) * 32;
+}
 
 // layout of the env kernel (epi_env.cuh) for CTAs of `threads` threads
 void build_env_layout(epi_engine* h, int threads, int64_t smem_max) {
@@ -1039,7 +1042,7 @@ std::string gen_spec(const epi_engine* h) {
   uint64_t k = 1469598103934665603ull;
   auto mix = [&](const void* p, size_t n) { for (size_t i = 0; i < n; i++) { k ^= ((const unsigned char*)p)[i]; k *= 1099511628211ull; } };
   mix(body.data(), body.size());
-  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 21 /* generator revision */};
+  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 22 /* generator revision */};
   mix(abi, sizeof abi);
   char kb[32];
   snprintf(kb, sizeof kb, "%016llx", (unsigned long long)k);
@@ -1047,7 +1050,7 @@ std::string gen_spec(const epi_engine* h) {
          kb + "\"\n#define EPI_SPEC_BIG " + (P.LG > 32 ? "1" : "0") + "\n" +
          "#define EPI_SPEC_PROLOGUE " + (spec_prologue ? "1" : "0") + "\n" +
          "#define EPI_SPEC_ROLES " + std::to_string(P.cl.roles > 0 ? P.cl.roles : 1) + "\n" +
-         (P.LG > 32 ? std::string("#define EPI_ENV_MINB ") + (P.el.big_in_smem ? "2" : "4") + "\n" : std::string()) + body;
+         (P.LG > 32 ? std::string("#define EPI_ENV_MINB ") + std::to_string((P.el.big_in_smem ? 512 : 1024) / (P.el.threads > 0 ? P.el.threads : 256)) + "\n" : std::string()) + body;
 }
 
 void alloc_state(epi_engine* h, DevState& S, int N) {
