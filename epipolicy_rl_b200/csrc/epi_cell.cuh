@@ -1050,12 +1050,23 @@ __device__ __forceinline__ void step_warp(const DevPlan& P, const DevState& S, c
     if (on && t_day >= P.horizon) on = false;  // the reference's EpiEnv.step stops its day loop at done
   }
   // ---- store
-  if (on0) {
-    for (int k = 0; k < C; k++) {
-      double x = LA(X, k);
-      gX[k * LG + c.cell] = x;
-      if (a.obs_out) ((real*)a.obs_out)[e * CLG + k * LG + c.cell] = (real)x;
+  if (a.obs_out) {
+    // the observations of the warp's envs are one contiguous [EPW][C*L*G] block: lanes write consecutive words
+    // (full lines - this matters when obs_out is mapped host memory, epi_step_host) from the [k][lane] state column
+#ifdef EPI_HOST_EMU
+    const int nthr = EPI_LW;
+#else
+    const int nthr = 32;
+#endif
+    const int e0 = group * P.cl.epw, nv = a.N - e0 < P.cl.epw ? a.N - e0 : P.cl.epw;
+    real* out = (real*)a.obs_out + (size_t)e0 * CLG;
+    for (int idx = lane; idx < nv * CLG; idx += nthr) {
+      const int sl = idx / CLG, rem = idx - sl * CLG, k = rem / LG, cl = rem - k * LG;
+      out[idx] = (real)LO(X, k, sl * LG + cl);
     }
+  }
+  if (on0) {
+    for (int k = 0; k < C; k++) gX[k * LG + c.cell] = LA(X, k);
     for (int s = 0; s < DIM(n_slot); s++) S.mvY[e * nM + s * LG + c.cell] = LA(mvY, s);
     for (int a_ = 0; a_ < DIM(n_acc); a_++) gAcc[a_ * LG] = LA(accY, a_);
     for (int i = c.cell; i < nC; i += LG) {

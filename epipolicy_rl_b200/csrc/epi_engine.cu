@@ -76,6 +76,10 @@ struct epi_engine {
   void* h_obs = nullptr; void* d_obs = nullptr;
   double* h_rew = nullptr; double* d_rew = nullptr;
   uint8_t* h_done = nullptr; uint8_t* d_done = nullptr;
+  // device-side addresses of the pinned (mapped) host buffers: the kernel reads actions from / writes results to
+  // host memory directly over PCIe (EPI_HOST_ZEROCOPY: bit 0 results, bit 1 actions)
+  float* m_act = nullptr; void* m_obs = nullptr; double* m_rew = nullptr; uint8_t* m_done = nullptr;
+  int zerocopy = 1;
   cudaStream_t stream = nullptr;
   mutable std::string err;
   double* dbg_attempts = nullptr;   // [N,64,2], allocated on first use of state selector 9
@@ -1273,10 +1277,13 @@ void do_reset(epi_engine* h, const uint8_t* mask, void* obs_out, cudaStream_t st
 void ensure_host_buffers(epi_engine* h) {
   if (h->h_act) return;
   const size_t N = h->N, A = h->plan.A ? h->plan.A : 1, rs = h->real_size(), CLG = h->plan.CLG;
-  CK(cudaMallocHost(&h->h_act, N * A * 4)); h->d_act = h->dalloc<float>(N * A);
-  CK(cudaMallocHost(&h->h_obs, N * CLG * rs)); h->d_obs = h->dalloc<char>(N * CLG * rs);
-  CK(cudaMallocHost(&h->h_rew, N * 8)); h->d_rew = h->dalloc<double>(N);
-  CK(cudaMallocHost(&h->h_done, N)); h->d_done = h->dalloc<uint8_t>(N);
+  CK(cudaHostAlloc(&h->h_act, N * A * 4, cudaHostAllocMapped)); h->d_act = h->dalloc<float>(N * A);
+  CK(cudaHostAlloc(&h->h_obs, N * CLG * rs, cudaHostAllocMapped)); h->d_obs = h->dalloc<char>(N * CLG * rs);
+  CK(cudaHostAlloc(&h->h_rew, N * 8, cudaHostAllocMapped)); h->d_rew = h->dalloc<double>(N);
+  CK(cudaHostAlloc(&h->h_done, N, cudaHostAllocMapped)); h->d_done = h->dalloc<uint8_t>(N);
+  CK(cudaHostGetDevicePointer((void**)&h->m_act, h->h_act, 0)); CK(cudaHostGetDevicePointer(&h->m_obs, h->h_obs, 0));
+  CK(cudaHostGetDevicePointer((void**)&h->m_rew, h->h_rew, 0)); CK(cudaHostGetDevicePointer((void**)&h->m_done, h->h_done, 0));
+  if (const char* z = getenv("EPI_HOST_ZEROCOPY")) h->zerocopy = atoi(z);
   // dalloc's cudaMemset runs on the legacy default stream, which h->stream (non-blocking) does not wait for
   CK(cudaDeviceSynchronize());
 }
@@ -1438,17 +1445,24 @@ int epi_step_host(epi_t* h, const float* actions_host, int n_days, void* obs_out
     CK(cudaSetDevice(h->device));
     const size_t N = h->N, rs = h->real_size(), CLG = h->plan.CLG;
     ensure_host_buffers(h);
+    // The buffers are pinned and mapped: by default the kernel epilogue writes obs / reward / done straight into host
+    // memory (posted PCIe writes that overlap the envs still being stepped) and no copy is enqueued behind the launch;
+    // the actions (24 B per env) are read by the kernel head the same way when bit 1 is set.
+    const bool zc_out = h->zerocopy & 1, zc_act = h->zerocopy & 2;
     if (h->plan.A > 0) {
       if (actions_host != h->h_act) memcpy(h->h_act, actions_host, N * h->plan.A * 4);
-      CK(cudaMemcpyAsync(h->d_act, h->h_act, N * h->plan.A * 4, cudaMemcpyHostToDevice, h->stream));
+      if (!zc_act) CK(cudaMemcpyAsync(h->d_act, h->h_act, N * h->plan.A * 4, cudaMemcpyHostToDevice, h->stream));
     }
     epi::StepArgs a{};
-    a.actions = h->d_act; a.variant = 0; a.n_days = n_days; a.N = h->N;
-    a.obs_out = obs_out_host ? h->d_obs : nullptr; a.reward_out = h->d_rew; a.done_out = h->d_done;
+    a.actions = zc_act ? h->m_act : h->d_act; a.variant = 0; a.n_days = n_days; a.N = h->N;
+    a.obs_out = obs_out_host ? (zc_out ? h->m_obs : h->d_obs) : nullptr;
+    a.reward_out = zc_out ? h->m_rew : h->d_rew; a.done_out = zc_out ? h->m_done : h->d_done;
     launch(h, h->S, a, h->stream);
-    if (obs_out_host) CK(cudaMemcpyAsync(h->h_obs, h->d_obs, N * CLG * rs, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->h_rew, h->d_rew, N * 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->h_done, h->d_done, N, cudaMemcpyDeviceToHost, h->stream));
+    if (!zc_out) {
+      if (obs_out_host) CK(cudaMemcpyAsync(h->h_obs, h->d_obs, N * CLG * rs, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpyAsync(h->h_rew, h->d_rew, N * 8, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpyAsync(h->h_done, h->d_done, N, cudaMemcpyDeviceToHost, h->stream));
+    }
     CK(cudaStreamSynchronize(h->stream));
     // callers that use the library's own pinned buffers (epi_host_buffers) read the results in place
     if (obs_out_host && obs_out_host != h->h_obs) memcpy(obs_out_host, h->h_obs, N * CLG * rs);

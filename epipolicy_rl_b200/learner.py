@@ -164,3 +164,186 @@ class BatchedPPO:
             if log and self.rank == 0:
                 log(st)
         return hist
+
+
+# ----------------------------------------------------------------------------------------------
+# SAC (runner.py --algo sac; algorithm as the reference's in-house optimizer/sac.py:44-341: replay buffer,
+# twin Q functions with Polyak-averaged targets, squashed Gaussian policy; hyper-parameters as
+# configs/sac_default.yaml) restated for a batch of GPU-resident envs: the replay buffer is a ring of device
+# tensors fed N transitions per gym step, actions are squashed into the env's Box(0, 1) action space.
+# ----------------------------------------------------------------------------------------------
+def _mlp(inp: int, out: int, hidden=(256, 256)):
+    layers, d = [], inp
+    for h in hidden:
+        layers += [nn.Linear(d, h), nn.ReLU()]
+        d = h
+    return nn.Sequential(*layers, nn.Linear(d, out))
+
+
+class SquashedGaussianActor(nn.Module):
+    LOG_STD_MIN, LOG_STD_MAX = -20.0, 2.0
+
+    def __init__(self, obs_dim: int, act_dim: int, hidden=(256, 256)):
+        super().__init__()
+        self.net = _mlp(obs_dim, 2 * act_dim, hidden)
+
+    def forward(self, obs, deterministic: bool = False, with_logprob: bool = True):
+        mu, log_std = self.net(obs).chunk(2, -1)
+        log_std = log_std.clamp(self.LOG_STD_MIN, self.LOG_STD_MAX)
+        u = mu if deterministic else mu + log_std.exp() * torch.randn_like(mu)
+        a = 0.5 * (torch.tanh(u) + 1.0)  # Box(0, 1)
+        logp = None
+        if with_logprob:
+            # N(u; mu, std) with the change of variables a = (tanh(u) + 1) / 2:  da/du = (1 - tanh(u)^2) / 2
+            logp = (-0.5 * ((u - mu) / log_std.exp()) ** 2 - log_std - 0.5 * math.log(2 * math.pi)).sum(-1)
+            logp = logp - (2.0 * (math.log(2.0) - u - nn.functional.softplus(-2.0 * u)) - math.log(2.0)).sum(-1)
+        return a, logp
+
+
+class ReplayRing:
+    """Fixed-size ring of transitions in device memory; `store` takes a whole batch of envs at once."""
+
+    def __init__(self, obs_dim: int, act_dim: int, size: int, device):
+        self.o = torch.zeros((size, obs_dim), device=device)
+        self.o2 = torch.zeros((size, obs_dim), device=device)
+        self.a = torch.zeros((size, act_dim), device=device)
+        self.r = torch.zeros(size, device=device)
+        self.d = torch.zeros(size, device=device)
+        self.size, self.ptr, self.n = size, 0, 0
+
+    def store(self, o, a, r, o2, d):
+        m = o.shape[0]
+        if m > self.size:
+            o, a, r, o2, d = (x[-self.size:] for x in (o, a, r, o2, d))
+            m = self.size
+        idx = (self.ptr + torch.arange(m, device=self.o.device)) % self.size
+        self.o[idx], self.a[idx], self.r[idx], self.o2[idx], self.d[idx] = o, a, r, o2, d
+        self.ptr = (self.ptr + m) % self.size
+        self.n = min(self.size, self.n + m)
+
+    def sample(self, batch: int):
+        idx = torch.randint(0, self.n, (batch,), device=self.o.device)
+        return self.o[idx], self.a[idx], self.r[idx], self.o2[idx], self.d[idx]
+
+
+class BatchedSAC:
+    """SAC on a BatchedEpiEnv-like object (same env protocol as BatchedPPO). Multi-GPU: every rank steps its shard
+    with an actor replica; one all-gather per gym step delivers the packed transitions; rank 0 owns the replay ring,
+    runs the gradient steps and broadcasts the actor."""
+
+    def __init__(self, env, obs_dim: int, act_dim: int, obs_scale, gamma: float = 0.9, tau: float = 0.1,
+                 lr: float = 3e-3, batch_size: int = 256, buffer_size: int = 1 << 20, learning_starts: int = 0,
+                 gradient_steps: int = 4, target_entropy: float | None = None, reward_scale: float = 1e-7,
+                 device="cuda", seed: int = 10):
+        torch.manual_seed(seed)
+        self.env, self.dev = env, torch.device(device)
+        self.obs_scale = torch.as_tensor(obs_scale, dtype=torch.float32, device=self.dev)
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.actor = SquashedGaussianActor(obs_dim, act_dim).to(self.dev)
+        self.q1, self.q2 = _mlp(obs_dim + act_dim, 1).to(self.dev), _mlp(obs_dim + act_dim, 1).to(self.dev)
+        self.q1_t, self.q2_t = _mlp(obs_dim + act_dim, 1).to(self.dev), _mlp(obs_dim + act_dim, 1).to(self.dev)
+        self.q1_t.load_state_dict(self.q1.state_dict()); self.q2_t.load_state_dict(self.q2.state_dict())
+        for p in list(self.q1_t.parameters()) + list(self.q2_t.parameters()):
+            p.requires_grad_(False)
+        self.log_alpha = torch.zeros((), device=self.dev, requires_grad=True)
+        self.target_entropy = float(-act_dim if target_entropy is None else target_entropy)
+        self.opt_pi = torch.optim.Adam(self.actor.parameters(), lr=lr)
+        self.opt_q = torch.optim.Adam(list(self.q1.parameters()) + list(self.q2.parameters()), lr=lr)
+        self.opt_alpha = torch.optim.Adam([self.log_alpha], lr=lr)
+        self.gamma, self.tau, self.batch_size, self.gradient_steps = gamma, tau, batch_size, gradient_steps
+        self.learning_starts, self.reward_scale = learning_starts, reward_scale
+        self.ring = ReplayRing(obs_dim, act_dim, buffer_size, self.dev) if self.rank == 0 else None
+        self._obs, self.total_steps = None, 0
+        self.ep_return, self.finished_returns = None, []
+
+    def _norm(self, obs):
+        return obs.to(torch.float32) / self.obs_scale
+
+    def _all(self, x):
+        if self.world == 1:
+            return x
+        out = [torch.empty_like(x) for _ in range(self.world)]
+        dist.all_gather(out, x.contiguous())
+        return torch.cat(out, 0)
+
+    @torch.no_grad()
+    def collect_step(self):
+        """one gym step of every env; the transitions of all shards land in the learner's ring"""
+        if self._obs is None:
+            self._obs = self.env.reset().clone()
+            self.ep_return = torch.zeros(self._obs.shape[0], dtype=torch.float64, device=self.dev)
+        o = self._norm(self._obs)
+        if self.total_steps < self.learning_starts:
+            a = torch.rand((o.shape[0], self.actor.net[-1].out_features // 2), device=self.dev)
+        else:
+            a, _ = self.actor(o, with_logprob=False)
+        obs, rew, done, _ = self.env.step(a.contiguous())
+        o2 = self._norm(obs)  # the terminal observation, before any reset
+        self.ep_return += rew
+        d = done.to(torch.bool)
+        if d.any():
+            self.finished_returns += self.ep_return[d].tolist()
+            self.ep_return[d] = 0
+            self.env.reset(done)
+            obs = self.env.epi.obs
+        r = rew.to(torch.float32) * self.reward_scale
+        rec = self._all(torch.cat([o, a, r[:, None], o2, d.to(torch.float32)[:, None]], 1))
+        if self.rank == 0:
+            nd, na = o.shape[1], a.shape[1]
+            self.ring.store(rec[:, :nd], rec[:, nd:nd + na], rec[:, nd + na], rec[:, nd + na + 1:2 * nd + na + 1],
+                            rec[:, 2 * nd + na + 1])
+        self._obs = obs.clone()
+        self.total_steps += rec.shape[0]
+        return float(rew.mean())
+
+    def update(self):
+        stats = {}
+        if self.rank == 0 and self.ring.n >= self.batch_size and self.total_steps >= self.learning_starts:
+            for _ in range(self.gradient_steps):
+                o, a, r, o2, d = self.ring.sample(self.batch_size)
+                alpha = self.log_alpha.exp().detach()
+                with torch.no_grad():
+                    a2, logp2 = self.actor(o2)
+                    oa2 = torch.cat([o2, a2], -1)
+                    q_t = torch.min(self.q1_t(oa2), self.q2_t(oa2)).squeeze(-1)
+                    backup = r + self.gamma * (1.0 - d) * (q_t - alpha * logp2)
+                oa = torch.cat([o, a], -1)
+                loss_q = ((self.q1(oa).squeeze(-1) - backup) ** 2).mean() + ((self.q2(oa).squeeze(-1) - backup) ** 2).mean()
+                self.opt_q.zero_grad(set_to_none=True)
+                loss_q.backward()
+                self.opt_q.step()
+                pi, logp = self.actor(o)
+                op = torch.cat([o, pi], -1)
+                loss_pi = (alpha * logp - torch.min(self.q1(op), self.q2(op)).squeeze(-1)).mean()
+                self.opt_pi.zero_grad(set_to_none=True)
+                loss_pi.backward()
+                self.opt_pi.step()
+                loss_alpha = -(self.log_alpha * (logp.detach() + self.target_entropy).mean())
+                self.opt_alpha.zero_grad(set_to_none=True)
+                loss_alpha.backward()
+                self.opt_alpha.step()
+                with torch.no_grad():
+                    for net, tgt in ((self.q1, self.q1_t), (self.q2, self.q2_t)):
+                        for p, pt in zip(net.parameters(), tgt.parameters()):
+                            pt.mul_(1.0 - self.tau).add_(p, alpha=self.tau)
+            stats = {"q_loss": float(loss_q.detach()), "pi_loss": float(loss_pi.detach()), "alpha": float(self.log_alpha.detach().exp())}
+        if self.world > 1:
+            flat = torch.cat([p.data.reshape(-1) for p in self.actor.parameters()])
+            dist.broadcast(flat, 0)
+            off = 0
+            for p in self.actor.parameters():
+                p.data.copy_(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+        return stats
+
+    def train(self, n_steps: int, log=None):
+        hist = []
+        for s in range(n_steps):
+            mean_r = self.collect_step()
+            st = self.update()
+            st.update(step=s, mean_step_reward=mean_r, episodes=len(self.finished_returns))
+            hist.append(st)
+            if log and self.rank == 0:
+                log(st)
+        return hist

@@ -97,6 +97,9 @@ inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) { *p = (T*)calloc(n ? n : 1, 1); return *p ? 0 : 2; }
 template <class T> inline cudaError_t cudaMallocHost(T** p, size_t n) { *p = (T*)calloc(n ? n : 1, 1); return *p ? 0 : 2; }
 inline cudaError_t cudaFree(void* p) { free(p); return 0; }
+enum { cudaHostAllocMapped = 2 };
+template <class T> inline cudaError_t cudaHostAlloc(T** p, size_t n, unsigned) { *p = (T*)calloc(n ? n : 1, 1); return *p ? 0 : 2; }
+inline cudaError_t cudaHostGetDevicePointer(void** d, void* h, unsigned) { *d = h; return 0; }
 inline cudaError_t cudaFreeHost(void* p) { free(p); return 0; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return 0; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return 0; }

@@ -146,6 +146,23 @@ def test_fused_week_equals_seven_days_and_host_path():
         e.close()
 
 
+@pytest.mark.parametrize("mode", ["0", "1", "3"])
+@pytest.mark.parametrize("name,n", [("COVID_C", 100), ("SIR_A", 7), ("syn_s", 5)])
+def test_host_path_zero_copy_modes(name, n, mode, monkeypatch):
+    """epi_step_host with staged copies (0), results written by the kernel into the mapped pinned buffers (1, the
+    default) and the actions read from them as well (3): identical to the device-buffer call, ragged last warp."""
+    monkeypatch.setenv("EPI_HOST_ZEROCOPY", mode)
+    d, _ = load(name)
+    a = torch.rand((n, d.A), generator=torch.Generator().manual_seed(5))
+    ed, eh = _engine(d, n, "fp32"), _engine(d, n, "fp32")
+    for _ in range(2):
+        od, rd, dd = ed.step(a.cuda(), 7)
+        oh, rh, dh = eh.step_host(a.numpy(), 7)
+        assert np.array_equal(oh, od.cpu().numpy()) and np.array_equal(rh, rd.cpu().numpy())
+        assert np.array_equal(dh, dd.cpu().numpy())
+    ed.close(); eh.close()
+
+
 def test_reset_mask_done_and_state_roundtrip():
     d, _ = load("SIRV_A")
     eng = _engine(d, 8, "fp64")

@@ -76,3 +76,39 @@ def test_two_rank_gather_and_broadcast(tmp_path):
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     w0, w1 = torch.load(tmp_path / "w0.pt"), torch.load(tmp_path / "w1.pt")
     assert torch.equal(w0, w1)
+
+
+def test_squashed_gaussian_logprob_matches_torch_transform():
+    from epipolicy_rl_b200.learner import SquashedGaussianActor
+    torch.manual_seed(0)
+    actor = SquashedGaussianActor(3, 2)
+    obs = torch.rand(16, 3)
+    a, logp = actor(obs)
+    assert a.min() >= 0 and a.max() <= 1
+    mu, log_std = actor.net(obs).chunk(2, -1)
+    base = torch.distributions.Normal(mu, log_std.clamp(-20, 2).exp())
+    tr = torch.distributions.TransformedDistribution(base, [torch.distributions.transforms.TanhTransform(),
+                                                           torch.distributions.transforms.AffineTransform(0.5, 0.5)])
+    ref = tr.log_prob(a.clamp(1e-6, 1 - 1e-6)).sum(-1)
+    assert torch.allclose(logp, ref, atol=1e-3, rtol=1e-3)
+
+
+def test_replay_ring_wraps():
+    from epipolicy_rl_b200.learner import ReplayRing
+    ring = ReplayRing(1, 1, 8, "cpu")
+    for k in range(3):
+        v = torch.arange(3, dtype=torch.float32)[:, None] + 10 * k
+        ring.store(v, v, v[:, 0], v, torch.zeros(3))
+    assert ring.n == 8 and ring.ptr == 1
+    assert ring.o[0, 0] == 22 and ring.o[1, 0] == 1  # the 9th transition overwrote slot 0
+
+
+def test_sac_learns_on_toy_env():
+    from epipolicy_rl_b200.learner import BatchedSAC
+    env = ToyEnv(128)
+    sac = BatchedSAC(env, 3, 2, obs_scale=np.ones(3), gamma=0.0, lr=3e-3, batch_size=256, buffer_size=1 << 14,
+                     gradient_steps=4, reward_scale=1.0, device="cpu", seed=3)
+    hist = sac.train(120)
+    first = np.mean([h["mean_step_reward"] for h in hist[:10]])
+    last = np.mean([h["mean_step_reward"] for h in hist[-10:]])
+    assert last > first + 0.02, (first, last)
