@@ -498,10 +498,16 @@ __device__ __forceinline__ int prologue(const DevPlan& P, const Cx& c, bool on, 
   __syncwarp();
   if (on) {
     // the previous state for tomorrow's 'change' selects is today's start state (epidemic.py:96-99)
+#if defined(EPI_SPEC) && EPI_SPEC_PROLOGUE
+#pragma unroll
+    for (int k = 0; k < C; k++)
+      if (spec::chg_slot[k] >= 0) Xprev_g[spec::chg_slot[k] * LG + c.cell] = LA(X, k);
+#else
     for (int k = 0; k < C; k++) {
       int sl = P.chg_slot_of_comp[k];
       if (sl >= 0) Xprev_g[sl * LG + c.cell] = LA(X, k);
     }
+#endif
     // 2. expressions
     for (int e = c.cell; e < P.n_expr; e += LG) {
 #if defined(EPI_SPEC) && EPI_SPEC_PROLOGUE
@@ -596,6 +602,51 @@ __device__ __forceinline__ int prologue(const DevPlan& P, const Cx& c, bool on, 
     // 5. move table of today (nb_move, executor.py:166-234; different compartment, same locale)
     for (int sl = 0; sl < DIM(n_slot); sl++) LA(mvD, sl) = 0.0f;
   }
+#if defined(EPI_SPEC) && EPI_SPEC_PROLOGUE
+  // the same loop nest over compile-time tables: fully unrolled, no table loads
+#pragma unroll
+  for (int mo = 0; mo < spec::n_mv_op; mo++) {
+    const bool live = on && EV(live, spec::mv_op[mo]);
+    const bool mine = live && ((spec::mv_gmask[mo] >> c.u) & 1) && ((spec::mv_lmask[mo] >> c.j) & 1);
+    double part = 0;
+    if (mine) {
+#pragma unroll
+      for (int q = 0; q < spec::mv_max_c1; q++)
+        if (q < spec::mv_nc1[mo]) part += LA(X, spec::mv_c1[spec::mv_c1_off[mo] + q]);
+    }
+    double depart_sum;
+    TEAM_SUM(depart_sum, part, on);
+    if (live && depart_sum > 0) {
+      const double value = EV(expr, spec::mv_expr[mo]);
+      if (mine) {
+#pragma unroll
+        for (int q1 = 0; q1 < spec::mv_max_c1; q1++)
+          if (q1 < spec::mv_nc1[mo]) {
+            const int c1 = spec::mv_c1[spec::mv_c1_off[mo] + q1];
+            const double depart = LA(X, c1) / depart_sum * value;
+            double arrive = 0;
+#pragma unroll
+            for (int q = 0; q < spec::mv_max_c2; q++)
+              if (q < spec::mv_nc2[mo]) arrive += LA(X, spec::mv_c2[spec::mv_c2_off[mo] + q]);
+#pragma unroll
+            for (int q = 0; q < spec::mv_max_c2; q++)
+              if (q < spec::mv_nc2[mo]) {
+                const int c2 = spec::mv_c2[spec::mv_c2_off[mo] + q];
+                const double amt = arrive > 0 ? LA(X, c2) / arrive * depart : 1.0 / spec::mv_nc2[mo] * depart;
+                float* cellp = &LA(mvD, spec::slot_of_pair[c1 * spec::C + c2]);
+                *cellp = (float)((double)*cellp + amt);  // CooMatrix.element_add: f32 cell (coo.py:52-57)
+              }
+          }
+      }
+#pragma unroll
+      for (int q1 = 0; q1 < spec::mv_max_c1; q1++)
+#pragma unroll
+        for (int q = 0; q < spec::mv_max_c2; q++)
+          if (q1 < spec::mv_nc1[mo] && q < spec::mv_nc2[mo])
+            ex_d |= 1 << spec::slot_of_pair[spec::mv_c1[spec::mv_c1_off[mo] + q1] * spec::C + spec::mv_c2[spec::mv_c2_off[mo] + q]];
+    }
+  }
+#else
   for (int mo = 0; mo < P.n_mv_op; mo++) {
     int o = P.mv_op[mo];
     bool live = on && EV(live, o);
@@ -628,8 +679,12 @@ __device__ __forceinline__ int prologue(const DevPlan& P, const Cx& c, bool on, 
         for (int q = 0; q < nc2; q++) ex_d |= 1 << P.slot_of_pair[c1s[q1] * C + c2s[q]];
     }
   }
+#endif
   if (on) {
     // 6. cost rates of today (nb_add, executor.py:236-243)
+#if defined(EPI_SPEC) && EPI_SPEC_PROLOGUE
+    for (int it = c.cell; it < DIM(I) * L; it += LG) EV(crD, it) = spec::cost_rate(it, &EV(live, 0), &EV(expr, 0));
+#else
     for (int it = c.cell; it < P.I * L; it += LG) {
       double cr = 0;
       for (int q = __ldg(P.cr_off + it); q < __ldg(P.cr_off + it + 1); q++) {  // the ADD ops covering (i, l), in op order
@@ -638,6 +693,7 @@ __device__ __forceinline__ int prologue(const DevPlan& P, const Cx& c, bool on, 
       }
       EV(crD, it) = cr;
     }
+#endif
   }
   __syncwarp();
   if (on && !dyn && rebuild) fill_tables<real>(P, c, 0.0f);  // constant over the day: filled once

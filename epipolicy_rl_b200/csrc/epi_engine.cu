@@ -53,6 +53,8 @@ struct HostTabs {
   std::vector<uint8_t> sel_c, sel_l, sel_g;
   std::vector<int> sel_mode, chg_slot, selc_off, selc, cls_off, cls_op, op_expr, expr_off, tok_op, tok_arg, tok_f32;
   std::vector<double> tok_val;
+  std::vector<int> mv_op, mv_c1_off, mv_c1, mv_c2_off, mv_c2, slot_of_pair, cr_off, cr_ops, add_op, add_parts;
+  std::vector<uint8_t> mv_g, mv_l1;
 };
 
 struct epi_engine {
@@ -526,6 +528,9 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
     T.op_expr = vec(d.op_expr, d.NOP); T.expr_off = vec(d.expr_off, d.NEXPR + 1);
     T.tok_op = vec(d.tok_op, d.NTOK); T.tok_arg = vec(d.tok_arg, d.NTOK); T.tok_f32 = vec(d.tok_f32, d.NTOK);
     T.tok_val = vec(d.tok_val, d.NTOK);
+    T.mv_op = mv_op; T.mv_c1_off = mv_c1_off; T.mv_c1 = mv_c1; T.mv_c2_off = mv_c2_off; T.mv_c2 = mv_c2;
+    T.slot_of_pair = slot_of_pair; T.mv_g = mv_g; T.mv_l1 = mv_l1;
+    T.cr_off = cr_off; T.cr_ops = cr_ops; T.add_op = add_op; T.add_parts = add_parts;
   }
 
   // ---- workspace layout
@@ -1033,6 +1038,38 @@ std::string gen_spec(const epi_engine* h) {
       o << " break;\n";
     }
     o << "  }\n  return m;\n}\n";
+    // compartments whose start-of-day value feeds tomorrow's 'change' selects (epidemic.py:96-99)
+    arr("chg_slot", T.chg_slot);
+    // today's cost rate of (intervention, locale) entry `it`: the ADD ops covering it, in op order (nb_add,
+    // executor.py:236-243)
+    o << "__device__ __forceinline__ double cost_rate(int it, const unsigned char* live, const double* expr) {\n  double cr = 0;\n  switch (it) {\n";
+    for (int it = 0; it < P.I * P.L; it++) {
+      o << "  case " << it << ":";
+      for (int q = T.cr_off[it]; q < T.cr_off[it + 1]; q++) {
+        int ao = T.cr_ops[q], op = T.add_op[ao];
+        o << " if (live[" << op << "]) cr += expr[" << T.op_expr[op] << "] / " << T.add_parts[ao] << ".0;";
+      }
+      o << " break;\n";
+    }
+    o << "  }\n  return cr;\n}\n";
+    // move ops (nb_move, executor.py:166-234): op, expression, group / source-locale masks, compartment lists
+    {
+      const int NM = (int)T.mv_op.size();
+      o << "constexpr int n_mv_op = " << NM << ";\n";
+      std::vector<int> mexpr(NM), gm(NM), lm(NM), nc1(NM), nc2(NM);
+      int m1 = 1, m2 = 1;
+      for (int mo = 0; mo < NM; mo++) {
+        mexpr[mo] = T.op_expr[T.mv_op[mo]];
+        for (int g = 0; g < P.G; g++) if (T.mv_g[(size_t)mo * P.G + g]) gm[mo] |= 1 << g;
+        for (int l = 0; l < P.L; l++) if (T.mv_l1[(size_t)mo * P.L + l]) lm[mo] |= 1 << l;
+        nc1[mo] = T.mv_c1_off[mo + 1] - T.mv_c1_off[mo]; nc2[mo] = T.mv_c2_off[mo + 1] - T.mv_c2_off[mo];
+        m1 = std::max(m1, nc1[mo]); m2 = std::max(m2, nc2[mo]);
+      }
+      arr("mv_op", T.mv_op); arr("mv_expr", mexpr); arr("mv_gmask", gm); arr("mv_lmask", lm);
+      arr("mv_nc1", nc1); arr("mv_nc2", nc2); arr("mv_c1_off", T.mv_c1_off); arr("mv_c2_off", T.mv_c2_off);
+      arr("mv_c1", T.mv_c1); arr("mv_c2", T.mv_c2); arr("slot_of_pair", T.slot_of_pair);
+      o << "constexpr int mv_max_c1 = " << m1 << ", mv_max_c2 = " << m2 << ";\n";
+    }
   }
   o << "__device__ __forceinline__ void acc_rt(const real* col, size_t stride, real* out) {\n";
   for (int a = 0; a < P.n_acc; a++) {
@@ -1046,7 +1083,7 @@ std::string gen_spec(const epi_engine* h) {
   uint64_t k = 1469598103934665603ull;
   auto mix = [&](const void* p, size_t n) { for (size_t i = 0; i < n; i++) { k ^= ((const unsigned char*)p)[i]; k *= 1099511628211ull; } };
   mix(body.data(), body.size());
-  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 22 /* generator revision */};
+  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 23 /* generator revision */};
   mix(abi, sizeof abi);
   char kb[32];
   snprintf(kb, sizeof kb, "%016llx", (unsigned long long)k);
