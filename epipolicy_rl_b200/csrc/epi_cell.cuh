@@ -140,6 +140,10 @@ __device__ __forceinline__ real acc_gather(const DevPlan& P, const real* col, in
 }
 #endif
 
+// first-same-as-last across the day boundary (see rk45_day: skip0); fp32 throughput mode only
+#ifndef EPI_FSAL_DAYS
+#define EPI_FSAL_DAYS 1
+#endif
 // the stage input y of my cell: registers in the specialised build, the ys column otherwise
 #ifdef EPI_SPEC
 #define Y_DECL real y[spec::C]
@@ -715,8 +719,8 @@ __device__ __forceinline__ int prologue(const DevPlan& P, const Cx& c, bool on, 
 // threshold.
 // ------------------------------------------------------------------------------------------
 template <class real>
-__device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on, bool dyn, int ex_bits, int* trace,
-                                         double* last_err_out, double* dbg) {
+__device__ __forceinline__ bool rk45_day(const DevPlan& P, const Cx& c, bool on, bool dyn, int ex_bits, int* trace,
+                                         double* last_err_out, double* dbg, bool skip0) {
   const double rtol = 1e-3, atol = 1e-6;
   const real rtolr = (real)1e-3, atolr = (real)1e-6;
   const int C = DIM(C), LG = DIM(LG), nC = DIM(I) * DIM(L), nS = DIM(has_src64) ? DIM(n_slot) : 0, NSRC = DIM(NSRC),
@@ -748,7 +752,10 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on,
         h_abs = fabs(h);
       }
     }
-    const bool ev = phase <= 1 ? on : (phase == 8 ? redo : run);
+    // skip0 (fp32 mode, days 2.. of a fused launch whose parameters do not move today): f(0, y0) is yesterday's
+    // last stage f(1, y_new) - same state, same parameters up to float rounding - and its derivatives (K slot 0),
+    // move-source derivative and flows are still in place (FSAL across the day boundary); nfev counts it
+    const bool ev = phase == 0 ? (on && !skip0) : (phase == 1 ? on : (phase == 8 ? redo : run));
     // per-phase scalars from constant tables (epi_rk.cuh): no branch chains on the single warp's critical path
     const int nj = PH_NJ[phase];
     const double hh = phase <= 1 ? h0 : h;
@@ -1008,6 +1015,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Cx& c, bool on,
     trace[3] = nfev; trace[4] = nsteps; trace[5] = nrej; trace[2] = status;
     *last_err_out = last_err;
   }
+  return on && status == 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1076,7 +1084,7 @@ __device__ __forceinline__ void step_warp(const DevPlan& P, const DevState& S, c
   __syncwarp();
 
   double reward = 0;
-  bool on = on0, tabs_current = false;
+  bool on = on0, tabs_current = false, fsal_ok = false;
   const int n_days = a.init_only ? 1 : a.n_days;
   for (int day = 0; day < n_days; day++) {
     if (!__any_sync(EPI_FULL, on)) break;
@@ -1086,8 +1094,9 @@ __device__ __forceinline__ void step_warp(const DevPlan& P, const DevState& S, c
       double c0 = 0, c1 = 0;
       if (on)
         for (int i = c.cell; i < nC; i += LG) c0 += EV(cost, i);
-      rk45_day<real>(P, c, on, dyn, ex_bits, meta, S.last_err + e,
-                     a.dbg_attempts ? a.dbg_attempts + e * 128 : nullptr);
+      const bool skip0 = EPI_FSAL_DAYS && sizeof(real) == 4 && fsal_ok && !dyn;
+      fsal_ok = rk45_day<real>(P, c, on, dyn, ex_bits, meta, S.last_err + e,
+                               a.dbg_attempts ? a.dbg_attempts + e * 128 : nullptr, skip0);
       if (on)
         for (int i = c.cell; i < nC; i += LG) c1 += EV(cost, i);
       // reward = -sum(cumulative_cost_next - cumulative_cost_current)  (epidemic.py:115)

@@ -120,3 +120,27 @@ def test_alternative_kernels_on_covid_c(knobs, monkeypatch):
     assert worst <= 1e-9 and mism == 0
     assert rej > 0  # the trajectory exercised the reject path
     eng.close()
+
+
+@pytest.mark.parametrize("name", ["COVID_C", "SIRV_B", "SIR_A"])
+def test_fused_week_fp32_reuses_last_stage_across_days(name):
+    """fp32 throughput mode, 7 fused days: from the second day on f(0, y0) is not evaluated again (the previous
+    day's last stage is reused, rk45_day: skip0). Weekly observations stay within the fp32 tolerance of the
+    reference, and the RK45 evaluation counts equal those of the day-by-day run that evaluates everything."""
+    d, z = load(name)
+    fused, daily = EmuEngine(d, 2, "fp32"), EmuEngine(d, 2, "fp32")
+    acts = np.stack([z["rnd_actions"], z["lax_actions"]], 1)
+    ref = np.stack([z["rnd_obs_weekly"], z["lax_obs_weekly"]], 1)
+    worst, weeks = 0.0, min(12, len(ref))
+    for w in range(weeks):
+        obs, r7, _ = fused.step(acts[w], 7)
+        r1 = np.zeros(2)
+        for _ in range(7):
+            _, r, _ = daily.step(acts[w], 1)
+            r1 += r
+        worst = max(worst, x_err(obs, ref[w], d))
+        assert np.array_equal(fused.get_state("trace")[:, 0], daily.get_state("trace")[:, 0])  # nfev of the last day
+        assert np.allclose(r7, r1, rtol=1e-5)
+    print(f"{name} fused fp32: X {worst:.2e}")
+    assert worst <= TOL["fp32"]
+    fused.close(); daily.close()
