@@ -1091,7 +1091,7 @@ std::string gen_spec(const epi_engine* h) {
          kb + "\"\n#define EPI_SPEC_BIG " + (P.LG > 32 ? "1" : "0") + "\n" +
          "#define EPI_SPEC_PROLOGUE " + (spec_prologue ? "1" : "0") + "\n" +
          "#define EPI_SPEC_ROLES " + std::to_string(P.cl.roles > 0 ? P.cl.roles : 1) + "\n" +
-         (P.LG > 32 ? std::string("#define EPI_ENV_MINB ") + std::to_string((P.el.big_in_smem ? 512 : 1024) / (P.el.threads > 0 ? P.el.threads : 256)) + "\n" : std::string()) + body;
+         (P.LG > 32 ? std::string("#define EPI_ENV_MINB ") + (P.el.big_in_smem ? "2" : "4") + "\n" : std::string()) + body;
 }
 
 void alloc_state(epi_engine* h, DevState& S, int N) {

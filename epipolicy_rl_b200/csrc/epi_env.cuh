@@ -22,6 +22,10 @@ namespace epi {
 namespace env {
 using namespace rk;
 
+#ifndef EPI_FSAL_DAYS
+#define EPI_FSAL_DAYS 1  // fp32 mode: first-same-as-last across the day boundary of a fused launch
+#endif
+
 #ifdef EPI_SPEC
 #define EDIM(x) (spec::x)
 #define ESLOT_C1(i) (spec::slot_c1[i])
@@ -598,8 +602,8 @@ __device__ __forceinline__ int prologue(const DevPlan& P, const Bx& b, int varia
 // one simulated day: scipy RK45 state machine (see epi_cell.cuh: rk45_day), uniform over the CTA
 // ------------------------------------------------------------------------------------------
 template <class real>
-__device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn, int ex_bits, int* trace,
-                                         double* last_err_out, double* dbg) {
+__device__ __forceinline__ bool rk45_day(const DevPlan& P, const Bx& b, bool dyn, int ex_bits, int* trace,
+                                         double* last_err_out, double* dbg, bool skip0, int& rot) {
   const double rtol = 1e-3, atol = 1e-6;
   const real rtolr = (real)1e-3, atolr = (real)1e-6;
   const int C = EDIM(C), nC = EDIM(I) * EDIM(L), nS = EDIM(has_src64) ? EDIM(n_slot) : 0, NSRC = EDIM(NSRC),
@@ -609,7 +613,8 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
   double last_err = 0, t = 0.0, h_abs = 0, h = 0, t_new = 0, h0 = 0, d0 = 0, d1 = 0;
   bool run = true, rejected = false;
   auto qd = [](double tt) { return (double)(float)((-3.0 * tt + 4.0) * tt); };
-  int rot = 0;  // flow-slot mode: stage s of the current attempt lives in slot (s + rot) % 7
+  // flow-slot mode: stage s of the current attempt lives in slot (s + rot) % 7; rot persists over the days of a launch
+  // so that yesterday's last stage is found in today's slot 0 (skip0, see epi_cell.cuh: rk45_day)
   auto ps = [&](int st) { int v = st + rot; return v >= 7 ? v - 7 : v; };
 
   int phase = 0;
@@ -642,8 +647,9 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
       co[j] = rkCO(real(0), phase, j);
       coS[j] = RK_CO64[phase][j];
     }
-    rhs<real>(P, b, dyn, t_eval, ex_bits, stage, bw, ew, PH_ACC[phase], PH_KEEP[phase] != 0,
-              hh, nj, co, coS, ps(stage));
+    if (!(phase == 0 && skip0))
+      rhs<real>(P, b, dyn, t_eval, ex_bits, stage, bw, ew, PH_ACC[phase], PH_KEEP[phase] != 0,
+                hh, nj, co, coS, ps(stage));
     if (phase == 0) {
       // select_initial_step (common.py:68-134), first half
       double s0 = 0, s1 = 0;
@@ -894,6 +900,7 @@ __device__ __forceinline__ void rk45_day(const DevPlan& P, const Bx& b, bool dyn
     trace[3] = nfev; trace[4] = nsteps; trace[5] = nrej; trace[2] = status;
     *last_err_out = last_err;
   }
+  return status == 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -933,7 +940,8 @@ __device__ __forceinline__ void step_cta(const DevPlan& P, const DevState& S, co
     __syncthreads();
 
     double reward = 0;
-    bool tabs_current = false;
+    bool tabs_current = false, fsal_ok = false;
+    int rot = 0;
     const int n_days = a.init_only ? 1 : a.n_days;
     for (int day = 0; day < n_days; day++) {
       bool dyn = true;
@@ -941,7 +949,9 @@ __device__ __forceinline__ void step_cta(const DevPlan& P, const DevState& S, co
       if (!a.init_only) {
         double c0 = 0, c1 = 0;
         for (int i = b.tid; i < nC; i += b.nt) c0 += b.cost[i];
-        rk45_day<real>(P, b, dyn, ex_bits, meta, S.last_err + e, a.dbg_attempts ? a.dbg_attempts + e * 128 : nullptr);
+        const bool skip0 = EPI_FSAL_DAYS && sizeof(real) == 4 && fsal_ok && !dyn;
+        fsal_ok = rk45_day<real>(P, b, dyn, ex_bits, meta, S.last_err + e,
+                                 a.dbg_attempts ? a.dbg_attempts + e * 128 : nullptr, skip0, rot);
         for (int i = b.tid; i < nC; i += b.nt) c1 += b.cost[i];
         reward -= block_sum(b, c1 - c0);  // -sum(cumulative_cost_next - cumulative_cost_current), epidemic.py:115
         t_day++;

@@ -112,6 +112,37 @@ class BatchedEpidemic:
                                       self.reward.data_ptr(), self.done.data_ptr(), self._stream()))
         return self.obs, self.reward, self.done
 
+    def run(self, cpv: torch.Tensor, active: torch.Tensor | None = None, record_obs: bool = True,
+            schedule_programs: bool = True):
+        """Epidemic.run (core/epidemic.py:118-134) for a batch of what-if schedules: reset, then one day per launch
+        with day t's Acts taken from the schedule. cpv: [T, N, NCP] (or [T, NCP], broadcast to all envs) full
+        control-parameter vectors; active: [T, N, I] / [T, I] flags of the interventions that have an Act on
+        day t (None: all). Returns {"reward": [T, N] float64, "done": [N] uint8, "obs": [T, N, C*L*G]} on the device
+        (obs only if record_obs; the reporter quantities of the reference are not rebuilt here)."""
+        c = cpv.to(device=self.device, dtype=torch.float32)
+        T = c.shape[0]
+        if c.dim() == 2:
+            c = c[:, None, :].expand(T, self.n_envs, c.shape[-1])
+        a = None
+        if active is not None:
+            a = active.to(device=self.device, dtype=torch.uint8)
+            if a.dim() == 2:
+                a = a[:, None, :].expand(T, self.n_envs, a.shape[-1])
+        if c.shape[1] != self.n_envs or (a is not None and a.shape[:2] != c.shape[:2]):
+            raise ValueError("schedule must be [T, N, NCP] / [T, NCP] with matching active flags")
+        self.reset()
+        rew = torch.empty((T, self.n_envs), dtype=torch.float64, device=self.device)
+        obs = torch.empty((T, self.n_envs, self.obs_dim), dtype=self.dtype, device=self.device) if record_obs else None
+        for t in range(T):
+            o, r, _ = self.step_plan(c[t], None if a is None else a[t], schedule_programs, 1)
+            rew[t].copy_(r)
+            if record_obs:
+                obs[t].copy_(o)
+        out = {"reward": rew, "done": self.done}
+        if record_obs:
+            out["obs"] = obs
+        return out
+
     def step_host(self, actions: np.ndarray, n_days: int = PERIOD):
         """The same step through host (numpy) buffers: H2D, launch, D2H inside the call."""
         a = np.ascontiguousarray(actions, np.float32)

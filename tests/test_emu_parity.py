@@ -122,11 +122,16 @@ def test_alternative_kernels_on_covid_c(knobs, monkeypatch):
     eng.close()
 
 
-@pytest.mark.parametrize("name", ["COVID_C", "SIRV_B", "SIR_A"])
-def test_fused_week_fp32_reuses_last_stage_across_days(name):
+@pytest.mark.parametrize("name,knobs", [("COVID_C", {}), ("SIRV_B", {}), ("SIR_A", {}),
+                                        ("COVID_C", {"EPI_TEAM": "env", "EPI_ENV_FLOWSLOTS": "0"}),
+                                        ("COVID_C", {"EPI_TEAM": "env", "EPI_ENV_FLOWSLOTS": "1"})],
+                         ids=["COVID_C", "SIRV_B", "SIR_A", "COVID_C-env-flowsums", "COVID_C-env-flowslots"])
+def test_fused_week_fp32_reuses_last_stage_across_days(name, knobs, monkeypatch):
     """fp32 throughput mode, 7 fused days: from the second day on f(0, y0) is not evaluated again (the previous
     day's last stage is reused, rk45_day: skip0). Weekly observations stay within the fp32 tolerance of the
     reference, and the RK45 evaluation counts equal those of the day-by-day run that evaluates everything."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
     d, z = load(name)
     fused, daily = EmuEngine(d, 2, "fp32"), EmuEngine(d, 2, "fp32")
     acts = np.stack([z["rnd_actions"], z["lax_actions"]], 1)

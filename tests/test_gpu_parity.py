@@ -73,6 +73,25 @@ def test_schedule_plan_vs_reference(name):
     eng.close()
 
 
+def test_run_batch_of_schedules():
+    """BatchedEpidemic.run (Epidemic.run for a batch): env 0 follows SIR_A's own schedule, env 1 the same schedule
+    with every control parameter halved; env 0 reproduces the golden trajectory, env 1 differs."""
+    d, z = load("SIR_A")
+    eng = _engine(d, 2, "fp64")
+    T = 60
+    cpv = torch.from_numpy(z["sched_plan_cpv"][:T]).float()[:, None, :].repeat(1, 2, 1)
+    cpv[:, 1, :] *= 0.5
+    act = torch.from_numpy(z["sched_plan_active"][:T].astype(np.uint8))
+    out = eng.run(cpv, act)
+    obs = out["obs"].cpu().numpy()
+    assert obs.shape == (T, 2, d.C * d.L * d.G) and out["reward"].shape == (T, 2)
+    for day in (0, 17, T - 1):
+        assert x_err(obs[day, 0], z["sched_X"][day], d) <= 1e-9
+    assert np.allclose(out["reward"][:, 0].cpu().numpy(), z["sched_rewards"][:T], rtol=1e-9)
+    assert x_err(obs[T - 1, 1], z["sched_X"][T - 1], d) > 1e-6
+    eng.close()
+
+
 def test_known_answer_user_ipynb():
     d, _ = load("warmup_scenario")
     eng = _engine(d, 1, "fp64")
