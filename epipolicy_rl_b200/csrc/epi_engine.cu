@@ -656,7 +656,7 @@ void build_env_layout(epi_engine* h, int threads, int64_t smem_max) {
   // regime stores the 7 stages' flows instead (less traffic per evaluation, more workspace)
   for (int pass = 0; pass < 2; pass++) {
     o = 0;
-    Y.l_X = take(8 * C * LG); Y.l_ys = take(rs * C * LG); Y.l_K = take(rs * 7 * C * LG);
+    Y.l_X = take(8 * C * LG); Y.l_XF = take(rs == 4 ? 4 * C * LG : 0); Y.l_ys = take(rs * C * LG); Y.l_K = take(rs * 7 * C * LG);
     if (Y.flow_slots) {
       Y.l_fls = take(rs * 7 * P.NSRC * LG); Y.l_accYn = take(rs * (int64_t)P.n_acc * LG);
       Y.l_fl = Y.l_FBE = Y.l_fls;

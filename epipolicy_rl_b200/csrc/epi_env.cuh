@@ -49,6 +49,7 @@ struct Bx {
 #define BA(arr, i) (((T_##arr*)(b.big + P.el.l_##arr))[(size_t)(i) * EDIM(LG) + cell])
 #define CM(arr, i, cl) (((T_##arr*)(b.comm + P.el.l_##arr))[(size_t)(i) * EDIM(LG) + (cl)])
 #define ET(arr, i) (((T_##arr*)(b.tab + P.el.e_##arr))[i])
+#define EXF (sizeof(real) == 4)  // fp32 mode keeps a float copy of the state for the stage inputs and the norms
 #define FOR_CELLS for (int cell = b.tid; cell < EDIM(LG); cell += b.nt)
 
 // block sum; every thread receives the bit-identical result
@@ -154,7 +155,8 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Bx& b, bool dyn, dou
 #pragma unroll
       for (int j = 0; j < 6; j++)
         if (j < nj) dy += BA(K, j * C + k) * co[j];
-      EYV(k) = (real)(BA(X, k) + (double)dy * hh);
+      if (EXF) EYV(k) = dy * (real)hh + BA(XF, k);  // fp32 mode: float copy of the state (half the bytes of X)
+      else EYV(k) = (real)(BA(X, k) + (double)dy * hh);
     }
     for (int q = 0; q < nS; q++) {
       double dy = 0;
@@ -657,7 +659,7 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, const Bx& b, bool dyn
         real a0 = 0, a1 = 0;
 #pragma unroll
         for (int k = 0; k < C; k++) {
-          real yv = (real)BA(X, k), sc = atolr + fabs(yv) * rtolr;
+          real yv = EXF ? BA(XF, k) : (real)BA(X, k), sc = atolr + fabs(yv) * rtolr;
           real a = fdiv(yv, sc), bq = fdiv(BA(K, k), sc);
           a0 += a * a; a1 += bq * bq;
         }
@@ -699,7 +701,8 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, const Bx& b, bool dyn
         real a2 = 0;
 #pragma unroll
         for (int k = 0; k < C; k++) {
-          real sc = atolr + fabs((real)BA(X, k)) * rtolr, a = fdiv(BA(K, C + k) - BA(K, k), sc);
+          real sc = atolr + fabs(EXF ? BA(XF, k) : (real)BA(X, k)) * rtolr;
+          real a = fdiv(BA(K, C + k) - BA(K, k), sc);
           a2 += a * a;
         }
         if (EFS) {
@@ -750,10 +753,19 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, const Bx& b, bool dyn
         real ae = 0;
 #pragma unroll
         for (int k = 0; k < C; k++) {
-          real sc = atolr + fmax(fabs((real)BA(X, k)), fabs(BA(ys, k))) * rtolr;
-          real e = 0;
+          real sc = atolr + fmax(fabs(EXF ? BA(XF, k) : (real)BA(X, k)), fabs(BA(ys, k))) * rtolr;
+          // one pass over the stage derivatives gives the error estimate and the 5th-order increment; stage 1 has
+          // B = E = 0 (not read), and its slot - dead until the next attempt rewrites it - keeps the increment for
+          // the commit
+          real e = 0, dy = 0;
 #pragma unroll
-          for (int j = 0; j < 7; j++) e += BA(K, j * C + k) * rkE(real(0), j);
+          for (int j = 0; j < 7; j++) {
+            if (j == 1) continue;
+            const real kj = BA(K, j * C + k);
+            e += kj * rkE(real(0), j);
+            if (j < 6) dy += kj * rkB(real(0), j);
+          }
+          BA(K, C + k) = dy;
           real a = fdiv(e * (real)h, sc);
           ae += a * a;
         }
@@ -847,14 +859,15 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, const Bx& b, bool dyn
         FOR_CELLS {
 #pragma unroll
           for (int k = 0; k < C; k++) {
-            real dy = 0;
-#pragma unroll
-            for (int j = 0; j < 6; j++) dy += BA(K, j * C + k) * rkB(real(0), j);
-            BA(X, k) = BA(X, k) + h * (double)dy;
+            const real dy = BA(K, C + k);  // sum_j B_j K_j, left there by the error-norm pass
+            const double xn = BA(X, k) + h * (double)dy;
+            BA(X, k) = xn;
+            if (EXF) BA(XF, k) = (real)xn;
             BA(K, k) = BA(K, 6 * C + k);
           }
           for (int q = 0; q < nS; q++) {
             BA(X, ESLOT_C1(q)) = BA(ysS, q);  // = X + h * sum_j B_j KS_j in double
+            if (EXF) BA(XF, ESLOT_C1(q)) = (real)BA(ysS, q);
             BA(KS, q) = BA(KS, 6 * nS + q);
           }
           if (EFS) {
@@ -922,7 +935,11 @@ __device__ __forceinline__ void step_cta(const DevPlan& P, const DevState& S, co
     double* gXprev = S.Xprev + e * P.n_chg * LG;
     int* meta = S.meta + e * 8;
     FOR_CELLS {
-      for (int k = 0; k < C; k++) BA(X, k) = gX[(size_t)k * LG + cell];
+      for (int k = 0; k < C; k++) {
+        const double x = gX[(size_t)k * LG + cell];
+        BA(X, k) = x;
+        if (EXF) BA(XF, k) = (real)x;
+      }
       for (int s = 0; s < EDIM(n_slot); s++) BA(mvY, s) = S.mvY[e * nM + (size_t)s * LG + cell];
       for (int a_ = 0; a_ < EDIM(n_acc); a_++) BA(accY, a_) = gAcc[(size_t)a_ * LG + cell];
     }

@@ -38,7 +38,7 @@ struct EnvLayout {
   int enabled, threads, comm_in_smem, big_in_smem;
   int flow_slots;  // 1: the 7 stages' flows are stored (columns fls, accYn) instead of the flow sums (fl, FBE)
   int64_t l_fls, l_accYn;
-  int64_t l_X, l_ys, l_K, l_fl, l_FBE, l_accY, l_mvY, l_mvD, l_ysS, l_KS;  // big region
+  int64_t l_X, l_XF, l_ys, l_K, l_fl, l_FBE, l_accY, l_mvY, l_mvD, l_ysS, l_KS;  // big region
   int64_t l_cmA, l_cmB;                                                      // comm region
   int64_t e_mult_y, e_mult_d, e_cpv, e_act, e_expr, e_sel, e_mpy, e_mpg, e_mpt0, e_mpFy, e_mpFg, e_coefS, e_Tnum,
       e_Tden, e_fi_y, e_fi_gap, e_ft_y, e_ft_gap, e_cost, e_crY, e_crD;

@@ -61,6 +61,7 @@ __device__ __forceinline__ double rkCO(double, int ph, int j) { return RK_CO64[p
 
 // per-lane columns and per-env tables: element types
 #define T_X double
+#define T_XF real
 #define T_ys real
 #define T_K real
 #define T_fl real

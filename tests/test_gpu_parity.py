@@ -75,12 +75,12 @@ def test_schedule_plan_vs_reference(name):
 
 def test_run_batch_of_schedules():
     """BatchedEpidemic.run (Epidemic.run for a batch): env 0 follows SIR_A's own schedule, env 1 the same schedule
-    with every control parameter halved; env 0 reproduces the golden trajectory, env 1 differs."""
+    with both degrees raised; env 0 reproduces the golden trajectory, env 1 differs."""
     d, z = load("SIR_A")
     eng = _engine(d, 2, "fp64")
     T = 60
     cpv = torch.from_numpy(z["sched_plan_cpv"][:T]).float()[:, None, :].repeat(1, 2, 1)
-    cpv[:, 1, :] *= 0.5
+    cpv[:, 1, 0], cpv[:, 1, 3] = 0.7, 0.5
     act = torch.from_numpy(z["sched_plan_active"][:T].astype(np.uint8))
     out = eng.run(cpv, act)
     obs = out["obs"].cpu().numpy()
