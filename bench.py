@@ -3,8 +3,10 @@
 
 A "step" is one gym step (EpiEnv.step: 7 simulated days with one action, fused in ONE kernel launch)
 over the rank's whole batch of environments. Weak scaling: every rank owns `--envs` environments of
-the same scenario; at N > 1 each step ends with the NCCL all-gather of observations / rewards / done
-flags to the learner ranks that the north_star asks for.
+the same scenario; at N > 1 the observations / rewards / done flags of every shard are delivered to the learner
+rank each step: the step kernel's epilogue stores them into rank 0's receive buffer over NVLink (symmetric memory;
+one device-side barrier per step), or, with --gather nccl / when symmetric memory is unavailable, one NCCL
+all-gather per step as the north_star words it.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload covid_c|syn_small|syn] [--envs E]
   python bench.py --impl reference ...   # the CPU restatement of the reference on all host cores
@@ -186,10 +188,12 @@ def run_ours(args):
     acts_host = torch.rand((K + W, n_envs, desc.A), generator=g)
     acts = acts_host.cuda()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-    gather = None
+    gather, gather_kind = None, "none"
     if world > 1:
-        from epipolicy_rl_b200.dist import LearnerGather
-        gather = LearnerGather(eng, world)
+        # results of every shard go to the learner rank: by default the step kernel's epilogue stores them straight
+        # into rank 0's receive buffer over NVLink (dist.PeerGather); --gather nccl = one all-gather per gym step
+        from epipolicy_rl_b200.dist import make_gather
+        gather, gather_kind = make_gather(eng, world, prefer_peer=args.gather == "peer")
 
     def one_step(i):
         obs, rew, done = eng.step(acts[i], PERIOD)
@@ -271,7 +275,7 @@ def run_ours(args):
                        "kernel": {0: "warp-team", 1: "cta-team", 2: "cell", 3: "env"}[info.team_kind] +
                                  ("+specialised" if info.specialized else ""),
                        "threads": info.threads, "grid": info.grid,
-                       "smem_bytes": info.smem_bytes, "collective": "all_gather obs/reward/done" if world > 1 else "none"},
+                       "smem_bytes": info.smem_bytes, "collective": gather_kind},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "bytes_per_env_launch": base_b,
                          "bytes_per_env_launch_with_rk45_accumulators": ctrl_b,
@@ -297,6 +301,7 @@ def main():
     ap.add_argument("--workload", default="covid_c")
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N > 1: how results reach the learner rank")
     ap.add_argument("--cpu-sample-envs", type=int, default=64)
     ap.add_argument("--cpu-sample-steps", type=int, default=53)
     ap.add_argument("--ref-envs-per-core", type=int, default=64)

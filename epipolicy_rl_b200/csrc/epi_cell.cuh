@@ -1125,9 +1125,12 @@ __device__ __forceinline__ void step_warp(const DevPlan& P, const DevState& S, c
 #endif
     const int e0 = group * P.cl.epw, nv = a.N - e0 < P.cl.epw ? a.N - e0 : P.cl.epw;
     real* out = (real*)a.obs_out + (size_t)e0 * CLG;
+    real* out2 = a.obs_out2 ? (real*)a.obs_out2 + (size_t)e0 * CLG : nullptr;
     for (int idx = lane; idx < nv * CLG; idx += nthr) {
       const int sl = idx / CLG, rem = idx - sl * CLG, k = rem / LG, cl = rem - k * LG;
-      out[idx] = (real)LO(X, k, sl * LG + cl);
+      const real v = (real)LO(X, k, sl * LG + cl);
+      out[idx] = v;
+      if (out2) out2[idx] = v;
     }
   }
   if (on0) {
@@ -1143,6 +1146,8 @@ __device__ __forceinline__ void step_warp(const DevPlan& P, const DevState& S, c
       meta[0] = t_day; meta[1] = ex_y;
       if (a.reward_out) a.reward_out[env] = reward;
       if (a.done_out) a.done_out[env] = (uint8_t)(t_day >= P.horizon);
+      if (a.reward_out2) a.reward_out2[env] = reward;
+      if (a.done_out2) a.done_out2[env] = (uint8_t)(t_day >= P.horizon);
     }
   }
 }

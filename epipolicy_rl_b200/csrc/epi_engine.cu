@@ -82,6 +82,8 @@ struct epi_engine {
   // host memory directly over PCIe (EPI_HOST_ZEROCOPY: bit 0 results, bit 1 actions)
   float* m_act = nullptr; void* m_obs = nullptr; double* m_rew = nullptr; uint8_t* m_done = nullptr;
   int zerocopy = 1;
+  // epi_bind_mirror: second destination of every device-buffer step's results (peer memory of the learner rank)
+  void* mir_obs = nullptr; double* mir_rew = nullptr; uint8_t* mir_done = nullptr;
   cudaStream_t stream = nullptr;
   mutable std::string err;
   double* dbg_attempts = nullptr;   // [N,64,2], allocated on first use of state selector 9
@@ -1445,6 +1447,21 @@ int epi_reset(epi_t* h, const uint8_t* mask_dev, void* obs_out_dev, void* cuda_s
   });
 }
 
+// the team kernels (A/B baselines) do not write the mirror in their epilogue: copy behind the launch instead
+static void mirror_fallback(epi_engine* h, const epi::StepArgs& a, cudaStream_t st) {
+  if (h->cta_mode >= 2) return;
+  const size_t N = h->N;
+  if (a.obs_out2 && a.obs_out) CK(cudaMemcpyAsync(a.obs_out2, a.obs_out, N * h->plan.CLG * h->real_size(), cudaMemcpyDefault, st));
+  if (a.reward_out2 && a.reward_out) CK(cudaMemcpyAsync(a.reward_out2, a.reward_out, N * 8, cudaMemcpyDefault, st));
+  if (a.done_out2 && a.done_out) CK(cudaMemcpyAsync(a.done_out2, a.done_out, N, cudaMemcpyDefault, st));
+}
+
+int epi_bind_mirror(epi_t* h, void* obs_dev, double* reward_dev, uint8_t* done_dev) {
+  if (!h) return EPI_E_INVALID;
+  h->mir_obs = obs_dev; h->mir_rew = reward_dev; h->mir_done = done_dev;
+  return EPI_OK;
+}
+
 int epi_step(epi_t* h, const float* actions_dev, int n_days, void* obs_out_dev, double* reward_out_dev,
              uint8_t* done_out_dev, void* cuda_stream) {
   if (!h) return EPI_E_INVALID;
@@ -1455,7 +1472,9 @@ int epi_step(epi_t* h, const float* actions_dev, int n_days, void* obs_out_dev, 
     epi::StepArgs a{};
     a.actions = actions_dev; a.variant = 0; a.n_days = n_days; a.N = h->N;
     a.obs_out = obs_out_dev; a.reward_out = reward_out_dev; a.done_out = done_out_dev;
+    a.obs_out2 = obs_out_dev ? h->mir_obs : nullptr; a.reward_out2 = h->mir_rew; a.done_out2 = h->mir_done;
     launch(h, h->S, a, (cudaStream_t)cuda_stream);
+    mirror_fallback(h, a, (cudaStream_t)cuda_stream);
   });
 }
 
@@ -1469,7 +1488,9 @@ int epi_step_plan(epi_t* h, const float* cpv_dev, const uint8_t* active_dev, int
     epi::StepArgs a{};
     a.cpv = cpv_dev; a.active = active_dev; a.variant = schedule_programs ? 1 : 0; a.n_days = n_days; a.N = h->N;
     a.obs_out = obs_out_dev; a.reward_out = reward_out_dev; a.done_out = done_out_dev;
+    a.obs_out2 = obs_out_dev ? h->mir_obs : nullptr; a.reward_out2 = h->mir_rew; a.done_out2 = h->mir_done;
     launch(h, h->S, a, (cudaStream_t)cuda_stream);
+    mirror_fallback(h, a, (cudaStream_t)cuda_stream);
   });
 }
 

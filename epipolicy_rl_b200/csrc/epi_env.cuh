@@ -43,7 +43,12 @@ struct Bx {
   char* tab;    // per-env tables (shared memory)
   double* red;  // [nt] reduction scratch (shared memory)
   double *cost, *crY, *crD;  // [I*L] cumulative cost, yesterday's / today's cost rate of the current env (global)
+  // flow-slot mode: the accumulators y and the candidate y_new of the current attempt are two columns that swap
+  // roles when the attempt is accepted (no copy); byte offsets into `big`
+  int64_t o_acc, o_accn;
 };
+#define ACCY(i) (((real*)(b.big + b.o_acc))[(size_t)(i) * EDIM(LG) + cell])
+#define ACCYN(i) (((real*)(b.big + b.o_accn))[(size_t)(i) * EDIM(LG) + cell])
 
 // element i of cell `cell` in a column; entry i of an env table
 #define BA(arr, i) (((T_##arr*)(b.big + P.el.l_##arr))[(size_t)(i) * EDIM(LG) + cell])
@@ -604,7 +609,7 @@ __device__ __forceinline__ int prologue(const DevPlan& P, const Bx& b, int varia
 // one simulated day: scipy RK45 state machine (see epi_cell.cuh: rk45_day), uniform over the CTA
 // ------------------------------------------------------------------------------------------
 template <class real>
-__device__ __forceinline__ bool rk45_day(const DevPlan& P, const Bx& b, bool dyn, int ex_bits, int* trace,
+__device__ __forceinline__ bool rk45_day(const DevPlan& P, Bx& b, bool dyn, int ex_bits, int* trace,
                                          double* last_err_out, double* dbg, bool skip0, int& rot) {
   const double rtol = 1e-3, atol = 1e-6;
   const real rtolr = (real)1e-3, atolr = (real)1e-6;
@@ -667,7 +672,7 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, const Bx& b, bool dyn
           EACC_DECL(g0, ECOL_slot(ps(0)));
 #pragma unroll
           for (int a_ = 0; a_ < n_acc; a_++) {
-            real yv = BA(accY, a_), sc = atolr + fabs(yv) * rtolr;
+            real yv = ACCY(a_), sc = atolr + fabs(yv) * rtolr;
             real a = fdiv(yv, sc), bq = fdiv(EACC_AT(g0, a_, ECOL_slot(ps(0))), sc);
             a0 += a * a; a1 += bq * bq;
           }
@@ -675,7 +680,7 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, const Bx& b, bool dyn
           EACC_DECL(g0, ECOL_fl);
 #pragma unroll
           for (int a_ = 0; a_ < n_acc; a_++) {
-            real yv = BA(accY, a_), sc = atolr + fabs(yv) * rtolr;
+            real yv = ACCY(a_), sc = atolr + fabs(yv) * rtolr;
             real a = fdiv(yv, sc), bq = fdiv(EACC_AT(g0, a_, ECOL_fl), sc);
             a0 += a * a; a1 += bq * bq;
           }
@@ -710,7 +715,7 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, const Bx& b, bool dyn
           EACC_DECL(g0, ECOL_slot(ps(0)));
 #pragma unroll
           for (int a_ = 0; a_ < n_acc; a_++) {
-            real sc = atolr + fabs(BA(accY, a_)) * rtolr;
+            real sc = atolr + fabs(ACCY(a_)) * rtolr;
             real a = fdiv(EACC_AT(g1, a_, ECOL_slot(ps(1))) - EACC_AT(g0, a_, ECOL_slot(ps(0))), sc);
             a2 += a * a;
           }
@@ -719,7 +724,7 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, const Bx& b, bool dyn
           EACC_DECL(g0, ECOL_FE);
 #pragma unroll
           for (int a_ = 0; a_ < n_acc; a_++) {
-            real sc = atolr + fabs(BA(accY, a_)) * rtolr;
+            real sc = atolr + fabs(ACCY(a_)) * rtolr;
             real a = fdiv(EACC_AT(g1, a_, ECOL_fl) - EACC_AT(g0, a_, ECOL_FE), sc);
             a2 += a * a;
           }
@@ -807,17 +812,17 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, const Bx& b, bool dyn
               vE += se * (real)__ldg(P.ag_coef + q);
             }
 #endif
-            real yv = BA(accY, a_), yn = yv + (real)h * vB;
+            real yv = ACCY(a_), yn = yv + (real)h * vB;
             real sc = atolr + fmax(fabs(yv), fabs(yn)) * rtolr, a = fdiv(vE * (real)h, sc);
             ae += a * a;
-            BA(accYn, a_) = yn;
+            ACCYN(a_) = yn;
           }
         } else {
           EACC_DECL(gB, ECOL_FB);
           EACC_DECL(gE, ECOL_FE);
 #pragma unroll
           for (int a_ = 0; a_ < n_acc; a_++) {
-            real yv = BA(accY, a_), yn = yv + (real)h * EACC_AT(gB, a_, ECOL_FB);
+            real yv = ACCY(a_), yn = yv + (real)h * EACC_AT(gB, a_, ECOL_FB);
             real sc = atolr + fmax(fabs(yv), fabs(yn)) * rtolr, a = fdiv(EACC_AT(gE, a_, ECOL_FE) * (real)h, sc);
             ae += a * a;
           }
@@ -871,12 +876,11 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, const Bx& b, bool dyn
             BA(KS, q) = BA(KS, 6 * nS + q);
           }
           if (EFS) {
-#pragma unroll
-            for (int a_ = 0; a_ < n_acc; a_++) BA(accY, a_) = BA(accYn, a_);
+            // (the candidate column becomes the accumulator column after this pass: see below)
           } else {
             EACC_DECL(gB, ECOL_FB);
 #pragma unroll
-            for (int a_ = 0; a_ < n_acc; a_++) BA(accY, a_) += hr * EACC_AT(gB, a_, ECOL_FB);
+            for (int a_ = 0; a_ < n_acc; a_++) ACCY(a_) += hr * EACC_AT(gB, a_, ECOL_FB);
           }
           if (!EFS)
           for (int i = 0; i < NSRC; i++) {  // the last stage's flows open the next attempt (FSAL)
@@ -897,7 +901,12 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, const Bx& b, bool dyn
         t = t_new;
         rejected = false;
         if (!(t < 1.0)) run = false;
-        if (EFS) rot = ps(6);  // FSAL: the slot of stage 6 becomes the slot of stage 0
+        if (EFS) {
+          rot = ps(6);  // FSAL: the slot of stage 6 becomes the slot of stage 0
+          const int64_t t_ = b.o_acc;  // y = y_new for the accumulators: the columns swap roles
+          b.o_acc = b.o_accn;
+          b.o_accn = t_;
+        }
         __syncthreads();
         phase = run ? 2 : -1;
       } else {
@@ -934,6 +943,8 @@ __device__ __forceinline__ void step_cta(const DevPlan& P, const DevState& S, co
     real* gAcc = (real*)S.acc + e * nA;
     double* gXprev = S.Xprev + e * P.n_chg * LG;
     int* meta = S.meta + e * 8;
+    b.o_acc = P.el.l_accY;
+    b.o_accn = P.el.l_accYn;
     FOR_CELLS {
       for (int k = 0; k < C; k++) {
         const double x = gX[(size_t)k * LG + cell];
@@ -941,7 +952,7 @@ __device__ __forceinline__ void step_cta(const DevPlan& P, const DevState& S, co
         if (EXF) BA(XF, k) = (real)x;
       }
       for (int s = 0; s < EDIM(n_slot); s++) BA(mvY, s) = S.mvY[e * nM + (size_t)s * LG + cell];
-      for (int a_ = 0; a_ < EDIM(n_acc); a_++) BA(accY, a_) = gAcc[(size_t)a_ * LG + cell];
+      for (int a_ = 0; a_ < EDIM(n_acc); a_++) ACCY(a_) = gAcc[(size_t)a_ * LG + cell];
     }
     for (int i = b.tid; i < P.n_cls; i += b.nt) ET(mult_y, i) = S.multY[e * P.n_cls + i];
     for (int k = b.tid; k < P.NCP; k += b.nt) {
@@ -987,15 +998,18 @@ __device__ __forceinline__ void step_cta(const DevPlan& P, const DevState& S, co
         double x = BA(X, k);
         gX[(size_t)k * LG + cell] = x;
         if (a.obs_out) ((real*)a.obs_out)[e * CLG + (size_t)k * LG + cell] = (real)x;
+        if (a.obs_out2) ((real*)a.obs_out2)[e * CLG + (size_t)k * LG + cell] = (real)x;
       }
       for (int s = 0; s < EDIM(n_slot); s++) S.mvY[e * nM + (size_t)s * LG + cell] = BA(mvY, s);
-      for (int a_ = 0; a_ < EDIM(n_acc); a_++) gAcc[(size_t)a_ * LG + cell] = BA(accY, a_);
+      for (int a_ = 0; a_ < EDIM(n_acc); a_++) gAcc[(size_t)a_ * LG + cell] = ACCY(a_);
     }
     for (int i = b.tid; i < P.n_cls; i += b.nt) S.multY[e * P.n_cls + i] = ET(mult_y, i);
     if (b.tid == 0) {
       meta[0] = t_day; meta[1] = ex_y;
       if (a.reward_out) a.reward_out[env] = reward;
       if (a.done_out) a.done_out[env] = (uint8_t)(t_day >= P.horizon);
+      if (a.reward_out2) a.reward_out2[env] = reward;
+      if (a.done_out2) a.done_out2[env] = (uint8_t)(t_day >= P.horizon);
     }
     __syncthreads();
   }

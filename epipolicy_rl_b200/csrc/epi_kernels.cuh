@@ -719,6 +719,11 @@ struct StepArgs {
   void* obs_out;          // real [N,CLG] or null
   double* reward_out;     // [N] or null
   uint8_t* done_out;      // [N] or null
+  // second destination of the same results (epi_bind_mirror): the learner rank's receive buffer, mapped peer memory
+  // over NVLink - the epilogue's stores ARE the gather, overlapped with the envs still being stepped
+  void* obs_out2;
+  double* reward_out2;
+  uint8_t* done_out2;
   char* big_scratch;      // n_teams * big_bytes when !big_in_smem
   char* small_scratch;    // n_teams * small_bytes when !small_in_smem
   double* dbg_attempts;   // optional [N,64,2]: (h, error_norm) of each attempted RK step of the last day

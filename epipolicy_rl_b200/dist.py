@@ -65,3 +65,58 @@ class LearnerGather:
         """[(obs, reward, done) of rank r for r in range(world)] as views of the receive buffer."""
         n = self.layout.nbytes
         return [self.layout.views(self.recv[r * n:(r + 1) * n]) for r in range(self.world)]
+
+
+class PeerGather:
+    """Gather to the learner rank WITHOUT a collective call: every rank maps the learner's receive buffer (symmetric
+    memory over NVLink / NVSwitch, torch.distributed._symmetric_memory) and binds its own slice of it as the
+    engine's mirror output (engine.bind_mirror): the step kernel's epilogue stores each env's obs / reward / done
+    into the learner's memory as the env finishes, overlapped with the envs still being stepped. What remains
+    per gym step is one device-side barrier over the signal pads, so that the learner reads complete records.
+    Same record layout as LearnerGather; `gathered()` is valid on the learner rank."""
+
+    def __init__(self, eng, world: int, learner: int = 0, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.layout = PackedLayout(eng.n_envs, eng.obs_dim, eng.dtype)
+        self.world, self.learner, self.rank = world, learner, dist.get_rank(group)
+        n = self.layout.nbytes
+        self.recv = symm.empty(world * n, dtype=torch.uint8, device=eng.device)
+        self.recv.zero_()
+        self.hdl = symm.rendezvous(self.recv, group if group is not None else dist.group.WORLD)
+        peer = self.hdl.get_buffer(learner, (world * n,), torch.uint8)  # the learner's buffer, mapped here
+        self.mine = self.layout.views(peer[self.rank * n:(self.rank + 1) * n])
+        eng.bind_mirror(*self.mine)
+        self.eng = eng
+
+    def __call__(self, obs=None, rew=None, done=None):
+        # the kernel has already stored this rank's records into the learner's buffer: order the reader behind every
+        # rank's step kernel (stream-ordered barrier on the signal pads)
+        self.hdl.barrier(channel=0)
+        return self.gathered() if self.rank == self.learner else None
+
+    def gathered(self):
+        n = self.layout.nbytes
+        return [self.layout.views(self.recv[r * n:(r + 1) * n]) for r in range(self.world)]
+
+    def close(self):
+        self.eng.bind_mirror(None, None, None)
+
+
+def make_gather(eng, world: int, prefer_peer: bool = True):
+    """PeerGather when symmetric memory can be set up on this box, else the NCCL all-gather. All ranks take the same
+    branch (the outcome is agreed with an all-reduce)."""
+    g, ok = None, 0
+    if prefer_peer and eng.device.type == "cuda":
+        try:
+            g = PeerGather(eng, world)
+            ok = 1
+        except Exception as e:  # noqa: BLE001 - no symmetric memory on this box / build
+            import sys
+            print(f"[epi-b200] peer-memory gather unavailable ({type(e).__name__}: {e}); using NCCL all-gather", file=sys.stderr)
+    t = torch.tensor([ok], device=eng.device, dtype=torch.int32)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if int(t.item()) == 1:
+        return g, "peer-memory stores in the step kernel epilogue + signal-pad barrier (no collective call)"
+    if g is not None:
+        g.close()
+    return LearnerGather(eng, world), "all_gather obs/reward/done"

@@ -84,6 +84,16 @@ class BatchedEpidemic:
         obs.copy_(self.obs); reward.copy_(self.reward); done.copy_(self.done)
         self.obs, self.reward, self.done = obs, reward, done
 
+    def bind_mirror(self, obs: torch.Tensor | None, reward: torch.Tensor | None, done: torch.Tensor | None) -> None:
+        """Second destination of every following step's results, written by the kernel epilogue itself: tensors that
+        alias the learner rank's receive buffer (peer memory, dist.PeerGather). None unbinds."""
+        if obs is not None:
+            assert obs.shape == (self.n_envs, self.obs_dim) and obs.dtype == self.dtype and obs.is_contiguous()
+            assert reward.shape == (self.n_envs,) and reward.dtype == torch.float64
+            assert done.shape == (self.n_envs,) and done.dtype == torch.uint8
+        self._mirror = (obs, reward, done)  # keep the mappings alive
+        self._ck(self.L.epi_bind_mirror(self._h, *(None if t is None else t.data_ptr() for t in (obs, reward, done))))
+
     # ---------------------------------------------------------------------------------
     def reset(self, mask: torch.Tensor | None = None) -> torch.Tensor:
         """Epidemic.reset (epidemic.py:104-106) for all envs, or those where mask != 0."""

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libepi_b200.so")
 EPI_FP64, EPI_FP32 = 0, 1
 EXPORTS = ["epi_create", "epi_destroy", "epi_last_error", "epi_info", "epi_reset", "epi_step", "epi_step_plan",
            "epi_step_host", "epi_get_state", "epi_set_state", "epi_launch_count", "epi_spec_source", "epi_spec_source_desc",
-           "epi_spec_attach", "epi_host_buffers"]
+           "epi_spec_attach", "epi_host_buffers", "epi_bind_mirror"]
 
 
 class EpiInfo(ctypes.Structure):
@@ -76,6 +76,8 @@ def bind(L):
     L.epi_spec_source_desc.argtypes = [ctypes.POINTER(CEpiDesc), I, P, SZ, ctypes.POINTER(SZ)]
     L.epi_host_buffers.restype = I
     L.epi_host_buffers.argtypes = [P, ctypes.POINTER(P), ctypes.POINTER(P), ctypes.POINTER(P), ctypes.POINTER(P)]
+    L.epi_bind_mirror.restype = I
+    L.epi_bind_mirror.argtypes = [P, P, P, P]
     L.epi_spec_attach.restype = I
     L.epi_spec_attach.argtypes = [P, ctypes.c_char_p]
     return L

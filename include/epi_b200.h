@@ -75,6 +75,14 @@ int epi_step_plan(epi_t* h, const float* cpv_dev, const uint8_t* active_dev, int
 int epi_step_host(epi_t* h, const float* actions_host, int n_days, void* obs_out_host, double* reward_out_host,
                   uint8_t* done_out_host);
 
+/* Second destination for the results of every following epi_step / epi_step_plan (any pointer may be NULL; all NULL
+ * unbinds): the kernel epilogue stores obs [n_envs, obs_dim] real, reward [n_envs] double and done [n_envs] uint8 there
+ * as well. Meant for the learner rank's receive buffer mapped into this process (peer memory over NVLink): the stores
+ * are the gather of SURVEY.md 8(e) (epipolicy_environment.py:56-62 returns obs/reward/done to the single caller; here
+ * the caller that learns sits on another GPU), overlapped with the environments still being stepped. The caller
+ * orders the reader behind the launch (stream + cross-rank barrier). */
+int epi_bind_mirror(epi_t* h, void* obs_dev, double* reward_dev, uint8_t* done_dev);
+
 /* The library's own pinned host buffers of the host path: actions float32 [n_envs, action_dim], obs real
  * [n_envs, obs_dim], reward double [n_envs], done uint8 [n_envs]. A caller that fills `*actions` and passes these
  * very pointers to epi_step_host gets the results in place, without the staging copies. Valid until epi_destroy;

@@ -90,7 +90,7 @@ inline void run_warps(int n_warps, int width, size_t smem_bytes, const std::func
 typedef int cudaError_t;
 typedef void* cudaStream_t;
 enum { cudaSuccess = 0 };
-enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
 enum { cudaStreamNonBlocking = 1, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 struct cudaDeviceProp { size_t sharedMemPerBlockOptin = 232448, sharedMemPerMultiprocessor = 233472; int multiProcessorCount = 148; };
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }

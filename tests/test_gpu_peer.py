@@ -1,0 +1,51 @@
+"""Two-GPU test of the collective-free gather (dist.PeerGather): every rank's step kernel stores its results into
+the learner rank's buffer over NVLink; the learner sees exactly what each rank computed locally."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import load
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, n, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    from epipolicy_rl_b200.dist import PeerGather
+    from epipolicy_rl_b200.engine import BatchedEpidemic
+    d, _ = load("COVID_C")
+    eng = BatchedEpidemic(d, n, device=rank, precision="fp32")
+    g = PeerGather(eng, world)
+    gen = torch.Generator().manual_seed(100 + rank)
+    for step in range(3):
+        a = torch.rand((n, d.A), generator=gen).cuda()
+        obs, rew, done = eng.step(a, 7)
+        got = g()
+        # reference exchange through NCCL for the check
+        all_obs = [torch.empty_like(obs) for _ in range(world)]
+        all_rew = [torch.empty_like(rew) for _ in range(world)]
+        dist.all_gather(all_obs, obs.contiguous())
+        dist.all_gather(all_rew, rew.contiguous())
+        if rank == 0:
+            for r in range(world):
+                assert torch.equal(got[r][0], all_obs[r]), (step, r)
+                assert torch.equal(got[r][1], all_rew[r]), (step, r)
+                assert not got[r][2].any()
+        g.hdl.barrier(channel=1)  # nobody overwrites the learner's buffer before it has been checked
+    if rank == 0:
+        open(os.path.join(out, "ok"), "w").write("1")
+    eng.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_peer_gather_two_gpus(tmp_path):
+    port = 29700 + os.getpid() % 200
+    mp.spawn(_worker, args=(2, port, 100, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok").exists()
