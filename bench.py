@@ -56,6 +56,18 @@ def algorithmic_bytes(desc, info, w, fused_days):
     return base, ctrl
 
 
+def algorithmic_flops(desc, info, nfev_per_day, fused_days):
+    """fp32 flops one env needs per launch, after the obvious algebra (one force-of-infection
+    numerator per distinct weighted infectious sum n_w, one shared denominator): per right-hand-side evaluation
+    2 nnz G (n_w+1) [CSC gathers] + 2 L F G^2 (n_w+1) [G x G mixing] + 3 L G F n_w + 2 nnz G n_w [CSR gather]
+    + 4 E L G + 2 C L G [edges, scatter, alive], plus the RK45 stage algebra 2*7*C*L*G per evaluation."""
+    C, L, G, F = desc.C, desc.L, desc.G, desc.F
+    nnz, E, nw = int(desc.scalars["nnz"]), int(desc.scalars["E"]), max(1, info.n_groups_inf)
+    rhs = (2 * nnz * G * (nw + 1) + 2 * L * F * G * G * (nw + 1) + 3 * L * G * F * nw + 2 * nnz * G * nw
+           + 4 * E * L * G + 2 * C * L * G)
+    return fused_days * nfev_per_day * (rhs + 2 * 7 * C * L * G)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
 
@@ -265,6 +277,13 @@ def run_ours(args):
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(f"{args.workload}:{args.precision}:{n_envs}", {}).get("dram_bytes_per_launch")
+        # the second roofline (SURVEY.md §8d asks for both): algorithmic fp32 flops against the CUDA-core peak
+        # 148 SMs x 128 lanes x 2 x SM clock; nfev of the last simulated day of this run, averaged over the envs
+        nfev = float(eng.get_state("trace")[:, 0].mean())
+        flops = algorithmic_flops(desc, info, nfev, PERIOD)
+        sm_ghz = (clocks.get("sm_max_mhz") or 1965.0) / 1e3
+        fp32_peak = 148 * 128 * 2 * sm_ghz / 1e3  # TFLOP/s
+        fp32_ach = n_envs * flops / (ms_per_step * 1e-3) / 1e12
         cpu_v, cpu_dt, cpu_ne, cpu_ns = cpu_port_rate(desc, args.cpu_sample_envs, args.cpu_sample_steps)
         line = {
             "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -279,7 +298,10 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "bytes_per_env_launch": base_b,
                          "bytes_per_env_launch_with_rk45_accumulators": ctrl_b,
-                         "frac_with_rk45_accumulators": n_envs * ctrl_b / (ms_per_step * 1e-3) / 1e9 / peak},
+                         "frac_with_rk45_accumulators": n_envs * ctrl_b / (ms_per_step * 1e-3) / 1e9 / peak,
+                         "fp32_cuda_core": {"achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s",
+                                            "frac": fp32_ach / fp32_peak, "flops_per_env_launch": flops,
+                                            "nfev_per_day": nfev}},
             "cpu_baseline": {"value": cpu_v, "unit": "env-steps/s", "cores": 1, "kind": "port",
                              "sample": f"{cpu_ne} envs x {cpu_ns} gym steps, {cpu_dt:.1f} s, "
                                        "oracle/epi_oracle.c single thread"},

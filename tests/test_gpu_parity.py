@@ -276,3 +276,32 @@ def test_batched_ppo_runs_on_device():
     assert len(hist) == 2 and all(np.isfinite(h["mean_step_reward"]) and h["mean_step_reward"] < 0 for h in hist)
     assert np.isfinite(hist[-1]["v_loss"])
     env.close()
+
+
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+def test_full_size_properties_covid_c_4096(prec):
+    """BASELINE.json configs[2] at full size through properties that do not need the oracle:
+    (1) people are conserved per (locale, group): sum over compartments == population (deaths are a compartment,
+        mobility moves infection pressure, not residents);
+    (2) env independence: an env's trajectory does not depend on its position in the batch or on the batch size
+        (bit-identical between a 4096-env batch and a 9-env batch fed the same actions);
+    (3) permutation: reversing the env order of the actions reverses the results bit for bit."""
+    d, _ = load("COVID_C")
+    n, steps = 4096, 12
+    acts = torch.rand((steps, n, d.A), generator=torch.Generator().manual_seed(1234))
+    pick = torch.tensor([0, 1, 2, 3, 1000, 2047, 4093, 4094, 4095])
+    big, small, rev = _engine(d, n, prec), _engine(d, len(pick), prec), _engine(d, n, prec)
+    for s in range(steps):
+        ob, rb, _ = big.step(acts[s].cuda(), 7)
+        os_, rs, _ = small.step(acts[s][pick].cuda(), 7)
+        orv, rrv, _ = rev.step(acts[s].flip(0).cuda(), 7)
+        assert torch.equal(ob[pick.cuda()], os_) and torch.equal(rb[pick.cuda()], rs), s
+        assert torch.equal(ob, orv.flip(0)) and torch.equal(rb, rrv.flip(0)), s
+    X = big.get_state("X")  # [N, C, L, G] float64
+    pop = d.pop.reshape(1, d.L, d.G)
+    cons = np.max(np.abs(X.sum(1) - pop) / pop)
+    print(f"COVID_C x4096 {prec}: population conservation {cons:.2e}")
+    assert cons <= (1e-9 if prec == "fp64" else 1e-5)
+    assert np.all(X > -1e-6 * pop[:, None]) and np.all(rb.cpu().numpy() < 0)
+    for e in (big, small, rev):
+        e.close()
