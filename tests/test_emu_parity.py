@@ -149,3 +149,26 @@ def test_fused_week_fp32_reuses_last_stage_across_days(name, knobs, monkeypatch)
     print(f"{name} fused fp32: X {worst:.2e}")
     assert worst <= TOL["fp32"]
     fused.close(); daily.close()
+
+
+@pytest.mark.parametrize("knobs", [{}, {"EPI_TEAM": "env"}, {"EPI_TEAM": "warp"}], ids=["cell", "env", "warp-team"])
+def test_mirror_outputs_equal_primary_outputs(knobs, monkeypatch):
+    """epi_bind_mirror: the second destination (the learner rank's buffer on a GPU box) receives exactly the primary
+    results, from the epilogue of the cell / env kernels and from the copy behind the launch for the team kernels;
+    ragged last warp (7 envs); unbinding stops the writes."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    d, _ = load("COVID_C")
+    n = 7
+    eng = EmuEngine(d, n, "fp32")
+    obs2 = np.full((n, d.C * d.L * d.G), -1, np.float32)
+    rew2, done2 = np.full(n, -1.0), np.full(n, 9, np.uint8)
+    eng._ck(eng.L.epi_bind_mirror(eng._h, obs2.ctypes.data, rew2.ctypes.data, done2.ctypes.data))
+    a = np.random.default_rng(4).uniform(0, 1, (n, d.A)).astype(np.float32)
+    obs, rew, done = eng.step(a, 7)
+    assert np.array_equal(obs2, obs) and np.array_equal(rew2, rew) and np.array_equal(done2, done)
+    eng._ck(eng.L.epi_bind_mirror(eng._h, None, None, None))
+    keep = obs2.copy()
+    eng.step(a, 7)
+    assert np.array_equal(obs2, keep) and not np.array_equal(eng.obs, keep)
+    eng.close()
