@@ -172,3 +172,41 @@ def test_mirror_outputs_equal_primary_outputs(knobs, monkeypatch):
     eng.step(a, 7)
     assert np.array_equal(obs2, keep) and not np.array_equal(eng.obs, keep)
     eng.close()
+
+
+def test_create_rejects_bad_arguments():
+    """C-ABI error behaviour (integer codes, never throw across the boundary)."""
+    import ctypes
+    from epipolicy_rl_b200 import lib
+    d, _ = load("SIR_A")
+    L = EmuEngine(d, 1).L
+    c, h = d.as_c(), ctypes.c_void_p()
+    assert L.epi_create(None, 1, 0, 0, ctypes.byref(h)) == -1
+    assert L.epi_create(ctypes.byref(c), 0, 0, 0, ctypes.byref(h)) == -1   # empty batch
+    assert L.epi_create(ctypes.byref(c), -3, 0, 0, ctypes.byref(h)) == -1
+    assert L.epi_create(ctypes.byref(c), 1, 0, 7, ctypes.byref(h)) == -1   # unknown precision
+    assert L.epi_create(ctypes.byref(c), 1, 0, 0, None) == -1
+    assert L.epi_last_error(None)  # a message is available without a handle
+    assert L.epi_step(None, None, 7, None, None, None, None) == -1
+    assert L.epi_bind_mirror(None, None, None, None) == -1
+    with pytest.raises(lib.EpiError):
+        e = EmuEngine(d, 2)
+        e._ck(L.epi_step(e._h, None, 7, e.obs.ctypes.data, e.reward.ctypes.data, e.done.ctypes.data, None))  # no actions
+
+
+def test_stepping_past_the_horizon_keeps_simulating():
+    """No auto-reset (epidemic.py:116, baselines.py:29-52 steps 100 000 times without reset): done stays set, the day
+    counter and the state keep advancing; a fused week stops at the horizon day."""
+    d, _ = load("SIR_A")
+    eng = EmuEngine(d, 1, "fp64")
+    a = np.full((1, d.A), 0.5, np.float32)
+    for _ in range(52):
+        _, _, done = eng.step(a, 7)
+        assert not done[0]
+    _, _, done = eng.step(a, 7)  # days 364 (horizon 365): only one of the 7 days runs
+    assert done[0] and eng.get_state("day")[0] == 365
+    x = eng.get_state("X").copy()
+    _, r, done = eng.step(a, 7)
+    assert done[0] and eng.get_state("day")[0] > 365 and r[0] < 0
+    assert not np.array_equal(eng.get_state("X"), x)
+    eng.close()
