@@ -80,7 +80,15 @@ class BatchedPPO:
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self._obs = None
         self.ep_return = None
-        self.finished_returns = []
+        # finished episodes of this rank's shard, kept on the device (no host sync inside the rollout)
+        self._fin_sum = torch.zeros((), dtype=torch.float64, device=self.dev)
+        self._fin_cnt = torch.zeros((), dtype=torch.int64, device=self.dev)
+
+    @property
+    def finished_episodes(self) -> tuple[int, float]:
+        """(count, mean return) of the episodes finished so far on this rank (one host sync)"""
+        n = int(self._fin_cnt)
+        return n, (float(self._fin_sum) / n if n else math.nan)
 
     def _norm(self, obs):
         return obs.to(torch.float32) / self.obs_scale
@@ -105,18 +113,22 @@ class BatchedPPO:
             obs, rew, done, _ = self.env.step(a.clamp(0.0, 1.0).contiguous())
             self.ep_return += rew
             d = done.to(torch.bool)
-            if d.any():
-                self.finished_returns += self.ep_return[d].tolist()
-                self.ep_return[d] = 0
-                self.env.reset(done)
-                obs = self.env.epi.obs
-            # one packed exchange per gym step: what the learner needs from every shard
-            rec = torch.cat([o, a, lp[:, None], v[:, None], (rew.to(torch.float32) * self.reward_scale)[:, None],
-                             d.to(torch.float32)[:, None]], 1)
-            rec = self._all(rec)
-            nd, na = o.shape[1], a.shape[1]
-            O.append(rec[:, :nd]); A.append(rec[:, nd:nd + na]); LP.append(rec[:, nd + na]); V.append(rec[:, nd + na + 1])
-            R.append(rec[:, nd + na + 2]); D.append(rec[:, nd + na + 3])
+            # episode bookkeeping and the masked restart stay on the device: no `if d.any()` host round trip per step
+            self._fin_sum += torch.where(d, self.ep_return, torch.zeros_like(self.ep_return)).sum()
+            self._fin_cnt += d.sum()
+            self.ep_return = torch.where(d, torch.zeros_like(self.ep_return), self.ep_return)
+            r32 = rew.to(torch.float32) * self.reward_scale  # before the restart: reward may alias an engine buffer
+            d32 = d.to(torch.float32)
+            self.env.reset(done)  # restarts the envs whose flag is set (a launch that touches nothing otherwise)
+            obs = self.env.epi.obs
+            if self.world == 1:
+                O.append(o); A.append(a); LP.append(lp); V.append(v); R.append(r32); D.append(d32)
+            else:
+                # one packed exchange per gym step: what the learner needs from every shard
+                rec = self._all(torch.cat([o, a, lp[:, None], v[:, None], r32[:, None], d32[:, None]], 1))
+                nd, na = o.shape[1], a.shape[1]
+                O.append(rec[:, :nd]); A.append(rec[:, nd:nd + na]); LP.append(rec[:, nd + na]); V.append(rec[:, nd + na + 1])
+                R.append(rec[:, nd + na + 2]); D.append(rec[:, nd + na + 3])
             self._obs = obs.clone()
         last_v = self._all(self.ac.act(self._norm(self._obs))[2])
         return (torch.stack(O), torch.stack(A), torch.stack(LP), torch.stack(V), torch.stack(R), torch.stack(D), last_v)
@@ -157,9 +169,8 @@ class BatchedPPO:
             batch = self.collect()
             st = self.update(batch)
             mean_r = float(batch[4].sum(0).mean()) / self.reward_scale / self.n_steps
-            st.update(update=u, mean_step_reward=mean_r, episodes=len(self.finished_returns),
-                      mean_episode_return=(sum(self.finished_returns[-256:]) / max(1, len(self.finished_returns[-256:]))
-                                           if self.finished_returns else math.nan))
+            n_ep, mean_ep = self.finished_episodes
+            st.update(update=u, mean_step_reward=mean_r, episodes=n_ep, mean_episode_return=mean_ep)
             hist.append(st)
             if log and self.rank == 0:
                 log(st)
@@ -255,7 +266,9 @@ class BatchedSAC:
         self.learning_starts, self.reward_scale = learning_starts, reward_scale
         self.ring = ReplayRing(obs_dim, act_dim, buffer_size, self.dev) if self.rank == 0 else None
         self._obs, self.total_steps = None, 0
-        self.ep_return, self.finished_returns = None, []
+        self.ep_return = None
+        self._fin_sum = torch.zeros((), dtype=torch.float64, device=self.dev)
+        self._fin_cnt = torch.zeros((), dtype=torch.int64, device=self.dev)
 
     def _norm(self, obs):
         return obs.to(torch.float32) / self.obs_scale
@@ -282,12 +295,13 @@ class BatchedSAC:
         o2 = self._norm(obs)  # the terminal observation, before any reset
         self.ep_return += rew
         d = done.to(torch.bool)
-        if d.any():
-            self.finished_returns += self.ep_return[d].tolist()
-            self.ep_return[d] = 0
-            self.env.reset(done)
-            obs = self.env.epi.obs
+        self._fin_sum += torch.where(d, self.ep_return, torch.zeros_like(self.ep_return)).sum()
+        self._fin_cnt += d.sum()
+        self.ep_return = torch.where(d, torch.zeros_like(self.ep_return), self.ep_return)
         r = rew.to(torch.float32) * self.reward_scale
+        mean_r = rew.mean()
+        self.env.reset(done)  # masked restart, no host round trip
+        obs = self.env.epi.obs
         rec = self._all(torch.cat([o, a, r[:, None], o2, d.to(torch.float32)[:, None]], 1))
         if self.rank == 0:
             nd, na = o.shape[1], a.shape[1]
@@ -295,7 +309,7 @@ class BatchedSAC:
                             rec[:, 2 * nd + na + 1])
         self._obs = obs.clone()
         self.total_steps += rec.shape[0]
-        return float(rew.mean())
+        return mean_r
 
     def update(self):
         stats = {}
@@ -342,7 +356,7 @@ class BatchedSAC:
         for s in range(n_steps):
             mean_r = self.collect_step()
             st = self.update()
-            st.update(step=s, mean_step_reward=mean_r, episodes=len(self.finished_returns))
+            st.update(step=s, mean_step_reward=float(mean_r), episodes=int(self._fin_cnt))
             hist.append(st)
             if log and self.rank == 0:
                 log(st)

@@ -61,18 +61,22 @@ def main():
     lax[:, 0] = 2224526 * 0.9 / (12 * 30) / 9200  # baselines.py:35-39
     base = {"random": rollout_mean(lambda o: torch.rand((args.envs, desc.A), device=dev)),
             "lax": rollout_mean(lambda o: lax)}
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
+    log = lambda s: print(json.dumps(s), flush=True)  # noqa: E731
     if args.algo == "ppo":
         ppo = BatchedPPO(env, env.epi.obs_dim, desc.A, obs_scale=pop, n_steps=args.n_steps, lr=args.lr, device=dev)
-        hist = ppo.train(args.updates, log=lambda s: print(json.dumps(s), flush=True))
+        hist = ppo.train(1, log=log)  # first update untimed: cuBLAS / autograd / Adam state start-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        hist += ppo.train(args.updates, log=log)
         policy = lambda o: ppo.ac.act(ppo._norm(o), deterministic=True)[0].clamp(0, 1).contiguous()  # noqa: E731
     else:
         # the same number of gym steps as the PPO run: `updates` x `n_steps` collect steps, gradient steps after each
         sac = BatchedSAC(env, env.epi.obs_dim, desc.A, obs_scale=pop, lr=args.lr, batch_size=4096, gamma=0.98, tau=0.08,
                          gradient_steps=8, device=dev)
-        hist = sac.train(args.updates * args.n_steps,
-                         log=lambda s: print(json.dumps(s), flush=True) if s["step"] % args.n_steps == 0 else None)
+        hist = sac.train(args.n_steps)  # untimed start-up, as above
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        hist += sac.train(args.updates * args.n_steps, log=lambda s: log(s) if s["step"] % args.n_steps == 0 else None)
         policy = lambda o: sac.actor(sac._norm(o), deterministic=True, with_logprob=False)[0].contiguous()  # noqa: E731
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
