@@ -433,8 +433,22 @@ def export_static(epi) -> EpiDesc:
         control_params=[[str(c.name) for c in itv.cp_list] for itv in st.interventions],
         total_population=float(np.sum(a["X0"])),
         n_action_interventions=sum(1 for itv in st.interventions if not itv.is_cost),
+        reporter=reporter_meta(st),
     )
     return d.finalize()
+
+
+def reporter_meta(st) -> dict:
+    """What reporter.py needs from the Static: the hashed incidence edges (core_utils.py:243-254) as (c1, c2) pairs
+    and the INF-tagged compartments (get_matrix_with_tag, core_optimize.py:10-16)."""
+    from epipolicy.utility.singleton import INF_TAG
+    C = st.compartment_count
+    inf = [0.0] * C
+    if st.has_property_name("compartment_tag", INF_TAG):
+        ti = st.get_property_index("compartment_tag", INF_TAG)
+        inf = [float(st.compartment_tags[c, ti]) for c in range(C)]
+    return {"incidence_edges": [[int(h) // C, int(h) % C] for h in sorted(int(h) for h in st.hashed_incidence_edges)],
+            "inf_comps": inf}
 
 
 def export_initial_parameter(epi) -> dict:
