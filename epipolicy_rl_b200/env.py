@@ -68,7 +68,14 @@ class BatchedEpiEnv:
         self.epi.close()
 
 
-class EpiEnv:
+try:  # pragma: no cover - gym is not in this image; with it the twin is a real gym.Env (SB3's Monitor checks)
+    import gym as _gym
+    _EnvBase = _gym.Env
+except Exception:  # noqa: BLE001
+    _EnvBase = object
+
+
+class EpiEnv(_EnvBase):
     """Single-environment twin of the reference's EpiEnv."""
 
     metadata = {"render.modes": ["human"]}

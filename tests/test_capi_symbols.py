@@ -73,3 +73,16 @@ def test_engine_fails_loudly_without_cuda():
     d, _ = load("SIR_A")
     with pytest.raises(RuntimeError):
         BatchedEpidemic(d, 4)
+
+
+def test_compat_module_has_the_reference_module_surface():
+    """epipolicy_rl_b200/compat/epipolicy_environment.py stands in for the reference module of the same name
+    (epipolicy_environment.py:1-71): PERIOD and an EpiEnv class with the gym surface."""
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "epipolicy_rl_b200", "compat", "epipolicy_environment.py")
+    spec = importlib.util.spec_from_file_location("epipolicy_environment_compat", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.PERIOD == 7
+    for name in ("reset", "step", "render", "close"):
+        assert callable(getattr(mod.EpiEnv, name))
