@@ -112,3 +112,29 @@ def test_sac_learns_on_toy_env():
     first = np.mean([h["mean_step_reward"] for h in hist[:10]])
     last = np.mean([h["mean_step_reward"] for h in hist[-10:]])
     assert last > first + 0.02, (first, last)
+
+
+def _sac_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from epipolicy_rl_b200.learner import BatchedSAC
+    env = ToyEnv(32, seed=rank)
+    sac = BatchedSAC(env, 3, 2, obs_scale=np.ones(3), gamma=0.0, lr=1e-3, batch_size=64, buffer_size=4096,
+                     gradient_steps=2, reward_scale=1.0, device="cpu", seed=5 + rank)
+    for _ in range(12):  # episodes of 8 steps: the masked restart path is exercised
+        sac.collect_step()
+        sac.update()
+    if rank == 0:
+        assert sac.ring.n == 12 * 64  # the transitions of both shards land in the learner's ring
+    else:
+        assert sac.ring is None
+    flat = torch.cat([p.data.reshape(-1) for p in sac.actor.parameters()])
+    torch.save(flat, os.path.join(out, f"a{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_sac_two_rank_ring_on_learner_and_actor_broadcast(tmp_path):
+    port = 29800 + os.getpid() % 150
+    mp.spawn(_sac_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a0, a1 = torch.load(tmp_path / "a0.pt"), torch.load(tmp_path / "a1.pt")
+    assert torch.equal(a0, a1)  # different seeds per rank, same actor after the broadcast
