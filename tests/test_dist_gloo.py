@@ -55,3 +55,39 @@ def test_learner_gather_world2_gloo(tmp_path):
     assert np.array_equal(z["obs"], ids[:, None] * 10.0 + np.arange(obs_dim)[None])
     assert np.array_equal(z["rew"], -ids.astype(np.float64))
     assert np.array_equal(z["done"], (ids % 2).astype(np.uint8))
+
+
+class _FakeEngine:
+    """what dist.make_gather / LearnerGather use of a BatchedEpidemic"""
+
+    def __init__(self, n, obs_dim):
+        self.n_envs, self.obs_dim, self.dtype, self.device = n, obs_dim, torch.float32, torch.device("cpu")
+        self.obs = torch.zeros((n, obs_dim))
+        self.reward = torch.zeros(n, dtype=torch.float64)
+        self.done = torch.zeros(n, dtype=torch.uint8)
+
+    def bind_outputs(self, obs, reward, done):
+        self.obs, self.reward, self.done = obs, reward, done
+
+
+def _fallback_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    from epipolicy_rl_b200.dist import LearnerGather, make_gather
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    eng = _FakeEngine(4, 3)
+    g, kind = make_gather(eng, world)  # no CUDA device: every rank agrees on the all-gather
+    assert isinstance(g, LearnerGather) and kind.startswith("all_gather")
+    eng.obs.fill_(float(rank + 1))  # the "kernel" writes into the bound send buffer
+    parts = g(eng.obs, eng.reward, eng.done)
+    assert all(float(parts[r][0].mean()) == r + 1 for r in range(world))
+    if rank == 0:
+        open(out, "w").write("ok")
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_make_gather_falls_back_to_all_gather_without_peer_memory(tmp_path):
+    out = str(tmp_path / "ok")
+    mp.spawn(_fallback_worker, args=(2, 29300 + os.getpid() % 150, out), nprocs=2, join=True)
+    assert os.path.exists(out)
