@@ -1,0 +1,43 @@
+"""Fresh inputs (not in the golden files): the emulated kernels against the CPU oracle on random weekly actions, every
+shipped scenario, both precisions; and the same through the env kernel. The oracle itself is pinned against the
+reference in test_oracle_golden.py."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+from conftest import SCENARIOS  # noqa: E402
+from emu_engine import EmuEngine  # noqa: E402
+from helpers import cost_err, load, x_err  # noqa: E402
+
+from oracle.oracle import Oracle  # noqa: E402
+
+TOL = {"fp64": 1e-9, "fp32": 1e-4}
+
+
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_random_weekly_actions_vs_oracle(name, prec):
+    d, _ = load(name)
+    n, weeks = 4, 6
+    rng = np.random.default_rng(sum(name.encode()) + (0 if prec == "fp64" else 7))
+    acts = rng.uniform(0, 1, (weeks, n, d.A)).astype(np.float32)
+    acts[2, 1] = acts[1, 1]      # a repeated action: the "parameters do not move" path on the first day of a week
+    acts[3, 2] = 0.0             # boundary values of the action box
+    acts[4, 3] = 1.0
+    eng = EmuEngine(d, n, prec)
+    oracles = [Oracle(d) for _ in range(n)]
+    worst, worst_c, worst_r = 0.0, 0.0, 0.0
+    for w in range(weeks):
+        obs, rew, done = eng.step(acts[w], 7)
+        for e, o in enumerate(oracles):
+            o_obs, o_rew, o_done = o.step(acts[w, e], 7)
+            worst = max(worst, x_err(obs[e], o_obs, d))
+            worst_c = max(worst_c, cost_err(eng.get_state("cost")[e], o.cost))
+            worst_r = max(worst_r, abs(rew[e] - o_rew) / abs(o_rew))
+            assert bool(done[e]) == bool(o_done)
+    print(f"{name} {prec}: X {worst:.2e} cost {worst_c:.2e} reward {worst_r:.2e}")
+    assert worst <= TOL[prec] and worst_c <= TOL[prec] and worst_r <= TOL[prec]
+    eng.close()
