@@ -45,7 +45,11 @@ using namespace rk;
 #define EPI_LW (spec::LW)
 #define SLOT_C1(i) (spec::slot_c1[i])
 #define SLOT_C2(i) (spec::slot_c2[i])
+#ifdef EPI_HOST_EMU
+static thread_local char* cell_smem = nullptr;  // the emulated warp's block (tests: a specialised build on the host)
+#else
 extern __shared__ __align__(16) char cell_smem[];
+#endif
 #define COLP(arr) ((T_##arr*)(::epi::cell::cell_smem + spec::l_##arr))
 #define ENVP(arr) ((T_##arr*)(::epi::cell::cell_smem + (spec::e_base + spec::e_##arr) + c.ebase))
 #else
@@ -1024,6 +1028,9 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, const Cx& c, bool on,
 template <class real>
 __device__ __forceinline__ void step_warp(const DevPlan& P, const DevState& S, const StepArgs& a, char* warp_base,
                                           int lane, int group) {
+#if defined(EPI_SPEC) && defined(EPI_HOST_EMU)
+  cell_smem = warp_base;
+#endif
   Cx c;
   bind(P, warp_base, lane, c);
   const int C = DIM(C), CLG = DIM(CLG), LG = DIM(LG), nA = DIM(n_acc) * LG, nC = DIM(I) * DIM(L), nM = DIM(n_slot) * LG;

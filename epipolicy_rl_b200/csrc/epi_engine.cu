@@ -1224,7 +1224,10 @@ void launch_cell(epi_engine* h, const DevState& S, const epi::StepArgs& a, cudaS
   const int grid = (a.N + epw - 1) / epw;
 #ifdef EPI_HOST_EMU
   (void)st;
-  if (h->plan.cl.roles > 1)
+  if (h->spec_launch) {
+    if (h->spec_launch(&h->plan, &S, &a, grid, h->cellW, (size_t)h->plan.cl.warp_bytes, nullptr) != 0)
+      throw Invalid{"specialised cell kernel (host emulation)"};
+  } else if (h->plan.cl.roles > 1)
     emu::run_warps(grid, h->cellW * h->plan.cl.roles, (size_t)h->plan.cl.warp_bytes, [&](char* smem, int tid, int group) {
       epi::cteam::step_cta<real>(h->plan, S, a, smem, tid, group);
     });
@@ -1256,6 +1259,10 @@ void launch_env(epi_engine* h, const DevState& S, const epi::StepArgs& a, cudaSt
   const int grid = a.N < h->grid ? a.N : h->grid;
 #ifdef EPI_HOST_EMU
   (void)st;
+  if (h->spec_launch) {
+    if (h->spec_launch(&h->plan, &S, &a, grid, h->threads, h->smem_bytes, nullptr) != 0)
+      throw Invalid{"specialised env kernel (host emulation)"};
+  } else
   emu::run_warps(grid, h->threads, h->smem_bytes, [&](char* smem, int tid, int cta) {
     epi::env::Bx b = epi::env::bind(h->plan, a, smem, tid, h->threads, cta);
     epi::env::step_cta<real>(h->plan, S, a, b, cta, grid);
@@ -1668,9 +1675,9 @@ int epi_spec_attach(epi_t* h, const char* so_path) {
   if (!h || !so_path) return EPI_E_INVALID;
   return guarded(h, [&] {
     if (h->cta_mode < 2) throw Unsupported{"scenario specialisation exists for the cell and env kernels only"};
-#ifdef EPI_HOST_EMU
-    throw Unsupported{"no specialised kernels in the host emulation"};
-#else
+    // the generated build is the cell kernel for L*G <= 32 and the env kernel above: a kernel kind forced with EPI_TEAM
+    // (debugging aid) on the other side of that line has no specialised build and runs interpreted
+    if ((h->cta_mode == 3) != (h->plan.LG > 32)) throw Unsupported{"no specialised build for the forced kernel kind"};
     void* lib = dlopen(so_path, RTLD_NOW | RTLD_LOCAL);
     if (!lib) throw Invalid{std::string("dlopen failed: ") + dlerror()};
     auto keyf = (const char* (*)())dlsym(lib, "epi_spec_key");
@@ -1684,7 +1691,6 @@ int epi_spec_attach(epi_t* h, const char* so_path) {
     }
     h->spec_lib = lib;
     h->spec_launch = lf;
-#endif
   });
 }
 

@@ -16,6 +16,25 @@
 
 extern "C" const char* epi_spec_key() { return EPI_SPEC_KEY; }
 
+#ifdef EPI_HOST_EMU
+// tests only: the same specialised code on the host (tests/emu/cuda_runtime.h), warps / CTAs as lock-stepped pthreads
+extern "C" int epi_spec_launch(const DevPlan* P, const DevState* S, const epi::StepArgs* a, int grid, int threads,
+                               size_t smem, void*) {
+#if EPI_SPEC_BIG
+  emu::run_warps(grid, threads, smem, [&](char* sm, int tid, int cta) {
+    epi::env::Bx b = epi::env::bind(*P, *a, sm, tid, threads, cta);
+    epi::env::step_cta<epi::spec::real>(*P, *S, *a, b, cta, grid);
+  });
+#elif EPI_SPEC_ROLES > 1
+  return -1;
+#else
+  emu::run_warps(grid, threads, smem, [&](char* sm, int lane, int group) {
+    epi::cell::step_warp<epi::spec::real>(*P, *S, *a, sm, lane, group);
+  });
+#endif
+  return 0;
+}
+#else
 extern "C" int epi_spec_launch(const DevPlan* P, const DevState* S, const epi::StepArgs* a, int grid, int threads,
                                size_t smem, void* stream) {
   auto kern = EPI_SPEC_KERNEL;
@@ -24,3 +43,4 @@ extern "C" int epi_spec_launch(const DevPlan* P, const DevState* S, const epi::S
   kern<<<grid, threads, smem, (cudaStream_t)stream>>>(*P, *S, *a);
   return (int)cudaGetLastError();
 }
+#endif

@@ -48,7 +48,9 @@ class BatchedEpidemic:
             from . import spec as _spec
             path = _spec.ensure(desc, self.precision)
             if path is not None:
-                self._ck(self.L.epi_spec_attach(self._h, path.encode()))
+                rc = self.L.epi_spec_attach(self._h, path.encode())
+                if rc != -2:  # EPI_E_UNSUPPORTED: a kernel kind forced with EPI_TEAM has no specialised build
+                    self._ck(rc)
                 self._ck(self.L.epi_info(self._h, ctypes.byref(self.info)))
         with torch.cuda.device(dev):
             self.obs = torch.empty((self.n_envs, self.obs_dim), dtype=self.dtype, device=dev)

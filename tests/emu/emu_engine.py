@@ -74,3 +74,33 @@ class EmuEngine:
         out = np.empty(spec[1], spec[2])
         self._ck(self.L.epi_get_state(self._h, spec[0], out.ctypes.data, out.nbytes))
         return out
+
+    def attach_spec(self):
+        """Compile the scenario-specialised build of this engine's kernel FOR THE HOST (the generated header +
+        csrc/epi_spec_main.cu with -DEPI_HOST_EMU) and attach it: the generated per-cell program, prologue tables and
+        constexpr layout are then what the emulated warps run."""
+        import re
+        import subprocess
+        need = ctypes.c_size_t()
+        self._ck(self.L.epi_spec_source(self._h, None, 0, ctypes.byref(need)))
+        buf = ctypes.create_string_buffer(need.value)
+        self._ck(self.L.epi_spec_source(self._h, buf, need.value, None))
+        text = buf.value.decode()
+        key = re.search(r'EPI_SPEC_KEY "([0-9a-f]+)"', text).group(1)
+        csrc = os.path.join(os.path.dirname(os.path.dirname(HERE)), "epipolicy_rl_b200", "csrc")
+        d = os.path.join(HERE, "_spec")
+        os.makedirs(d, exist_ok=True)
+        hdr, out = os.path.join(d, f"spec_{key}.h"), os.path.join(d, f"spec_{key}.so")
+        newest = max(os.path.getmtime(os.path.join(csrc, f)) for f in os.listdir(csrc))
+        newest = max(newest, os.path.getmtime(os.path.join(HERE, "cuda_runtime.h")))
+        if not os.path.exists(out) or os.path.getmtime(out) < newest:
+            with open(hdr, "w") as f:
+                f.write(text)
+            subprocess.check_call(["g++", "-x", "c++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off",
+                                   "-DEPI_HOST_EMU", f'-DEPI_SPEC_HEADER="{hdr}"', "-I", HERE, "-I", csrc,
+                                   "-include", os.path.join(HERE, "cuda_runtime.h"),  # nvcc includes it implicitly
+                                   "-Wno-unused-variable", "-pthread", "-o", out + ".tmp", os.path.join(csrc, "epi_spec_main.cu")])
+            os.replace(out + ".tmp", out)
+        self._ck(self.L.epi_spec_attach(self._h, out.encode()))
+        self.L.epi_info(self._h, ctypes.byref(self.info))
+        return key
