@@ -8,7 +8,7 @@ rank each step: the step kernel's epilogue stores them into rank 0's receive buf
 one device-side barrier per step), or, with --gather nccl / when symmetric memory is unavailable, one NCCL
 all-gather per step as the north_star words it.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload covid_c|syn_small|syn] [--envs E]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload syn|covid_c|sirv_b|syn_s|syn_m] [--envs E]
   python bench.py --impl reference ...   # the CPU restatement of the reference on all host cores
 """
 import argparse
@@ -26,21 +26,32 @@ sys.path.insert(0, ROOT)
 
 PERIOD = 7
 WORKLOADS = {
-    # name: (desc file or generator, default envs per GPU, description)
-    "covid_c": ("tests/golden/desc_COVID_C.npz", 4096, "COVID_C.json x 4096 envs per GPU, fp32, random actions (BASELINE.json configs[2])"),
-    "sirv_b": ("tests/golden/desc_SIRV_B.npz", 1024, "SIRV_B.json x 1024 envs per GPU (BASELINE.json configs[1])"),
-    "syn_s": ("tests/golden/desc_syn_s.npz", 4096, "synthetic COVID-like L=20 G=4 F=8 (epipolicy_rl_b200/synth.py)"),
-    "syn_m": ("tests/golden/desc_syn_m.npz", 1024, "synthetic COVID-like L=100 G=8 F=8 (epipolicy_rl_b200/synth.py)"),
-    "syn": ("tests/golden/desc_syn.npz", 296, "synthetic COVID-like L=1000 G=16 F=8 (BASELINE.json configs[3])"),
+    # name: (shipped scenario, default envs per GPU, description)
+    "syn": ("syn", 4096, "synthetic COVID-like L=1000 G=16 F=8 x 4096 envs per GPU, fp32, random actions "
+                         "(BASELINE.json configs[3]: 65536 envs = --envs 8192 at 8 GPUs; the 4096-env batch is the one "
+                         "the north_star roofline target is quoted on)"),
+    "covid_c": ("COVID_C", 4096, "COVID_C.json x 4096 envs per GPU, fp32, random actions (BASELINE.json configs[2])"),
+    "sirv_b": ("SIRV_B", 1024, "SIRV_B.json x 1024 envs per GPU (BASELINE.json configs[1])"),
+    "syn_s": ("syn_s", 4096, "synthetic COVID-like L=20 G=4 F=8 (epipolicy_rl_b200/synth.py)"),
+    "syn_m": ("syn_m", 1024, "synthetic COVID-like L=100 G=8 F=8 (epipolicy_rl_b200/synth.py)"),
 }
 
 
 def load_desc(workload):
-    from epipolicy_rl_b200.desc import EpiDesc
-    if workload in WORKLOADS:
-        return EpiDesc.load(os.path.join(ROOT, WORKLOADS[workload][0]))
-    from epipolicy_rl_b200 import synth
-    return synth.workload_desc(workload)
+    """shipped scenario descriptor (epipolicy_rl_b200/scenarios); pure Python, loads no native library"""
+    from epipolicy_rl_b200 import scenarios
+    return scenarios.load(WORKLOADS[workload][0] if workload in WORKLOADS else workload)
+
+
+def workload_config(args, desc, n_envs):
+    """the `config` object of the JSON line: identical in both arms (it names the workload, nothing device-specific)"""
+    d = WORKLOADS.get(args.workload)
+    name = d[2] if d else f"scenario {args.workload}: L={desc.L} G={desc.G} F={desc.F} C={desc.C}"
+    state_gb = n_envs * (desc.C * desc.L * desc.G * 8 * 2) / 1e9
+    return {"workload": name, "scenario": args.workload, "envs_per_gpu": n_envs, "days_per_step": PERIOD,
+            "precision": args.precision, "actions": "U(0,1)^A per env and gym step, seed 1234 + rank",
+            "l2": f"per-step working set {state_gb:.2f} GB of env state (> 126 MB L2 when > 0.13) and a 256 MiB flush "
+                  "write between timed GPU steps"}
 
 
 def algorithmic_bytes(desc, info, w, fused_days):
@@ -109,79 +120,151 @@ class ClockSampler:
                 "samples": len(rows)}
 
 
+def _sample_plan(one_env_step_s, budget_s, want_envs, want_steps):
+    """bounded CPU sample: (n_envs, n_steps, days) that costs about `budget_s` seconds on one thread"""
+    if one_env_step_s * want_envs * want_steps <= budget_s:
+        return want_envs, want_steps, PERIOD
+    if one_env_step_s <= budget_s:
+        n_steps = max(1, min(want_steps, int(budget_s / one_env_step_s / max(want_envs, 1))))
+        return max(1, min(want_envs, int(budget_s / one_env_step_s / n_steps))), n_steps, PERIOD
+    # a whole gym step of one env does not fit the budget (SYN: about a minute): time single simulated days and
+    # scale by the 7 days of a gym step
+    return 1, 1, max(1, min(PERIOD, int(budget_s / (one_env_step_s / PERIOD))))
+
+
 def cpu_port_rate(desc, n_envs, n_steps, seed=0, budget_s=12.0):
-    """The oracle (C restatement of the reference), one host thread: env-steps/s on a bounded sample
-    (at most n_envs x n_steps gym steps, cut down to about `budget_s` seconds of CPU work)."""
+    """The oracle (C restatement of the reference), one host thread: env-steps/s on a bounded sample."""
     from oracle.oracle import rollout
     rng = np.random.default_rng(seed)
     t0 = time.perf_counter()
-    rollout(desc, rng.uniform(0, 1, (1, 1, desc.A)).astype(np.float32), PERIOD, want_final=False)
-    one = time.perf_counter() - t0
-    if one * n_envs * n_steps > budget_s:
-        n_steps = max(1, min(n_steps, int(budget_s / one / max(n_envs, 1))))
-        n_envs = max(1, min(n_envs, int(budget_s / one / n_steps)))
+    rollout(desc, rng.uniform(0, 1, (1, 1, desc.A)).astype(np.float32), 1, want_final=False)
+    one = (time.perf_counter() - t0) * PERIOD
+    n_envs, n_steps, days = _sample_plan(one, budget_s, n_envs, n_steps)
     acts = rng.uniform(0, 1, (n_envs, n_steps, desc.A)).astype(np.float32)
     t0 = time.perf_counter()
-    rollout(desc, acts, PERIOD, want_final=False)
+    rollout(desc, acts, days, want_final=False)
     dt = time.perf_counter() - t0
-    return n_envs * n_steps / dt, dt, n_envs, n_steps
+    rate = n_envs * n_steps * (days / PERIOD) / dt
+    sample = f"{n_envs} envs x {n_steps} gym steps" + ("" if days == PERIOD else f" x {days} of 7 days (scaled by days/7)")
+    return rate, dt, sample
 
 
 def _ref_worker(args):
-    desc_path_or_name, n_envs, n_steps, seed = args
-    desc = load_desc(desc_path_or_name)
+    workload, n_envs, n_steps, days, seed = args
+    desc = load_desc(workload)
     from oracle.oracle import rollout
     acts = np.random.default_rng(seed).uniform(0, 1, (n_envs, n_steps, desc.A)).astype(np.float32)
-    rollout(desc, acts, PERIOD, want_final=False)
-    return n_envs * n_steps
+    rollout(desc, acts, days, want_final=False)
+    return n_envs * n_steps * days / PERIOD
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port; the Python reference cannot travel to
-    the GPU box) on every host core, same workload/metric; each step = a bounded sample of the batch."""
+    """--impl reference: the reference's CPU algorithm on every host core, same workload / metric / config. The
+    reference is Python + numba and cannot travel to the GPU box, so what runs is its C restatement
+    (oracle/, cpu_baseline.kind = "port", about 56x faster per core than the Python reference). Each step is a bounded
+    sample of the batch; `value` is normalised to env-steps/s. Loads no GPU library."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
     desc = load_desc(args.workload)
+    n_envs = args.envs or (WORKLOADS[args.workload][1] if args.workload in WORKLOADS else 4096)
     cores = len(os.sched_getaffinity(0))
-    per_core = args.ref_envs_per_core
-    # bounded sample: about 2 s of CPU work per core and step
     t0 = time.perf_counter()
-    _ref_worker((args.workload, 1, 1, 7))
-    one = time.perf_counter() - t0
-    per_core = max(1, min(per_core, int(2.0 / max(one, 1e-6))))
+    _ref_worker((args.workload, 1, 1, 1, 7))
+    one = (time.perf_counter() - t0) * PERIOD
+    per_core, _, days = _sample_plan(one, args.ref_seconds_per_step, args.ref_envs_per_core, 1)
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
-        job = [(args.workload, per_core, 1, 100 + i) for i in range(cores)]
-        for _ in range(max(args.warmup, 1)):
+        job = [(args.workload, per_core, 1, days, 100 + i) for i in range(cores)]
+        for _ in range(max(min(args.warmup, 2), 1)):
             pool.map(_ref_worker, job)
         t0 = time.perf_counter()
-        done = 0
+        done = 0.0
         for k in range(args.steps):
-            done += sum(pool.map(_ref_worker, [(args.workload, per_core, 1, 1000 + k * cores + i) for i in range(cores)]))
+            done += sum(pool.map(_ref_worker, [(args.workload, per_core, 1, days, 1000 + k * cores + i) for i in range(cores)]))
         dt = time.perf_counter() - t0
     v = done / dt
-    sample = f"{per_core * cores} envs x 1 gym step (7 days) per step, {args.steps} steps, {cores} processes"
+    sample = (f"{per_core * cores} of the {n_envs} envs per step ({per_core} per core), "
+              + ("1 gym step (7 days)" if days == PERIOD else f"{days} of the 7 days of a gym step (scaled by days/7)")
+              + f", {args.steps} steps, {cores} processes of oracle/epi_oracle.c")
     line = {"impl": "reference", "metric": "env-steps/s", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args, desc), "sim_days_per_s": v * PERIOD},
-            "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": workload_config(args, desc, n_envs), "sim_days_per_s": v * PERIOD,
+            "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample,
+                             "python_reference_survey": PY_REF},
             "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def workload_name(args, desc):
-    d = WORKLOADS.get(args.workload)
-    base = d[2] if d else f"synthetic COVID-like {args.workload}: L={desc.L} G={desc.G} F={desc.F} C={desc.C}"
-    return base
+# the unmodified Python reference, timed in the build container (SURVEY.md §6 / Appendix F; it cannot run on the GPU box)
+PY_REF = {"covid_c_env_steps_per_s_per_core": 8.5, "syn_seconds_per_env_step": 194.6,
+          "where": "SURVEY.md §6, Appendix F: build container, one core, after the 105 s numba JIT"}
+
+
+def timed_steps(eng, torch, dist, world, acts, K, W, gather, flush):
+    """W warm-up steps, then K steps timed with CUDA events on the launching stream (L2 flushed outside the event
+    pairs), barrier + synchronize on both sides, max over ranks. Returns (ms_per_step, launches, t_wall0, t_wall1)."""
+    def one_step(i):
+        obs, rew, done = eng.step(acts[i], PERIOD)
+        if gather is not None:
+            gather(obs, rew, done)
+            gather.release()
+
+    for i in range(W):
+        one_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    launches0 = eng.launches
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    resets = 0
+    for i in range(K):
+        flush.zero_()            # evict L2 between timed iterations (outside the event pair)
+        ev[i][0].record()
+        one_step(W + i)
+        ev[i][1].record()
+        if (W + i + 1) % 45 == 0:    # episodes are 53 steps long: restart before the horizon (untimed)
+            torch.cuda.synchronize()
+            eng.reset()
+            resets += 1
+    torch.cuda.synchronize()
+    t_wall1 = time.perf_counter()
+    if world > 1:
+        dist.barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    if world > 1:
+        t = torch.tensor([dev_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+    return dev_ms / K, eng.launches - launches0 - resets, t_wall0, t_wall1
+
+
+def verify_gather(eng, gather, torch, dist, world, rank):
+    """after the timed region: what the learner rank holds in its gather buffer against one NCCL exchange of every
+    rank's local results, bit for bit (obs | reward | done of the last step)"""
+    got = gather.last() if rank == 0 else None
+    ok = True
+    for r in range(world):
+        for idx, t in enumerate((eng.obs, eng.reward, eng.done)):
+            tmp = t.clone() if rank == r else torch.empty_like(t)
+            dist.broadcast(tmp, src=r)
+            if rank == 0:
+                ok = ok and bool(torch.equal(got[r][idx], tmp))
+            del tmp
+    return ok
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
+    import __graft_entry__ as g
+    g.build()
     from epipolicy_rl_b200.engine import BatchedEpidemic
 
     rank = int(os.environ.get("RANK", "0"))
@@ -196,8 +279,8 @@ def run_ours(args):
     info = eng.info
     w = 4 if args.precision == "fp32" else 8
     K, W = args.steps, max(args.warmup, 3)
-    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
-    acts_host = torch.rand((K + W, n_envs, desc.A), generator=g)
+    gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    acts_host = torch.rand((K + W, n_envs, desc.A), generator=gen)
     acts = acts_host.cuda()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     gather, gather_kind = None, "none"
@@ -207,49 +290,21 @@ def run_ours(args):
         from epipolicy_rl_b200.dist import make_gather
         gather, gather_kind = make_gather(eng, world, prefer_peer=args.gather == "peer")
 
-    def one_step(i):
-        obs, rew, done = eng.step(acts[i], PERIOD)
-        if gather is not None:
-            gather(obs, rew, done)
-
-    for i in range(W):
-        one_step(i)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.15)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    launches0 = eng.launches
-    torch.cuda.synchronize()
-    t_wall0 = time.perf_counter()
-    for i in range(K):
-        flush.zero_()            # evict L2 between timed iterations (outside the event pair)
-        ev[i][0].record()
-        one_step(W + i)
-        ev[i][1].record()
-        if (i + 1) % 30 == 0:    # episodes are 53 steps long: restart before the horizon (untimed)
-            torch.cuda.synchronize()
-            eng.reset()
-    torch.cuda.synchronize()
-    t_wall1 = time.perf_counter()
-    if world > 1:
-        dist.barrier()
+    ms_per_step, launches, t_wall0, t_wall1 = timed_steps(eng, torch, dist, world, acts, K, W, gather, flush)
     clocks = sampler.stop(t_wall0, t_wall1)
-    launches = eng.launches - launches0 - (K // 30)
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    if world > 1:
-        t = torch.tensor([dev_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms = float(t.item())
-    ms_per_step = dev_ms / K
     value = world * n_envs / (ms_per_step * 1e-3)
+    nfev = float(eng.get_state("trace")[:, 0].mean())
+    gather_ok = verify_gather(eng, gather, torch, dist, world, rank) if world > 1 else None
+    if gather is not None and hasattr(gather, "close"):
+        gather.close()
 
     # ---- end to end through the host-buffer C-ABI call (H2D actions, launch, D2H obs/reward/done)
     eng.reset()
     acts_np = acts_host.numpy()
-    for i in range(3):
+    for i in range(2):
         eng.step_host(acts_np[i], PERIOD)
     Ke = min(K, 30)
     t0 = time.perf_counter()
@@ -263,75 +318,101 @@ def run_ours(args):
     e2e = world * n_envs * Ke / e2e_dt
     rs = 4 if args.precision == "fp32" else 8
     h2d, d2h = n_envs * desc.A * 4, n_envs * (info.obs_dim * rs + 8 + 1)
+    kernel_name = {0: "warp-team", 1: "cta-team", 2: "cell", 3: "env", 4: "env-group"}.get(info.team_kind, "?") + \
+        ("+specialised" if info.specialized else "")
+    launch = {"kernel": kernel_name, "threads": info.threads, "grid": info.grid, "smem_bytes": info.smem_bytes,
+              "collective": gather_kind}
+    eng.close()
+    del eng
+
+    # ---- secondary workload (flat keys): COVID_C x 4096 envs, the shipped-scenario configuration (configs[2])
+    sec = {}
+    if rank == 0 and args.workload == "syn" and not args.no_secondary:
+        d2 = load_desc("covid_c")
+        e2 = BatchedEpidemic(d2, 4096, device=local, precision=args.precision)
+        a2 = torch.rand((43, 4096, d2.A), generator=gen).cuda()
+        ms2, _, _, _ = timed_steps(e2, torch, dist, 1, a2, 40, 3, None, flush)
+        b2, c2 = algorithmic_bytes(d2, e2.info, w, PERIOD)
+        sec = {"covid_c_env_steps_per_s": 4096 / (ms2 * 1e-3), "covid_c_ms_per_step": ms2, "covid_c_envs": 4096,
+               "covid_c_bytes_per_env_launch": b2, "covid_c_hbm_frac": 4096 * b2 / (ms2 * 1e-3) / 1e9 / hbm_peak()[0]}
+        e2.close()
 
     if rank == 0:
         base_b, ctrl_b = algorithmic_bytes(desc, info, w, PERIOD)
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        peak, peak_src = hbm_peak()
         achieved = n_envs * base_b / (ms_per_step * 1e-3) / 1e9
         # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload
-        traffic = None
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(f"{args.workload}:{args.precision}:{n_envs}", {}).get("dram_bytes_per_launch")
+            ent = json.load(open(tpath)).get(f"{args.workload}:{args.precision}:{n_envs}", {})
+            traffic, traffic_src = ent.get("dram_bytes_per_launch"), ent.get("source")
         # the second roofline (SURVEY.md §8d asks for both): algorithmic fp32 flops against the CUDA-core peak
         # 148 SMs x 128 lanes x 2 x SM clock; nfev of the last simulated day of this run, averaged over the envs
-        nfev = float(eng.get_state("trace")[:, 0].mean())
         flops = algorithmic_flops(desc, info, nfev, PERIOD)
         sm_ghz = (clocks.get("sm_max_mhz") or 1965.0) / 1e3
         fp32_peak = 148 * 128 * 2 * sm_ghz / 1e3  # TFLOP/s
         fp32_ach = n_envs * flops / (ms_per_step * 1e-3) / 1e12
-        cpu_v, cpu_dt, cpu_ne, cpu_ns = cpu_port_rate(desc, args.cpu_sample_envs, args.cpu_sample_steps)
+        cpu_v, cpu_dt, cpu_sample = cpu_port_rate(desc, args.cpu_sample_envs, args.cpu_sample_steps)
+        dram_frac = traffic / (ms_per_step * 1e-3) / 1e9 / peak if traffic else None
         line = {
             "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.precision == "fp32" else "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args, desc), "envs_per_gpu": n_envs, "days_per_step": PERIOD,
-                       "sim_days_per_s": value * PERIOD, "l2": "flushed between timed steps (256 MiB write)",
-                       "kernel": {0: "warp-team", 1: "cta-team", 2: "cell", 3: "env"}[info.team_kind] +
-                                 ("+specialised" if info.specialized else ""),
-                       "threads": info.threads, "grid": info.grid,
-                       "smem_bytes": info.smem_bytes, "collective": gather_kind},
+            "config": workload_config(args, desc, n_envs), "launch": launch, "sim_days_per_s": value * PERIOD,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "bytes_per_env_launch": base_b,
-                         "bytes_per_env_launch_with_rk45_accumulators": ctrl_b,
-                         "frac_with_rk45_accumulators": n_envs * ctrl_b / (ms_per_step * 1e-3) / 1e9 / peak,
-                         "fp32_cuda_core": {"achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s",
-                                            "frac": fp32_ach / fp32_peak, "flops_per_env_launch": flops,
-                                            "nfev_per_day": nfev}},
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "bytes_per_env_launch": base_b, "bytes_per_env_launch_with_rk45_accumulators": ctrl_b,
+                         "note": "algorithmic bytes = state in / state out once per 7-day launch (SURVEY.md §8d); the "
+                                 "kernel keeps X in f64 in both modes (the fp32 mode's float copy is a second column), "
+                                 "so it cannot reach this denominator on the X term; with ~92 right-hand-side evaluations "
+                                 "per gym step the path is CUDA-core / latency bound, see fp32_flop_frac and dram_frac"},
+            # flat copies (the driver's parser keeps top-level scalars)
+            "bytes_day": base_b, "bytes_day_ctrl": ctrl_b, "hbm_frac_algorithmic": achieved / peak,
+            "hbm_frac_ctrl": n_envs * ctrl_b / (ms_per_step * 1e-3) / 1e9 / peak,
+            "dram_bytes_per_env_step": (traffic / n_envs) if traffic else None, "dram_frac": dram_frac,
+            "fp32_flop_frac": fp32_ach / fp32_peak, "fp32_tflops": fp32_ach, "fp32_peak_tflops": fp32_peak,
+            "flops_per_env_launch": flops, "nfev_per_day": nfev,
             "cpu_baseline": {"value": cpu_v, "unit": "env-steps/s", "cores": 1, "kind": "port",
-                             "sample": f"{cpu_ne} envs x {cpu_ns} gym steps, {cpu_dt:.1f} s, "
-                                       "oracle/epi_oracle.c single thread"},
+                             "sample": f"{cpu_sample}, {cpu_dt:.1f} s, oracle/epi_oracle.c single thread",
+                             "python_reference_survey": PY_REF},
             "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        if gather_ok is not None:
+            line["gather_verified"] = bool(gather_ok)
+        line.update(sec)
         print(json.dumps(line), flush=True)
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="covid_c")
+    ap.add_argument("--workload", default="syn")
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N > 1: how results reach the learner rank")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the COVID_C x 4096 secondary measurement")
     ap.add_argument("--cpu-sample-envs", type=int, default=64)
     ap.add_argument("--cpu-sample-steps", type=int, default=53)
     ap.add_argument("--ref-envs-per-core", type=int, default=64)
+    ap.add_argument("--ref-seconds-per-step", type=float, default=3.0,
+                    help="--impl reference: CPU seconds per core and step the bounded sample aims at")
     args = ap.parse_args()
-    import __graft_entry__ as g
-    g.build()
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args)   # CPU only: builds and loads oracle/ alone
     else:
         run_ours(args)
 

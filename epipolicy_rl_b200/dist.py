@@ -62,9 +62,15 @@ class LearnerGather:
         return self.gathered()
 
     def gathered(self):
-        """[(obs, reward, done) of rank r for r in range(world)] as views of the receive buffer."""
+        """[(obs, reward, done) of rank r for r in range(world)] as views of the receive buffer; valid until the next
+        call (the next all-gather overwrites them, stream-ordered)."""
         n = self.layout.nbytes
         return [self.layout.views(self.recv[r * n:(r + 1) * n]) for r in range(self.world)]
+
+    last = gathered
+
+    def release(self):
+        """nothing to release: the next all-gather is stream-ordered behind the readers"""
 
 
 class PeerGather:
@@ -73,30 +79,59 @@ class PeerGather:
     engine's mirror output (engine.bind_mirror): the step kernel's epilogue stores each env's obs / reward / done
     into the learner's memory as the env finishes, overlapped with the envs still being stepped. What remains
     per gym step is one device-side barrier over the signal pads, so that the learner reads complete records.
-    Same record layout as LearnerGather; `gathered()` is valid on the learner rank."""
+    Same record layout as LearnerGather; `gathered()` is valid on the learner rank.
 
-    def __init__(self, eng, world: int, learner: int = 0, group=None):
+    Write-after-read protection (a peer's step k+1 kernel must not store into records the learner is still reading
+    from step k):
+      * double_buffer=True (default while both buffers stay under 1 GiB): two receive buffers used by step parity. The
+        views returned for step k stay valid until the call for step k+1 returns on this stream: a peer can only
+        start step k+2 (same buffer) after barrier k+1, which the learner's stream reaches after its stream-ordered
+        reads of step k.
+      * double_buffer=False (large records, e.g. the synthetic 1000-locale scenario at 3.9 GB per rank): one buffer
+        and a second barrier, `release()`, which every rank calls after the learner's reads are enqueued and before
+        the next step is launched. Its cost is part of every benchmark that uses this mode."""
+
+    def __init__(self, eng, world: int, learner: int = 0, group=None, double_buffer: bool | None = None):
         import torch.distributed._symmetric_memory as symm
         self.layout = PackedLayout(eng.n_envs, eng.obs_dim, eng.dtype)
         self.world, self.learner, self.rank = world, learner, dist.get_rank(group)
         n = self.layout.nbytes
-        self.recv = symm.empty(world * n, dtype=torch.uint8, device=eng.device)
+        if double_buffer is None:
+            double_buffer = 2 * world * n <= (1 << 30)
+        self.nbuf = 2 if double_buffer else 1
+        self.recv = symm.empty(self.nbuf * world * n, dtype=torch.uint8, device=eng.device)
         self.recv.zero_()
         self.hdl = symm.rendezvous(self.recv, group if group is not None else dist.group.WORLD)
-        peer = self.hdl.get_buffer(learner, (world * n,), torch.uint8)  # the learner's buffer, mapped here
-        self.mine = self.layout.views(peer[self.rank * n:(self.rank + 1) * n])
-        eng.bind_mirror(*self.mine)
+        peer = self.hdl.get_buffer(learner, (self.nbuf * world * n,), torch.uint8)  # the learner's buffers, mapped here
+        self.mine = [self.layout.views(peer[(b * world + self.rank) * n:(b * world + self.rank + 1) * n])
+                     for b in range(self.nbuf)]
+        self.cur = 0      # buffer the NEXT step writes
+        self.prev = 0     # buffer of the last completed gather
+        eng.bind_mirror(*self.mine[0])
         self.eng = eng
 
     def __call__(self, obs=None, rew=None, done=None):
         # the kernel has already stored this rank's records into the learner's buffer: order the reader behind every
         # rank's step kernel (stream-ordered barrier on the signal pads)
         self.hdl.barrier(channel=0)
+        self.prev = self.cur
+        if self.nbuf == 2:
+            self.cur ^= 1
+            self.eng.bind_mirror(*self.mine[self.cur])   # pointers only; the next launch picks them up
         return self.gathered() if self.rank == self.learner else None
 
+    def release(self):
+        """single-buffer mode: the learner's reads of the last gather are enqueued; peers may overwrite after this"""
+        if self.nbuf == 1:
+            self.hdl.barrier(channel=1)
+
     def gathered(self):
-        n = self.layout.nbytes
-        return [self.layout.views(self.recv[r * n:(r + 1) * n]) for r in range(self.world)]
+        """[(obs, reward, done) of rank r] of the last completed gather, views of the learner's receive buffer (see the
+        class docstring for how long they stay valid)"""
+        n, b = self.layout.nbytes, self.prev
+        return [self.layout.views(self.recv[(b * self.world + r) * n:(b * self.world + r + 1) * n]) for r in range(self.world)]
+
+    last = gathered
 
     def close(self):
         self.eng.bind_mirror(None, None, None)

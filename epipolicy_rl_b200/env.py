@@ -88,8 +88,13 @@ class EpiEnv(_EnvBase):
         self.observation_space = self._b.observation_space
 
     def step(self, action):
-        a = np.asarray(action, np.float32).reshape(1, -1)
-        obs, rew, done = self.epi.step_host(a, PERIOD)
+        # the reference consumes the first n_free entries of the action and ignores the rest
+        # (epipolicy_environment.py:40-47): action_space counts non-cost interventions, which can exceed the number of
+        # free control parameters (warmup_scenario: 2 vs 0)
+        a = np.asarray(action, np.float32).reshape(-1)
+        if a.shape[0] < self.epi.action_dim:
+            raise ValueError(f"action has {a.shape[0]} entries, the scenario has {self.epi.action_dim} free control parameters")
+        obs, rew, done = self.epi.step_host(a[:self.epi.action_dim].reshape(1, -1), PERIOD)
         return obs[0].astype(np.float64), float(rew[0]), bool(done[0]), dict()
 
     def reset(self):

@@ -1,7 +1,7 @@
 """Synthetic COVID-like scenarios in the reference's own JSON session schema (SURVEY.md Appendix F,
 BASELINE.json configs[3]): L leaf locales x G groups x F facilities on top of COVID_C's model,
 interventions, costs, schedules and optimize ranges. The session is consumed by the reference's unmodified
-`construct_epidemic` (tools/gen_syn.py exports the resulting Static to tests/golden/desc_syn_*.npz), so the
+`construct_epidemic` (tools/gen_syn.py exports the resulting Static to epipolicy_rl_b200/scenarios/desc_syn_*.npz), so the
 GPU path and the oracle see exactly what the reference's parser / make_static produce for it."""
 from __future__ import annotations
 
@@ -12,7 +12,6 @@ import numpy as np
 
 SIZES = {"syn_s": (20, 4, 8), "syn_m": (100, 8, 8), "syn": (1000, 16, 8)}
 _HERE = os.path.dirname(os.path.abspath(__file__))
-GOLDEN = os.path.join(os.path.dirname(_HERE), "tests", "golden")
 
 
 def make_session(covid_c_session: dict, L: int, G: int, F: int, seed: int = 20260101) -> dict:
@@ -56,8 +55,5 @@ def make_session(covid_c_session: dict, L: int, G: int, F: int, seed: int = 2026
 
 def workload_desc(name: str):
     """EpiDesc of a synthetic workload: the fixture exported from the reference's Static (tools/gen_syn.py)."""
-    from .desc import EpiDesc
-    path = os.path.join(GOLDEN, f"desc_{name}.npz")
-    if not os.path.exists(path):
-        raise FileNotFoundError(f"{path} missing: generate it with tools/gen_syn.py (needs the reference importable)")
-    return EpiDesc.load(path)
+    from . import scenarios
+    return scenarios.load(name)

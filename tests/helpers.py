@@ -8,7 +8,8 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def load(name):
-    return EpiDesc.load(os.path.join(GOLDEN, f"desc_{name}.npz")), np.load(os.path.join(GOLDEN, f"traj_{name}.npz"))
+    from epipolicy_rl_b200 import scenarios
+    return scenarios.load(name), np.load(os.path.join(GOLDEN, f"traj_{name}.npz"))
 
 
 def x_err(x, ref, desc):

@@ -13,7 +13,7 @@ from helpers import load
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, n, out):
+def _worker(rank, world, port, n, out, dbuf):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
@@ -21,9 +21,10 @@ def _worker(rank, world, port, n, out):
     from epipolicy_rl_b200.engine import BatchedEpidemic
     d, _ = load("COVID_C")
     eng = BatchedEpidemic(d, n, device=rank, precision="fp32")
-    g = PeerGather(eng, world)
+    g = PeerGather(eng, world, double_buffer=dbuf)
     gen = torch.Generator().manual_seed(100 + rank)
-    for step in range(3):
+    pending = None
+    for step in range(5):
         a = torch.rand((n, d.A), generator=gen).cuda()
         obs, rew, done = eng.step(a, 7)
         got = g()
@@ -33,11 +34,17 @@ def _worker(rank, world, port, n, out):
         dist.all_gather(all_obs, obs.contiguous())
         dist.all_gather(all_rew, rew.contiguous())
         if rank == 0:
+            if dbuf and pending is not None:
+                # the views of step k-1 are still intact after step k has been launched and gathered (other buffer)
+                for r in range(world):
+                    assert torch.equal(pending[0][r][0], pending[1][r]), ("stale", step, r)
             for r in range(world):
                 assert torch.equal(got[r][0], all_obs[r]), (step, r)
                 assert torch.equal(got[r][1], all_rew[r]), (step, r)
                 assert not got[r][2].any()
-        g.hdl.barrier(channel=1)  # nobody overwrites the learner's buffer before it has been checked
+            pending = (got, all_obs)
+        g.release()  # single-buffer mode: nobody overwrites the learner's buffer before it has been read (the
+        # comparisons above are stream-ordered reads); double-buffer mode needs no second barrier
     if rank == 0:
         open(os.path.join(out, "ok"), "w").write("1")
     eng.close()
@@ -45,7 +52,8 @@ def _worker(rank, world, port, n, out):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_peer_gather_two_gpus(tmp_path):
-    port = 29700 + os.getpid() % 200
-    mp.spawn(_worker, args=(2, port, 100, str(tmp_path)), nprocs=2, join=True)
+@pytest.mark.parametrize("dbuf", [True, False])
+def test_peer_gather_two_gpus(tmp_path, dbuf):
+    port = 29700 + os.getpid() % 200 + (0 if dbuf else 200)
+    mp.spawn(_worker, args=(2, port, 100, str(tmp_path), dbuf), nprocs=2, join=True)
     assert (tmp_path / "ok").exists()

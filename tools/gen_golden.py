@@ -16,6 +16,7 @@ import numpy as np
 
 REF = os.environ.get("EPI_REFERENCE", "/root/reference")
 OUT = os.path.join(os.path.dirname(__file__), "..", "tests", "golden")
+SCN = os.path.join(os.path.dirname(__file__), "..", "epipolicy_rl_b200", "scenarios")  # product data: the descriptors
 
 import epipolicy.core.epidemic as ref_epidemic  # noqa: E402
 from epipolicy.obj.act import construct_act  # noqa: E402
@@ -131,7 +132,7 @@ def main(names):
         epi = env.epi
         d = export_static(epi)
         d.meta["scenario"] = name
-        d.save(os.path.join(OUT, f"desc_{name}.npz"))
+        d.save(os.path.join(SCN, f"desc_{name}.npz"))
         out = {f"init_{k[5:]}": v for k, v in export_initial_parameter(epi).items()}
         A = env.action_space.shape[0]
         n_steps = (d.horizon + 6) // 7

@@ -15,6 +15,7 @@ import numpy as np
 
 REF = os.environ.get("EPI_REFERENCE", "/root/reference")
 OUT = os.path.join(os.path.dirname(__file__), "..", "tests", "golden")
+SCN = os.path.join(os.path.dirname(__file__), "..", "epipolicy_rl_b200", "scenarios")  # product data: the descriptors
 
 from epipolicy.core.epidemic import construct_epidemic  # noqa: E402
 from epipolicy_rl_b200.desc import EpiDesc  # noqa: E402
@@ -37,7 +38,7 @@ def main(names, T=28):
                             comp_news=np.asarray(rep.comp_news),
                             incidence_edges=np.array(meta["incidence_edges"], np.int32).reshape(-1, 2),
                             inf_comps=np.array(meta["inf_comps"]), T=T)
-        dpath = os.path.join(OUT, f"desc_{name}.npz")
+        dpath = os.path.join(SCN, f"desc_{name}.npz")
         d = EpiDesc.load(dpath)
         d.meta["reporter"] = meta
         d.save(dpath)

@@ -13,6 +13,7 @@ import numpy as np
 
 REF = os.environ.get("EPI_REFERENCE", "/root/reference")
 OUT = os.path.join(os.path.dirname(__file__), "..", "tests", "golden")
+SCN = os.path.join(os.path.dirname(__file__), "..", "epipolicy_rl_b200", "scenarios")  # product data: the descriptors
 
 import epipolicy.core.epidemic as ref_epidemic  # noqa: E402
 from epipolicy_environment import EpiEnv  # noqa: E402
@@ -43,7 +44,7 @@ def main(names):
         env = EpiEnv(session)
         d = export_static(env.epi)
         d.meta["scenario"] = name
-        d.save(os.path.join(OUT, f"desc_{name}.npz"))
+        d.save(os.path.join(SCN, f"desc_{name}.npz"))
         print(f"{name}: constructed + exported in {time.time() - t0:.1f}s (L={d.L} G={d.G} F={d.F} nnz={d.nnz})", flush=True)
         A = env.action_space.shape[0]
         acts = np.random.default_rng(5).uniform(0.05, 0.6, (N_STEPS[name], A)).astype(np.float32)

@@ -43,7 +43,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    desc = EpiDesc.load(os.path.join(ROOT, "tests", "golden", f"desc_{args.scenario}.npz"))
+    from epipolicy_rl_b200 import scenarios
+    desc = scenarios.load(args.scenario)
     env = BatchedEpiEnv(desc, args.envs, device=local, precision=args.precision)
     pop = np.broadcast_to(desc.pop.reshape(1, desc.L, desc.G), (desc.C, desc.L, desc.G)).reshape(-1)
     dev = torch.device(f"cuda:{local}")
