@@ -63,6 +63,11 @@ struct epi_engine {
   // scenario-specialised build of the cell kernel (epi_spec_attach)
   void* spec_lib = nullptr;
   int (*spec_launch)(const DevPlan*, const DevState*, const epi::StepArgs*, int, int, size_t, void*) = nullptr;
+  // env-group kernel of the specialised build (epi_grp.cuh): cooperative launch of n_groups x S CTAs
+  int (*spec_launch_grp)(const DevPlan*, const DevState*, const epi::StepArgs*, int, int, size_t, void*) = nullptr;
+  char *grp_scratch = nullptr, *grp_cta_scratch = nullptr;
+  unsigned* grp_bar = nullptr;
+  int sms = 148;
   EpiDesc d{};                      // scalars only are valid after create
   DevPlan plan{};
   DevState S{}, init{};
@@ -700,6 +705,74 @@ void build_env_layout(epi_engine* h, int threads, int64_t smem_max) {
   Y.big_in_smem = Y.comm_in_smem && used + Y.big_bytes <= smem_max;
 }
 
+// layout of the env-group kernel (epi_grp.cuh): the fewest CTAs per env whose cells fit one per thread with the
+// stage derivatives in shared memory; then as many groups as the device has room for (all CTAs must be co-resident)
+void build_grp_layout(epi_engine* h, int sms, int64_t smem_max) {
+  DevPlan& P = h->plan;
+  GrpLayout& Y = P.gl;
+  Y = GrpLayout{};
+  const char* ev = getenv("EPI_GRP");  // "0": never; "2": also when the env fits one CTA's shared memory (tests)
+  const int mode = ev ? atoi(ev) : 1;
+  if (mode == 0 || h->precision != EPI_FP32 || P.LG <= 32 || P.G > 32 || P.F > 32) return;
+  if (P.el.big_in_smem && mode < 2) return;
+  const int64_t rs = 4, C = P.C, G = P.G, F = P.F, n_lc = P.n_lc, NG = P.NG;
+  const int64_t nS = P.has_src64 ? P.n_slot : 0;
+  const int forceS = getenv("EPI_GRP_S") ? atoi(getenv("EPI_GRP_S")) : 0;
+  // shared-memory layout of a CTA for groups of S CTAs; false if it does not fit
+  auto layout = [&](int S) {
+    const int lpc = (P.L + S - 1) / S;
+    const int threads = (int)(((int64_t)lpc * G + 31) / 32 * 32);
+    if (threads > 512) return false;
+    int64_t o = 0;
+    auto take = [&](int64_t bytes) { int64_t r = o; o = align16(o + bytes); return r; };
+    Y.trow = (int)(F * G + 4);
+    Y.np = P.n_sel + P.n_mv_op > 2 ? P.n_sel + P.n_mv_op : 2;
+    Y.s_K = take(rs * 6 * C * threads); Y.s_KS = take(8 * 6 * nS * threads); Y.s_cmB = take(rs * (1 + NG) * threads);
+    Y.s_red = take(8 * (32 + (int64_t)(2 * S > P.n_mv_op ? 2 * S : P.n_mv_op)));
+    Y.s_tab = o;
+    o = 0;
+    Y.e_mult_y = take(4 * (int64_t)P.n_cls); Y.e_mult_d = take(4 * (int64_t)P.n_cls);
+    Y.e_cpv = take(4 * (int64_t)P.NCP); Y.e_act = take(P.I);
+    Y.e_expr = take(8 * (int64_t)P.n_expr); Y.e_sel = take(8 * (int64_t)P.n_sel);
+    Y.e_mpy = take(4 * n_lc * P.P * G); Y.e_mpg = take(4 * n_lc * P.P * G); Y.e_mpt0 = take(4 * n_lc * P.P * G);
+    Y.e_mpFy = take(4 * (int64_t)P.n_igp * n_lc * F * G); Y.e_mpFg = take(4 * (int64_t)P.n_igp * n_lc * F * G);
+    Y.e_coefS = take(rs * NG * n_lc * F * G);
+    Y.e_Tnum = take(4 * n_lc * G * Y.trow); Y.e_Tden = take(rs * n_lc * G * Y.trow);
+    Y.e_ft_y = take(4 * n_lc * F * G); Y.e_ft_gap = take(4 * n_lc * F * G);
+    Y.tab_bytes = o;
+    Y.smem_bytes = Y.s_tab + Y.tab_bytes;
+    Y.lpc = lpc; Y.threads = threads; Y.S = S;
+    return Y.smem_bytes <= smem_max;
+  };
+  int S = 0;
+  if (forceS > 0) {
+    if (forceS <= P.L && layout(forceS)) S = forceS;
+  } else {
+    for (int s_ = 1; s_ <= sms && s_ <= P.L; s_++)
+      if (layout(s_)) { S = s_; break; }
+    if (S > 0) {
+      // as many groups as fit at this size, then all the SMs' worth of CTAs per group (fewer cells per CTA)
+      const int ng = sms / S;
+      int S2 = sms / ng;
+      if (S2 > P.L) S2 = P.L;
+      if (!layout(S2)) layout(S);
+    }
+  }
+  if (S == 0) { Y = GrpLayout{}; return; }
+  Y.n_groups = sms / Y.S;
+  const int64_t LG = P.LG;
+  int64_t o = 0;
+  auto take = [&](int64_t bytes) { int64_t r = o; o = (o + bytes + 255) & ~int64_t(255); return r; };
+  Y.g_XF = take(rs * C * LG); Y.g_cmA = take(rs * (1 + NG) * LG); Y.g_cmS = take(rs * (NG > 0 ? NG : 1) * LG);
+  Y.g_fl6 = take(rs * P.NSRC * LG); Y.g_accN = take(rs * (int64_t)P.n_acc * LG); Y.g_mvD = take(4 * (int64_t)P.n_slot * LG);
+  Y.g_crD = take(8 * (int64_t)P.I * P.L); Y.g_part = take(8 * 2 * (int64_t)Y.S * Y.np);
+  Y.g_bytes = o;
+  o = 0;
+  Y.c_fi_y = take(4 * n_lc * F * G * G); Y.c_fi_gap = take(4 * n_lc * F * G * G);
+  Y.c_bytes = o;
+  Y.enabled = 1;
+}
+
 // ------------------------------------------------------------------------------------------
 // scenario-specialised code generator: the per-cell program of the cell kernel as straight-line CUDA
 // (same operations in the same order as the interpreted path of epi_cell.cuh)
@@ -965,6 +1038,38 @@ std::string gen_spec(const epi_engine* h) {
     }
     rcp_of = nullptr;
     o << "}\n";
+    // ---- the same program for the env-group kernel (epi_grp.cuh): the flow sums FB += bw f, FE += ew f live in
+    // registers; `st`: the flows are also stored (last stage of an attempt)
+    o << "constexpr int grp_threads = " << P.gl.threads << ", grp_S = " << P.gl.S << ", grp_groups = " << P.gl.n_groups << ";\n";
+    o << "__device__ __forceinline__ void flows_acc(const real* y, real alive, const float* mp, const real* rs, real* d, real* FB, real* FE, real bw, real ew, real* out, size_t stride, bool st) {\n";
+    for (int c = 0; c < P.C; c++) o << "  d[" << c << "] = 0;\n";
+    if (h->precision == EPI_FP32) {
+      for (auto& dc : rdecl) o << "  real " << dc.first << "; { real dn = 0;" << dc.second << " " << dc.first << " = frcp(dn); }\n";
+      rcp_of = &rmap;
+    }
+    auto sums = [&](int src) {
+      o << " FB[" << src << "] += bw * f; FE[" << src << "] += ew * f; if (st) out[" << src << " * stride] = f;";
+    };
+    for (int k = 0; k < P.NG; k++) {
+      o << "  { real f = y[" << T.ig_c0[k] << "] * rs[" << k << "];";
+      sums(P.E + k);
+      scatter(P.E + k);
+      o << " }\n";
+    }
+    for (int e = 0; e < P.E; e++) {
+      const int* ep = T.ep.data() + T.ep_off[e];
+      int n = *ep++;
+      o << "  { real f; { real n = (real)1";
+      for (int q = 0; q < n; q++) o << " * " << val(*ep++);
+      o << ";";
+      emit_denominator(o, ep, val, "f");
+      o << "   ";
+      sums(e);
+      scatter(e);
+      o << " }\n";
+    }
+    rcp_of = nullptr;
+    o << "}\n";
     arr("ag_off", T.ag_off); arr("ag_src", T.ag_src);
     o << "__device__ constexpr float ag_coef[" << (T.ag_coef.empty() ? 1 : T.ag_coef.size()) << "] = {";
     if (T.ag_coef.empty()) o << "0";
@@ -1085,7 +1190,7 @@ std::string gen_spec(const epi_engine* h) {
   uint64_t k = 1469598103934665603ull;
   auto mix = [&](const void* p, size_t n) { for (size_t i = 0; i < n; i++) { k ^= ((const unsigned char*)p)[i]; k *= 1099511628211ull; } };
   mix(body.data(), body.size());
-  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 23 /* generator revision */};
+  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 24 /* generator revision */};
   mix(abi, sizeof abi);
   char kb[32];
   snprintf(kb, sizeof kb, "%016llx", (unsigned long long)k);
@@ -1093,7 +1198,8 @@ std::string gen_spec(const epi_engine* h) {
          kb + "\"\n#define EPI_SPEC_BIG " + (P.LG > 32 ? "1" : "0") + "\n" +
          "#define EPI_SPEC_PROLOGUE " + (spec_prologue ? "1" : "0") + "\n" +
          "#define EPI_SPEC_ROLES " + std::to_string(P.cl.roles > 0 ? P.cl.roles : 1) + "\n" +
-         (P.LG > 32 ? std::string("#define EPI_ENV_MINB ") + (P.el.big_in_smem ? "2" : "4") + "\n" : std::string()) + body;
+         (P.LG > 32 ? std::string("#define EPI_ENV_MINB ") + (P.el.big_in_smem ? "2" : "4") + "\n" : std::string()) +
+         (P.LG > 32 ? std::string("#define EPI_GRP_THREADS ") + std::to_string(P.gl.enabled ? P.gl.threads : 0) + "\n" : std::string()) + body;
 }
 
 void alloc_state(epi_engine* h, DevState& S, int N) {
@@ -1166,6 +1272,18 @@ void choose_launch(epi_engine* h) {
     if (!P.el.big_in_smem) h->big_scratch = h->dalloc<char>((size_t)P.el.big_bytes * h->grid, false);
     if (!P.el.comm_in_smem) h->small_scratch = h->dalloc<char>((size_t)P.el.comm_bytes * h->grid, false);
     h->cr_scratch = h->dalloc<double>((size_t)P.I * P.L * h->grid);
+    // the env-group kernel of the specialised build (used once such a build is attached, epi_spec_attach)
+    h->sms = sms;
+    build_grp_layout(h, sms, smem_max);
+#ifndef EPI_HOST_EMU
+    if (P.gl.enabled && !prop.cooperativeLaunch) P.gl.enabled = 0;
+#endif
+    if (P.gl.enabled) {
+      const int ng = P.gl.n_groups < h->N ? P.gl.n_groups : h->N;
+      h->grp_scratch = h->dalloc<char>((size_t)P.gl.g_bytes * ng, false);
+      h->grp_cta_scratch = h->dalloc<char>((size_t)P.gl.c_bytes * ng * P.gl.S, false);
+      h->grp_bar = h->dalloc<unsigned>((size_t)32 * ng);
+    }
     return;
   }
   if (force && !strcmp(force, "cta")) per_env = INT64_MAX / 16;
@@ -1281,8 +1399,23 @@ void launch_env(epi_engine* h, const DevState& S, const epi::StepArgs& a, cudaSt
   h->launches++;
 }
 
+// env-group kernel: n_groups x S co-resident CTAs (cooperative launch), arrive counters cleared in stream order
+void launch_grp(epi_engine* h, const DevState& S, epi::StepArgs a, cudaStream_t st) {
+  const GrpLayout& Y = h->plan.gl;
+  const int ng = Y.n_groups < a.N ? Y.n_groups : a.N;
+  a.grp_scratch = h->grp_scratch; a.grp_cta_scratch = h->grp_cta_scratch; a.grp_bar = h->grp_bar;
+  CK(cudaMemsetAsync(h->grp_bar, 0, sizeof(unsigned) * 32 * (size_t)ng, st));
+  int rc = h->spec_launch_grp(&h->plan, &S, &a, ng * Y.S, Y.threads, (size_t)Y.smem_bytes, (void*)st);
+  if (rc != 0) throw CudaFail{std::string("env-group kernel launch: ") + cudaGetErrorString((cudaError_t)rc)};
+  h->launches++;
+}
+
 void launch(epi_engine* h, const DevState& S, epi::StepArgs a, cudaStream_t st) {
   a.dbg_attempts = (a.N == h->N) ? h->dbg_attempts : nullptr;
+  if (h->cta_mode == 4) {
+    launch_grp(h, S, a, st);
+    return;
+  }
   if (h->cta_mode == 3) {
     a.big_scratch = h->big_scratch;
     a.small_scratch = h->small_scratch;
@@ -1436,9 +1569,11 @@ int epi_info(const epi_t* h, EpiInfo* o) {
   memset(o, 0, sizeof(*o));
   o->n_envs = h->N; o->precision = h->precision; o->device = h->device; o->obs_dim = P.CLG; o->action_dim = P.A;
   o->ncp = P.NCP; o->n_itv = P.I; o->horizon = P.horizon; o->n_flat = P.n_flat; o->n_acc = P.n_acc; o->n_slot = P.n_slot;
-  o->n_lc = P.n_lc; o->n_groups_inf = P.NG; o->n_cls = P.n_cls; o->team_kind = h->cta_mode; o->threads = h->threads;
-  o->grid = h->grid; o->envs_per_cta = h->cta_mode == 2 ? h->plan.cl.epw : (h->cta_mode ? 1 : h->wpb); o->smem_bytes = (int64_t)h->smem_bytes;
-  o->specialized = h->spec_launch ? 1 : 0; o->reserved = 0;
+  o->n_lc = P.n_lc; o->n_groups_inf = P.NG; o->n_cls = P.n_cls; o->team_kind = h->cta_mode;
+  o->threads = h->cta_mode == 4 ? P.gl.threads : h->threads;
+  o->grid = h->cta_mode == 4 ? (P.gl.n_groups < h->N ? P.gl.n_groups : h->N) * P.gl.S : h->grid; o->envs_per_cta = h->cta_mode == 2 ? h->plan.cl.epw : (h->cta_mode ? 1 : h->wpb);
+  o->smem_bytes = h->cta_mode == 4 ? P.gl.smem_bytes : (int64_t)h->smem_bytes;
+  o->specialized = h->spec_launch ? 1 : 0; o->reserved = h->cta_mode == 4 ? P.gl.S : 0;  // CTAs per env group
   o->small_bytes = P.small_bytes; o->big_bytes = P.big_bytes; o->scratch_bytes = (int64_t)h->scratch_bytes;
   int64_t rs = (int64_t)h->real_size();
   o->state_bytes_per_env = 8 * (P.CLG + (int64_t)P.n_chg * P.LG) + rs * (int64_t)P.n_acc * P.LG + 16 * (int64_t)P.I * P.L +
@@ -1657,7 +1792,10 @@ int epi_spec_source_desc(const EpiDesc* desc, int precision, char* buf, size_t c
     h->d = *desc;
     build_plan(h, *desc);
     if (h->plan.LG <= 32) build_cell_layout(h, 32);
-    else build_env_layout(h, env_threads(h->plan.LG), 232448 - 1024);  // B200: 227 KB opt-in shared memory per CTA
+    else {
+      build_env_layout(h, env_threads(h->plan.LG), 232448 - 1024);  // B200: 227 KB opt-in shared memory per CTA
+      build_grp_layout(h, 148, 232448 - 1024);                      // B200: 148 SMs
+    }
     std::string src = gen_spec(h);
     if (need) *need = src.size() + 1;
     if (buf && cap) {
@@ -1677,7 +1815,7 @@ int epi_spec_attach(epi_t* h, const char* so_path) {
     if (h->cta_mode < 2) throw Unsupported{"scenario specialisation exists for the cell and env kernels only"};
     // the generated build is the cell kernel for L*G <= 32 and the env kernel above: a kernel kind forced with EPI_TEAM
     // (debugging aid) on the other side of that line has no specialised build and runs interpreted
-    if ((h->cta_mode == 3) != (h->plan.LG > 32)) throw Unsupported{"no specialised build for the forced kernel kind"};
+    if ((h->cta_mode >= 3) != (h->plan.LG > 32)) throw Unsupported{"no specialised build for the forced kernel kind"};
     void* lib = dlopen(so_path, RTLD_NOW | RTLD_LOCAL);
     if (!lib) throw Invalid{std::string("dlopen failed: ") + dlerror()};
     auto keyf = (const char* (*)())dlsym(lib, "epi_spec_key");
@@ -1691,6 +1829,12 @@ int epi_spec_attach(epi_t* h, const char* so_path) {
     }
     h->spec_lib = lib;
     h->spec_launch = lf;
+    // the env-group kernel, when this build carries one and the layout is on for this engine
+    auto lg = (int (*)(const DevPlan*, const DevState*, const epi::StepArgs*, int, int, size_t, void*))dlsym(lib, "epi_spec_launch_grp");
+    if (lg && h->plan.gl.enabled && h->cta_mode == 3) {
+      h->spec_launch_grp = lg;
+      h->cta_mode = 4;
+    }
   });
 }
 

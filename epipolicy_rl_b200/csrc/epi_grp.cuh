@@ -1,0 +1,979 @@
+// epi_grp.cuh — the "env-group" kernel (sm_100a): ONE environment is stepped by a GROUP of S co-resident CTAs with
+// one (locale, group) cell per thread, so that the RK45 working set of a 1000-locale scenario never leaves the chip.
+// Scenario-specialised builds only (EPI_SPEC, fp32 throughput mode); the env kernel (epi_env.cuh) remains the
+// interpreted / fp64 path and the A/B baseline. BASELINE.json configs[3]: L=1000 x G=16 x F=8 -> 4 groups of 37 CTAs.
+//
+// Where the working set lives (per cell; the env kernel streamed all of it through HBM, 1.9 GB per env-step):
+//   * 6 stage-derivative slots K (stage 6 reuses the slot of stage 1, whose B = E = 0; accepted steps swap the slots
+//     of stages 0 and 1 instead of copying K_6 -> K_0) and the double-precision move-source derivatives: SHARED MEMORY,
+//     [word][thread] columns (conflict-free);
+//   * stage input y, the packed flow sums FB = sum_s B_s f_s and FE = sum_s E_s f_s (the scipy error norm's cumulative
+//     components are linear in the stage flows), the cell's alive count: REGISTERS, live across the whole attempt;
+//   * what crosses cells — alive / weighted-infectious columns for the CSC gather, the mixed force-of-infection terms
+//     for the CSR gather — goes through an L2-resident group scratch (12 + 8 B per cell and evaluation); the mixing
+//     itself only needs the locale's own groups: shared memory;
+//   * touched once per RK45 attempt: the float copy of the state, the double state X, the accumulators (global, L2).
+// One right-hand-side evaluation = pass 1 (stage input, alive, weighted sums) | GROUP BARRIER | pass 2 (CSC gather) |
+// CTA barrier | pass 3 (G x G facility mixing, 128-bit shared-memory table reads) | GROUP BARRIER | pass 4 (CSR gather,
+// edges, dX, flow sums), and pass 1 of the next stage follows without a barrier. The group barrier is an arrive counter
+// in L2 (release fence + atomic, acquire spin by one thread per CTA); the kernel is launched cooperatively so that all
+// CTAs of a group are resident. The controller state (t, h, accept / reject) is uniform over the group: every CTA
+// reduces the per-CTA partials of a norm in the same fixed order and so takes the same decision, without a broadcast.
+// Arithmetic, rounding points and the RK45 state machine are those of epi_env.cuh (flow-sum form).
+#pragma once
+#include "epi_kernels.cuh"
+#include "epi_rk.cuh"
+
+#ifdef EPI_SPEC
+namespace epi {
+namespace grp {
+using namespace rk;
+typedef spec::real real;
+
+#ifndef EPI_FSAL_DAYS
+#define EPI_FSAL_DAYS 1
+#endif
+
+struct Gx {
+  int tid, T;        // thread, threads per CTA (= width of a shared-memory column)
+  int cta, S;        // CTA inside the group, CTAs per group
+  int l0, nl;        // first locale / number of locales of this CTA
+  int j, u, lc, cell;  // this thread's locale, group, locale class, cell index j*G+u
+  bool valid;        // the thread carries a cell
+  char *smem, *tab;  // shared memory; per-env tables inside it
+  char *gs, *cs;     // the group's / this CTA's global scratch
+  unsigned* bar;     // the group's arrive counter
+  unsigned epoch;    // arrivals expected at the next barrier
+  int parity;        // reduction-partials buffer in use
+  int s0, s1;        // K slots of stage 0 and of stages 1 / 6
+  // current env
+  double *gX, *cost, *crY, *crD;
+  real *acc, *accn;  // accumulator column and candidate column (swap roles on an accepted step)
+  float *mvY, *mvD;
+};
+
+#define GL (P.gl)
+// threads per CTA and CTAs per group are compile-time constants of the specialised build (immediate shared-memory offsets)
+#define GTH (spec::grp_threads)
+#define GSS (spec::grp_S)
+#define GT(arr, i) (((T_##arr*)(b.tab + GL.e_##arr))[i])
+#define SK(slot, k) (((real*)(b.smem + GL.s_K))[((slot) * spec::C + (k)) * GTH + b.tid])
+#define SKS(slot, q) (((double*)(b.smem + GL.s_KS))[((slot) * spec::n_slot + (q)) * GTH + b.tid])
+#define SCMB(k, t) (((real*)(b.smem + GL.s_cmB))[(k) * GTH + (t)])
+#define GCOL(off, T_, i) (((T_*)(b.gs + (off)))[(size_t)(i) * spec::LG + b.cell])
+#define GXF(k) GCOL(GL.g_XF, real, k)
+
+#ifdef EPI_HOST_EMU
+__device__ __forceinline__ real ldcg(const real* p) { return *p; }
+__device__ __forceinline__ double ldcg(const double* p) { return *p; }
+#else
+__device__ __forceinline__ float ldcg(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ double ldcg(const double* p) { return __ldcg(p); }
+#endif
+
+// ---- group barrier: all S CTAs of the group; global writes before it are visible to every CTA after it
+__device__ __forceinline__ void grp_arrive(Gx& b) {
+  __syncthreads();
+  b.epoch += (unsigned)b.S;
+#ifdef EPI_HOST_EMU
+  emu::group_arrive_wait();
+#else
+  if (b.tid == 0) {
+    __threadfence();
+    atomicAdd(b.bar, 1u);
+  }
+#endif
+}
+__device__ __forceinline__ void grp_wait(Gx& b) {
+#ifndef EPI_HOST_EMU
+  if (b.tid == 0) {
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(b.bar) : "memory");
+    } while ((int)(v - b.epoch) < 0);
+    __threadfence();
+  }
+#endif
+  __syncthreads();
+}
+__device__ __forceinline__ void grp_sync(Gx& b) {
+  grp_arrive(b);
+  grp_wait(b);
+}
+
+// block sum (warp shuffles, then the warp partials in fixed order); every thread receives the bit-identical result
+__device__ __forceinline__ double block_sum(const DevPlan& P, const Gx& b, double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  double* red = (double*)(b.smem + GL.s_red);
+  const int w = b.tid >> 5;
+  constexpr int nw = GTH >> 5;
+  if ((b.tid & 31) == 0) red[w] = v;
+  __syncthreads();
+  double r = 0;
+#pragma unroll 1
+  for (int i = 0; i < nw; i++) r += red[i];
+  __syncthreads();
+  return r;
+}
+
+// group sum of n <= 2 values: block sums -> partials in the group scratch -> barrier -> every CTA adds the S partials
+// in the same order (so every thread of the group holds the same bits)
+template <int n>
+__device__ __forceinline__ void grp_sum(const DevPlan& P, Gx& b, double (&v)[n]) {
+  double* part = (double*)(b.gs + GL.g_part) + (size_t)b.parity * GSS * GL.np;
+#pragma unroll
+  for (int i = 0; i < n; i++) v[i] = block_sum(P, b, v[i]);
+  if (b.tid == 0) {
+#pragma unroll
+    for (int i = 0; i < n; i++) part[(size_t)b.cta * GL.np + i] = v[i];
+  }
+  grp_sync(b);
+  double* st = (double*)(b.smem + GL.s_red) + 32;
+  for (int q = b.tid; q < GSS * n; q += GTH) st[q] = ldcg(part + (size_t)(q / n) * GL.np + (q % n));
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < n; i++) {
+    double r = 0;
+#pragma unroll 1
+    for (int c = 0; c < GSS; c++) r += st[c * n + i];
+    v[i] = r;
+  }
+  __syncthreads();
+  b.parity ^= 1;
+}
+
+// time-t tables of the env (every CTA keeps its own copy in shared memory); mixing tables in the layout
+// T[lc][u0][v][u] with padded rows: a cell's thread reads its row with 128-bit loads, the two locales of a warp
+// read the same addresses (broadcast) and the 16 groups of a locale hit distinct banks
+__device__ __forceinline__ void fill_tables(const DevPlan& P, const Gx& b, float tf) {
+  constexpr int G = spec::G, F = spec::F, NG = spec::NG, n_lc = spec::n_lc, PP = spec::P;
+  const float* fi_y = (const float*)(b.cs + GL.c_fi_y);
+  const float* fi_gap = (const float*)(b.cs + GL.c_fi_gap);
+  for (int i = b.tid; i < n_lc * PP * G; i += b.T) GT(mpt0, i) = lerp_rn(GT(mpy, i), GT(mpg, i), tf);
+  for (int i = b.tid; i < n_lc * F * G * G; i += b.T) {
+    int u = i % G, u0 = (i / G) % G, lv = i / (G * G), lc = lv / F, v = lv - lc * F;
+    float ft = lerp_rn(GT(ft_y, lv * G + u), GT(ft_gap, lv * G + u), tf);
+    int a = (lv * G + u0) * G + u, bb = (lv * G + u) * G + u0;
+    float fa = lerp_rn(fi_y[a], fi_gap[a], tf), fb = lerp_rn(fi_y[bb], fi_gap[bb], tf);
+    const int it = (lc * G + u0) * GL.trow + v * G + u;
+    GT(Tnum, it) = __fmul_rn(__fmul_rn(ft, fa), fb);  // f32 product (core_optimize.py:114)
+    if (spec::has_ft_ops) GT(Tden, it) = (real)ft * (real)__ldg(P.fi0 + a) * (real)__ldg(P.fi0 + bb);
+  }
+  constexpr int FG = F * G, nFG = n_lc * FG;
+  for (int i = b.tid; i < NG * nFG; i += b.T) {
+    int k = i / nFG, r = i - k * nFG;  // r = (lc*F + v)*G + u0
+    real cf = (real)lerp_rn(GT(ft_y, r), GT(ft_gap, r), tf);
+    int pi = __ldg(P.ig_p0i + k);
+    cf *= (real)lerp_rn(GT(mpFy, pi * nFG + r), GT(mpFg, pi * nFG + r), tf);
+    for (int q = __ldg(P.ig_np_off + k); q < __ldg(P.ig_np_off + k + 1); q++) {
+      pi = __ldg(P.ig_npi + q);
+      cf *= (real)lerp_rn(GT(mpFy, pi * nFG + r), GT(mpFg, pi * nFG + r), tf);
+    }
+    for (int q = __ldg(P.ig_dp_off + k); q < __ldg(P.ig_dp_off + k + 1); q++) {
+      pi = __ldg(P.ig_dpi + q);
+      float m = lerp_rn(GT(mpFy, pi * nFG + r), GT(mpFg, pi * nFG + r), tf);
+      if (fabsf(m) > 0) cf /= (real)m;
+    }
+    GT(coefS, i) = cf;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// one right-hand-side evaluation (core_optimize.py:165-222). Stage input y = XF + hh * sum_{j<nj} co[j] K_j is
+// formed here and stays in registers; FB += bw * f, FE += ew * f for every flow f of the evaluation; `st6`: the
+// flows are also stored (last stage of an attempt / f(0, y0): they open the next attempt, first-same-as-last).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rhs(const DevPlan& P, Gx& b, bool dyn, double t, int ex_bits, int phase, int stage, real bw,
+                                    real ew, bool st6, double hh, int nj, real (&y)[spec::C], real (&FB)[spec::NSRC],
+                                    real (&FE)[spec::NSRC]) {
+  constexpr int G = spec::G, F = spec::F, LG = spec::LG, nnz = spec::nnz, NG = spec::NG, n_lc = spec::n_lc, PP = spec::P,
+                C = spec::C, nE = spec::E, nS = spec::has_src64 ? spec::n_slot : 0;
+  const float tf = (float)t;
+  const float qf = (float)((-3.0 * t + 4.0) * t);  // utility/utils.py:34-37, rounded like parameter.py:83
+  if (dyn) {
+    __syncthreads();  // the previous evaluation's readers of the time-t tables are done
+    fill_tables(P, b, tf);
+    __syncthreads();
+  }
+  const int kslot = stage == 0 ? b.s0 : (stage == 1 || stage == 6) ? b.s1 : stage;
+  real alive = 0;
+  double ysS[nS > 0 ? nS : 1];
+  // ---- pass 1: stage input, alive (N excludes death and hospitalized, :28-41,:168), weighted infectious sums
+  if (b.valid) {
+#pragma unroll
+    for (int k = 0; k < C; k++) y[k] = 0;
+    double dS[nS > 0 ? nS : 1];
+#pragma unroll
+    for (int q = 0; q < nS; q++) dS[q] = 0;
+#pragma unroll 1
+    for (int j = 0; j < nj; j++) {
+      const int sl = j == 0 ? b.s0 : j == 1 ? b.s1 : j;
+      const real cj = rkCO(real(0), phase, j);
+      const real* kj = &SK(sl, 0);
+#pragma unroll
+      for (int k = 0; k < C; k++) y[k] += kj[k * GTH] * cj;
+#pragma unroll
+      for (int q = 0; q < nS; q++) dS[q] += SKS(sl, q) * RK_CO64[phase][j];
+    }
+#pragma unroll
+    for (int k = 0; k < C; k++) y[k] = y[k] * (real)hh + GXF(k);
+#pragma unroll
+    for (int q = 0; q < nS; q++) ysS[q] = b.gX[(size_t)spec::slot_c1[q] * LG + b.cell] + dS[q] * hh;
+    real xw[NG > 0 ? NG : 1];
+    spec::phaseA(y, alive, xw);
+    GCOL(GL.g_cmA, real, 0) = alive;
+#pragma unroll
+    for (int k = 0; k < NG; k++) GCOL(GL.g_cmA, real, 1 + k) = xw[k];
+    // the stage input waits in the slot this evaluation will fill (its old content is dead): 15 registers less while
+    // the gathers and the mixing run
+    if (NG > 0) {
+#pragma unroll
+      for (int k = 0; k < C; k++) SK(kslot, k) = y[k];
+    }
+  }
+  real rs[NG > 0 ? NG : 1];
+#pragma unroll
+  for (int k = 0; k < NG; k++) rs[k] = 0;
+  if (NG > 0) {
+    grp_sync(b);
+    // ---- pass 2: CSC gather over source locales (compute_foi_entry inner loop, :105-111) -> shared memory
+    if (b.valid) {
+      real a = 0, xs[NG > 0 ? NG : 1];
+#pragma unroll
+      for (int k = 0; k < NG; k++) xs[k] = 0;
+      const real* cmA = (const real*)(b.gs + GL.g_cmA);
+      for (int q = __ldg(P.csc_indptr + b.j); q < __ldg(P.csc_indptr + b.j + 1); q++) {
+        const int src = __ldg(P.csc_indices + q) * G + b.u;
+        const real val = (real)__ldg(P.mx_csc + (size_t)b.u * nnz + q);
+        a += ldcg(cmA + src) * val;
+#pragma unroll
+        for (int k = 0; k < NG; k++) xs[k] += ldcg(cmA + (size_t)(1 + k) * LG + src) * val;
+      }
+      SCMB(0, b.tid) = a;
+#pragma unroll
+      for (int k = 0; k < NG; k++) SCMB(1 + k, b.tid) = xs[k];
+    }
+    __syncthreads();
+    // ---- pass 3: G x G facility mixing -> force of infection -> s[k] for (j, u0)  (:112-124, :146-157)
+    if (b.valid) {
+      real sk[NG > 0 ? NG : 1];
+#pragma unroll
+      for (int k = 0; k < NG; k++) sk[k] = 0;
+      const int row = b.tid - b.u;  // the locale's first column
+      const float* Tn = &GT(Tnum, (b.lc * G + b.u) * GL.trow);
+      const real* Td = &GT(Tden, (b.lc * G + b.u) * GL.trow);
+      real den[F], num[NG > 0 ? NG : 1][F];
+#pragma unroll
+      for (int v = 0; v < F; v++) {
+        den[v] = 0;
+#pragma unroll
+        for (int k = 0; k < NG; k++) num[k][v] = 0;
+      }
+      if (G % 4 == 0) {
+        // four groups of the locale at a time: their gathered columns in registers (128-bit broadcast reads), against
+        // the F rows of the cell's tables (128-bit reads, conflict-free over the locale's groups)
+#pragma unroll 1
+        for (int u4 = 0; u4 < G / 4; u4++) {
+          float4 c4[1 + NG];
+#pragma unroll
+          for (int k = 0; k < 1 + NG; k++) c4[k] = *(const float4*)&SCMB(k, row + 4 * u4);
+#pragma unroll
+          for (int v = 0; v < F; v++) {
+            const float4 tn = *(const float4*)(Tn + v * G + 4 * u4);
+            const float4 td = *(const float4*)(Td + v * G + 4 * u4);
+            den[v] += c4[0].x * td.x; den[v] += c4[0].y * td.y; den[v] += c4[0].z * td.z; den[v] += c4[0].w * td.w;
+#pragma unroll
+            for (int k = 0; k < NG; k++) {
+              num[k][v] += c4[1 + k].x * tn.x; num[k][v] += c4[1 + k].y * tn.y;
+              num[k][v] += c4[1 + k].z * tn.z; num[k][v] += c4[1 + k].w * tn.w;
+            }
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int u = 0; u < G; u++) {
+          real c1[1 + NG];
+#pragma unroll
+          for (int k = 0; k < 1 + NG; k++) c1[k] = SCMB(k, row + u);
+#pragma unroll
+          for (int v = 0; v < F; v++) {
+            den[v] += c1[0] * Td[v * G + u];
+#pragma unroll
+            for (int k = 0; k < NG; k++) num[k][v] += c1[1 + k] * (real)Tn[v * G + u];
+          }
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < F; v++) {
+        real dn = den[v];
+        if (dn <= (real)1e-15) dn = 1;
+        const real rden = frcp(dn);
+#pragma unroll
+        for (int k = 0; k < NG; k++) sk[k] += GT(coefS, ((k * n_lc + b.lc) * F + v) * G + b.u) * (num[k][v] * rden);
+      }
+#pragma unroll
+      for (int k = 0; k < NG; k++) GCOL(GL.g_cmS, real, k) = sk[k];
+    }
+    grp_sync(b);
+    // ---- pass 4a: CSR gather over destination locales (:144-158)
+    if (b.valid) {
+      const real* cmS = (const real*)(b.gs + GL.g_cmS);
+      for (int q = __ldg(P.csr_indptr + b.j); q < __ldg(P.csr_indptr + b.j + 1); q++) {
+        const int dst = __ldg(P.csr_indices + q) * G + b.u;
+        const real val = (real)__ldg(P.mx_csr + (size_t)b.u * nnz + q);
+#pragma unroll
+        for (int k = 0; k < NG; k++) rs[k] += ldcg(cmS + (size_t)k * LG + dst) * val;
+      }
+    }
+  }
+  // ---- pass 4b: edges, scatter into dX, clamped moves, flow sums
+  if (b.valid) {
+    const float* mp = &GT(mpt0, b.lc * PP * G + b.u);  // parameters from facility 0 only (:48)
+    if (NG > 0) {
+#pragma unroll
+      for (int k = 0; k < C; k++) y[k] = SK(kslot, k);
+    }
+    real d[C];
+    real* out = (real*)(b.gs + GL.g_fl6) + b.cell;
+    spec::flows_acc(y, alive, mp, rs, d, FB, FE, bw, ew, out, (size_t)LG, st6);
+#pragma unroll
+    for (int sl = 0; sl < spec::n_slot; sl++) {
+      real nv = 0;
+      const int c1 = spec::slot_c1[sl], c2 = spec::slot_c2[sl];
+      if (__ldg(P.slot_cover + (size_t)sl * LG + b.cell) && ((ex_bits >> sl) & 0x10001)) {
+        float my = ((ex_bits >> sl) & 1) ? b.mvY[(size_t)sl * LG + b.cell] : 0.0f;
+        float md = ((ex_bits >> (16 + sl)) & 1) ? b.mvD[(size_t)sl * LG + b.cell] : 0.0f;
+        float v = __fadd_rn(__fmul_rn(__fsub_rn(md, my), qf), my);  // coo.py scale/add in f32
+        double y1 = spec::has_src64 ? ysS[sl] : (double)y[c1], y2 = (double)y[c2];
+        double n1 = y1 + (double)d[c1], n2 = y2 + (double)d[c2];
+        double nvd = (double)v < n1 ? (double)v : n1;
+        double k1 = (n1 - nvd) - y1;
+        d[c1] = (real)k1;
+        d[c2] = (real)((n2 + nvd) - y2);
+        nv = (real)nvd;
+        if (spec::has_src64) SKS(kslot, sl) = k1;
+      } else if (spec::has_src64) {
+        SKS(kslot, sl) = (double)d[c1];
+      }
+      FB[nE + NG + sl] += bw * nv;
+      FE[nE + NG + sl] += ew * nv;
+      if (st6) out[(size_t)(nE + NG + sl) * LG] = nv;
+    }
+#pragma unroll
+    for (int k = 0; k < C; k++) SK(kslot, k) = d[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// day prologue (Executor.execute + get_parameter_from_delta + get_gap_parameter). Select sums and the departing
+// populations of the MOVE ops need the whole env: one group reduction for all of them; the rest is per cell or a
+// per-CTA copy of the env's small tables.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int prologue(const DevPlan& P, Gx& b, int variant, double* Xprev_g, int ex_y_bits, bool& dyn,
+                                        bool& tabs_current) {
+  constexpr int LG = spec::LG, G = spec::G, L = spec::L, C = spec::C, F = spec::F, PP = spec::P;
+  double x[C];
+#pragma unroll
+  for (int k = 0; k < C; k++) x[k] = b.valid ? b.gX[(size_t)k * LG + b.cell] : 0.0;
+  // 1. select sums (executor.py:346-359, ['Value'].sum()) and departing populations (executor.py:181-183)
+  double* part = (double*)(b.gs + GL.g_part) + (size_t)b.parity * GSS * GL.np;
+  for (int s = 0; s < P.n_sel; s++) {
+    double v = 0;
+    const int mode = P.sel_mode[s];
+    if (b.valid && P.sel_l[s * L + b.j] && P.sel_g[s * G + b.u]) {
+#pragma unroll
+      for (int k = 0; k < C; k++)
+        if (P.sel_c[s * C + k]) {
+          if (mode == 0) v += x[k];
+          else if (mode == 1) v += P.X0[(size_t)k * LG + b.cell];
+          else v += x[k] - Xprev_g[(size_t)P.chg_slot_of_comp[k] * LG + b.cell];
+        }
+    }
+    v = block_sum(P, b, v);
+    if (b.tid == 0) part[(size_t)b.cta * GL.np + s] = v;
+  }
+  for (int mo = 0; mo < P.n_mv_op; mo++) {
+    double v = 0;
+    if (b.valid && P.mv_g[mo * G + b.u] && P.mv_l1[mo * L + b.j])
+      for (int q = P.mv_c1_off[mo]; q < P.mv_c1_off[mo + 1]; q++) {
+        const int c1 = P.mv_c1[q];
+#pragma unroll
+        for (int k = 0; k < C; k++)
+          if (k == c1) v += x[k];
+      }
+    v = block_sum(P, b, v);
+    if (b.tid == 0) part[(size_t)b.cta * GL.np + P.n_sel + mo] = v;
+  }
+  grp_sync(b);
+  double* dep = (double*)(b.smem + GL.s_red) + 32;  // departing populations, [n_mv_op]
+  for (int i = b.tid; i < P.n_sel + P.n_mv_op; i += b.T) {
+    double r = 0;
+    for (int c = 0; c < b.S; c++) r += ldcg(part + (size_t)c * GL.np + i);
+    if (i < P.n_sel) GT(sel, i) = r;
+    else dep[i - P.n_sel] = r;
+  }
+  b.parity ^= 1;
+  __syncthreads();
+  // the previous state for tomorrow's 'change' selects is today's start state (epidemic.py:96-99)
+  if (b.valid) {
+#pragma unroll
+    for (int k = 0; k < C; k++) {
+      const int sl = P.chg_slot_of_comp[k];
+      if (sl >= 0) Xprev_g[(size_t)sl * LG + b.cell] = x[k];
+    }
+  }
+  // 2. expressions
+  for (int e = b.tid; e < P.n_expr; e += b.T) {
+    int itv = P.expr_itv[e];
+    bool live = GT(act, itv) && P.expr_prog[e] == (variant ? P.prog_init[itv] : P.prog_step[itv]);
+    GT(expr, e) = live ? eval_expr(P, e, &GT(cpv, 0), &GT(sel, 0)) : 0.0;
+  }
+  __syncthreads();
+  // 3. class multipliers: sequential f32 products in op order (nb_apply, executor.py:116-164)
+  for (int k = b.tid; k < P.n_cls; k += b.T) {
+    float m = 1.0f;
+    for (int q = P.cls_off[k]; q < P.cls_off[k + 1]; q++) {
+      int o = P.cls_op[q];
+      if (op_live(P, &GT(act, 0), variant, o)) m = __fmul_rn(m, (float)GT(expr, P.op_expr[o]));
+    }
+    GT(mult_d, k) = m;
+  }
+  __syncthreads();
+  {
+    int diff = 0;
+    for (int k = b.tid; k < P.n_cls; k += b.T) diff |= GT(mult_d, k) != GT(mult_y, k);
+    dyn = __syncthreads_or(diff) != 0;
+  }
+  const bool rebuild = dyn || !tabs_current;
+  if (rebuild) {
+    // 4. facility tables of yesterday and today -> (y, gap)   (parameter.py:64-65,:73-74)
+    float* fi_y = (float*)(b.cs + GL.c_fi_y);
+    float* fi_gap = (float*)(b.cs + GL.c_fi_gap);
+    for (int row = b.tid; row < P.n_lc * F * G; row += b.T) {
+      float a[32], bb[32];  // G <= 32 (checked on the host)
+      facility_row_fi(P, &GT(mult_y, 0), row, a);
+      facility_row_fi(P, &GT(mult_d, 0), row, bb);
+      for (int g2 = 0; g2 < G; g2++) {
+        fi_y[row * G + g2] = a[g2];
+        fi_gap[row * G + g2] = __fsub_rn(bb[g2], a[g2]);
+      }
+    }
+    for (int it = b.tid; it < P.n_lc * G; it += b.T) {
+      int lc = it / G, g = it % G;
+      float a[32], bb[32];  // F <= 32 (checked on the host)
+      float s = 0.0f, s2 = 0.0f;
+      for (int f = 0; f < F; f++) {
+        int i = (lc * F + f) * G + g;
+        a[f] = __fmul_rn(P.ft0[i], GT(mult_y, P.ft_cls[i]));
+        bb[f] = __fmul_rn(P.ft0[i], GT(mult_d, P.ft_cls[i]));
+        s = __fadd_rn(s, a[f]);
+        s2 = __fadd_rn(s2, bb[f]);
+      }
+      for (int f = 0; f < F; f++) {
+        int i = (lc * F + f) * G + g;
+        float ya = s > 1e-15f ? __fdiv_rn(a[f], s) : (f == 0 ? 1.0f : 0.0f);
+        float yb = s2 > 1e-15f ? __fdiv_rn(bb[f], s2) : (f == 0 ? 1.0f : 0.0f);
+        GT(ft_y, i) = ya;
+        GT(ft_gap, i) = __fsub_rn(yb, ya);
+      }
+    }
+    for (int i = b.tid; i < P.n_lc * PP * G; i += b.T) {
+      int g = i % G, p = (i / G) % PP, lc = i / (G * PP);
+      int idx = ((lc * PP + p) * F + 0) * G + g;
+      float m0 = __ldg(P.mp0 + idx);
+      int cls = __ldg(P.mp_cls + idx);
+      float yv = __fmul_rn(m0, GT(mult_y, cls)), dv = __fmul_rn(m0, GT(mult_d, cls));
+      GT(mpy, i) = yv;
+      GT(mpg, i) = __fsub_rn(dv, yv);
+    }
+    const int nFG = P.n_lc * F * G;
+    for (int i = b.tid; i < P.n_igp * nFG; i += b.T) {
+      int pi = i / nFG, r = i - pi * nFG, lc = r / (F * G), fg = r - lc * F * G;
+      int idx = (lc * PP + __ldg(P.igp + pi)) * F * G + fg;
+      float m0 = __ldg(P.mp0 + idx);
+      int cls = __ldg(P.mp_cls + idx);
+      float yv = __fmul_rn(m0, GT(mult_y, cls)), dv = __fmul_rn(m0, GT(mult_d, cls));
+      GT(mpFy, i) = yv;
+      GT(mpFg, i) = __fsub_rn(dv, yv);
+    }
+  }
+  // 5. move table of today (nb_move, executor.py:166-234; different compartment, same locale)
+  if (b.valid)
+    for (int sl = 0; sl < spec::n_slot; sl++) b.mvD[(size_t)sl * LG + b.cell] = 0.0f;
+  int ex_d = 0;
+  for (int mo = 0; mo < P.n_mv_op; mo++) {
+    int o = P.mv_op[mo];
+    bool live = op_live(P, &GT(act, 0), variant, o);
+    int nc1 = P.mv_c1_off[mo + 1] - P.mv_c1_off[mo], nc2 = P.mv_c2_off[mo + 1] - P.mv_c2_off[mo];
+    const int* c1s = P.mv_c1 + P.mv_c1_off[mo];
+    const int* c2s = P.mv_c2 + P.mv_c2_off[mo];
+    const double depart_sum = dep[mo];
+    if (live && depart_sum > 0) {
+      double value = GT(expr, P.op_expr[o]);
+      if (b.valid && P.mv_g[mo * G + b.u] && P.mv_l1[mo * L + b.j]) {
+        auto xv = [&](int c) {
+          double r = 0;
+#pragma unroll
+          for (int k = 0; k < C; k++)
+            if (k == c) r = x[k];
+          return r;
+        };
+        for (int q1 = 0; q1 < nc1; q1++) {
+          int c1 = c1s[q1];
+          double depart = xv(c1) / depart_sum * value;
+          double arrive = 0;
+          for (int q = 0; q < nc2; q++) arrive += xv(c2s[q]);
+          for (int q = 0; q < nc2; q++) {
+            double amt = arrive > 0 ? xv(c2s[q]) / arrive * depart : 1.0 / nc2 * depart;
+            int sl = P.slot_of_pair[c1 * C + c2s[q]];
+            float* cellp = &b.mvD[(size_t)sl * LG + b.cell];
+            *cellp = (float)((double)*cellp + amt);  // CooMatrix.element_add: f32 cell (coo.py:52-57)
+          }
+        }
+      }
+      for (int q1 = 0; q1 < nc1; q1++)
+        for (int q = 0; q < nc2; q++) ex_d |= 1 << P.slot_of_pair[c1s[q1] * C + c2s[q]];
+    }
+  }
+  // 6. cost rates of today (nb_add, executor.py:236-243) for the (intervention, locale) entries of this CTA
+  for (int q = b.tid; q < P.I * b.nl; q += b.T) {
+    int i = q / b.nl, l = b.l0 + q % b.nl;
+    double cr = 0;
+    for (int ao = 0; ao < P.n_add_op; ao++) {
+      int o = P.add_op[ao];
+      if (P.add_i[ao * P.I + i] && P.add_l[(size_t)ao * L + l] && op_live(P, &GT(act, 0), variant, o))
+        cr += GT(expr, P.op_expr[o]) / (double)P.add_parts[ao];
+    }
+    b.crD[(size_t)i * L + l] = cr;
+  }
+  __syncthreads();
+  if (!dyn && rebuild) fill_tables(P, b, 0.0f);  // constant over the day: filled once
+  tabs_current = !dyn;
+  __syncthreads();
+  return (ex_y_bits & 0xffff) | (ex_d << 16);
+}
+
+// ------------------------------------------------------------------------------------------
+// one simulated day: scipy RK45 state machine (rk.py:86-176, common.py:63-134), uniform over the group
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool rk45_day(const DevPlan& P, Gx& b, bool dyn, int ex_bits, int* trace, double* last_err_out,
+                                         double* dbg, bool skip0) {
+  const double rtol = 1e-3, atol = 1e-6;
+  const real rtolr = (real)1e-3, atolr = (real)1e-6;
+  constexpr int C = spec::C, L = spec::L, LG = spec::LG, nS = spec::has_src64 ? spec::n_slot : 0, NSRC = spec::NSRC,
+                n_acc = spec::n_acc;
+  const int nCl = spec::I * b.nl;  // cost entries of this CTA
+  const double inv_n = 1.0 / (double)P.n_flat;
+  int nfev = 0, nsteps = 0, nrej = 0, status = 0, n_att = 0, guard = 0;
+  double last_err = 0, t = 0.0, h_abs = 0, h = 0, t_new = 0, h0 = 0, d0 = 0, d1 = 0;
+  bool run = true, rejected = false;
+  auto qd = [](double tt) { return (double)(float)((-3.0 * tt + 4.0) * tt); };
+  auto centry = [&](int q) { return (size_t)(q / b.nl) * L + b.l0 + q % b.nl; };
+  real y[C];
+#pragma unroll
+  for (int k = 0; k < C; k++) y[k] = 0;
+  // the packed flow sums of the current attempt live in registers for the whole day
+  real FB[NSRC], FE[NSRC];
+#pragma unroll
+  for (int i = 0; i < NSRC; i++) FB[i] = FE[i] = 0;
+  const real* fl6 = (const real*)(b.gs + GL.g_fl6) + b.cell;
+
+  int phase = 0;
+  while (phase >= 0) {
+    const int stage = PH_STAGE[phase];
+    if (phase == 2) {
+      // a new attempt (rk.py:111-128)
+      double min_step = 10 * fabs(__longlong_as_double(__double_as_longlong(t) + 1) - t);  // nextafter(t, inf), t >= 0
+      if (h_abs < min_step) {
+        if (rejected) { status = -1; run = false; }
+        else h_abs = min_step;
+      }
+      if (++guard > 10000 || !(h_abs == h_abs)) { status = -1; run = false; }
+      if (!run) break;
+      h = h_abs;
+      t_new = t + h;
+      if (t_new - 1.0 > 0) t_new = 1.0;
+      h = t_new - t;
+      h_abs = fabs(h);
+    }
+    const int nj = PH_NJ[phase];
+    const double hh = phase <= 1 ? h0 : h;
+    const double t_eval = t + PH_TC[phase] * hh;
+    real bw = phBW(real(0), phase), ew = phEW(real(0), phase);
+    // the flow sums are accumulated (FB += bw f, FE += ew f); the phases that SET them clear first:
+    // phase 0: FE = f(0, y0); phase 1: FB = f(h0, y0 + h0 f0); phase 8: FB = B_0 f, FE = E_0 f
+    if (phase == 0) {
+      bw = 0; ew = 1;
+#pragma unroll
+      for (int i = 0; i < NSRC; i++) FE[i] = 0;
+    } else if (phase == 1) {
+      bw = 1; ew = 0;
+#pragma unroll
+      for (int i = 0; i < NSRC; i++) FB[i] = 0;
+    } else if (phase == 8) {
+#pragma unroll
+      for (int i = 0; i < NSRC; i++) FB[i] = FE[i] = 0;
+    }
+    if (phase == 0 && skip0) {
+      // f(0, y0) of this day is the previous day's last stage (same state, same parameters): its derivatives sit in
+      // slot s0 already, its flows in the last-stage column
+      if (b.valid) {
+#pragma unroll
+        for (int i = 0; i < NSRC; i++) FE[i] = fl6[(size_t)i * LG];
+      }
+    } else {
+      rhs(P, b, dyn, t_eval, ex_bits, phase, stage, bw, ew, phase == 7, hh, nj, y, FB, FE);
+    }
+    if (phase == 0) {
+      // select_initial_step (common.py:68-134), first half
+      double s01[2] = {0, 0};
+      if (b.valid) {
+        real a0 = 0, a1 = 0;
+#pragma unroll
+        for (int k = 0; k < C; k++) {
+          real yv = GXF(k), sc = atolr + fabs(yv) * rtolr;
+          real a = fdiv(yv, sc), bq = fdiv(SK(b.s0, k), sc);
+          a0 += a * a; a1 += bq * bq;
+        }
+#pragma unroll
+        for (int a_ = 0; a_ < n_acc; a_++) {
+          real g0 = 0;
+#pragma unroll
+          for (int q = spec::ag_off[a_]; q < spec::ag_off[a_ + 1]; q++) g0 += FE[spec::ag_src[q]] * (real)spec::ag_coef[q];
+          real yv = b.acc[(size_t)a_ * LG + b.cell], sc = atolr + fabs(yv) * rtolr;
+          real a = fdiv(yv, sc), bq = fdiv(g0, sc);
+          a0 += a * a; a1 += bq * bq;
+        }
+        s01[0] = (double)a0; s01[1] = (double)a1;
+      }
+      for (int q = b.tid; q < nCl; q += b.T) {
+        const size_t i = centry(q);
+        double yv = b.cost[i], sc = atol + fabs(yv) * rtol;
+        double a = norm_term(real(0), yv, sc), bq = norm_term(real(0), b.crY[i], sc);  // q(0) = 0
+        s01[0] += a * a; s01[1] += bq * bq;
+      }
+      grp_sum<2>(P, b, s01);
+      d0 = ctrl_sqrt(real(0), s01[0] * inv_n);
+      d1 = ctrl_sqrt(real(0), s01[1] * inv_n);
+      h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+      h0 = fmin(h0, 1.0);
+      nfev++;
+      phase = 1;
+    } else if (phase == 1) {
+      double s2[1] = {0};
+      const double q0 = qd(h0);
+      if (b.valid) {
+        real a2 = 0;
+#pragma unroll
+        for (int k = 0; k < C; k++) {
+          real sc = atolr + fabs(GXF(k)) * rtolr;
+          real a = fdiv(SK(b.s1, k) - SK(b.s0, k), sc);
+          a2 += a * a;
+        }
+#pragma unroll
+        for (int a_ = 0; a_ < n_acc; a_++) {
+          real g = 0;
+#pragma unroll
+          for (int q = spec::ag_off[a_]; q < spec::ag_off[a_ + 1]; q++)
+            g += (FB[spec::ag_src[q]] - FE[spec::ag_src[q]]) * (real)spec::ag_coef[q];
+          real sc = atolr + fabs(b.acc[(size_t)a_ * LG + b.cell]) * rtolr;
+          real a = fdiv(g, sc);
+          a2 += a * a;
+        }
+        s2[0] = (double)a2;
+      }
+      // stage-0 contributions of the first attempt
+#pragma unroll
+      for (int i = 0; i < NSRC; i++) {
+        const real f = FE[i];
+        FB[i] = rkB(real(0), 0) * f;
+        FE[i] = rkE(real(0), 0) * f;
+      }
+      for (int q = b.tid; q < nCl; q += b.T) {
+        const size_t i = centry(q);
+        double sc = atol + fabs(b.cost[i]) * rtol, a = norm_term(real(0), (b.crD[i] - b.crY[i]) * q0, sc);
+        s2[0] += a * a;
+      }
+      grp_sum<1>(P, b, s2);
+      double d2 = ctrl_sqrt(real(0), s2[0] * inv_n) / h0;
+      double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : ctrl_pow(real(0), 0.01 / fmax(d1, d2), 0.2);
+      h_abs = fmin(fmin(100 * h0, h1), 1.0);
+      nfev++;
+      phase = 2;
+    } else if (phase < 7) {
+      phase++;
+    } else if (phase == 7) {
+      // error norm over ALL n_flat components (common.py:63-65, rk.py:146-148), accept / reject
+      double e2[1] = {0}, qs[7];
+      nfev += 6;
+      real dy[C];
+      if (b.valid) {
+        real ae = 0;
+#pragma unroll
+        for (int k = 0; k < C; k++) {
+          // y[k] is the input of stage 6 = the 5th-order candidate y_new
+          real sc = atolr + fmax(fabs(GXF(k)), fabs(y[k])) * rtolr;
+          real e = 0, inc = 0;
+#pragma unroll
+          for (int j = 0; j < 7; j++) {
+            if (j == 1) continue;  // B_1 = E_1 = 0 (and slot s1 holds stage 6 by now)
+            const real kj = SK(j == 0 ? b.s0 : j == 6 ? b.s1 : j, k);
+            e += kj * rkE(real(0), j);
+            if (j < 6) inc += kj * rkB(real(0), j);
+          }
+          dy[k] = inc;
+          real a = fdiv(e * (real)h, sc);
+          ae += a * a;
+        }
+#pragma unroll
+        for (int a_ = 0; a_ < n_acc; a_++) {
+          real vB = 0, vE = 0;
+#pragma unroll
+          for (int q = spec::ag_off[a_]; q < spec::ag_off[a_ + 1]; q++) {
+            vB += FB[spec::ag_src[q]] * (real)spec::ag_coef[q];
+            vE += FE[spec::ag_src[q]] * (real)spec::ag_coef[q];
+          }
+          real yv = b.acc[(size_t)a_ * LG + b.cell], yn = yv + (real)h * vB;
+          real sc = atolr + fmax(fabs(yv), fabs(yn)) * rtolr, a = fdiv(vE * (real)h, sc);
+          ae += a * a;
+          b.accn[(size_t)a_ * LG + b.cell] = yn;
+        }
+        e2[0] = (double)ae;
+      }
+#pragma unroll
+      for (int j = 0; j < 7; j++) qs[j] = qd(t + RK_C[j] * h);  // cost rate is a closed form in t
+      for (int q = b.tid; q < nCl; q += b.T) {
+        const size_t i = centry(q);
+        double cy = b.crY[i], cg = b.crD[i] - cy, sb = 0, se = 0;
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+          double k = cy + cg * qs[j];
+          sb += k * RK_B[j];
+          se += k * RK_E[j];
+        }
+        double yv = b.cost[i], yn = yv + h * sb;
+        double sc = atol + fmax(fabs(yv), fabs(yn)) * rtol, a = norm_term(real(0), se * h, sc);
+        e2[0] += a * a;
+      }
+      grp_sum<1>(P, b, e2);
+      double err = ctrl_sqrt(real(0), e2[0] * inv_n);
+      last_err = err;
+      if (dbg && b.tid == 0 && b.cta == 0 && n_att < 64) { dbg[2 * n_att] = h; dbg[2 * n_att + 1] = err; }
+      n_att++;
+      bool accepted = false;
+      if (err < 1) {
+        double factor = err == 0 ? 10.0 : fmin(10.0, 0.9 * ctrl_pow(real(0), err, -0.2));
+        if (rejected) factor = fmin(1.0, factor);
+        h_abs *= factor;
+        accepted = true;
+      } else {
+        h_abs *= fmax(0.2, 0.9 * ctrl_pow(real(0), err, -0.2));
+        rejected = true;
+        nrej++;
+      }
+      if (accepted) {
+        // commit: y = y_new, f = f_new (the state is advanced in double in both modes)
+        if (b.valid) {
+          double xs[nS > 0 ? nS : 1];
+#pragma unroll
+          for (int q = 0; q < nS; q++) {
+            // the move slots' source compartments in double: X + h * sum_j B_j KS_j
+            double inc = 0;
+#pragma unroll
+            for (int j = 0; j < 6; j++) {
+              if (j == 1) continue;
+              inc += SKS(j == 0 ? b.s0 : j, q) * RK_B[j];
+            }
+            xs[q] = b.gX[(size_t)spec::slot_c1[q] * LG + b.cell] + inc * h;
+          }
+#pragma unroll
+          for (int k = 0; k < C; k++) {
+            double xn = b.gX[(size_t)k * LG + b.cell] + h * (double)dy[k];
+#pragma unroll
+            for (int q = 0; q < nS; q++)
+              if (k == spec::slot_c1[q]) xn = xs[q];
+            b.gX[(size_t)k * LG + b.cell] = xn;
+            GXF(k) = (real)xn;
+          }
+          // the last stage's flows open the next attempt (first same as last)
+#pragma unroll
+          for (int i = 0; i < NSRC; i++) {
+            const real f = fl6[(size_t)i * LG];
+            FB[i] = rkB(real(0), 0) * f;
+            FE[i] = rkE(real(0), 0) * f;
+          }
+        }
+        for (int q = b.tid; q < nCl; q += b.T) {
+          const size_t i = centry(q);
+          double cy = b.crY[i], cg = b.crD[i] - cy, sb = 0;
+#pragma unroll
+          for (int j = 0; j < 7; j++) sb += (cy + cg * qs[j]) * RK_B[j];
+          b.cost[i] += h * sb;
+        }
+        nsteps++;
+        t = t_new;
+        rejected = false;
+        if (!(t < 1.0)) run = false;
+        {  // stage 6 becomes stage 0 of the next attempt; the accumulators' candidate column becomes the column
+          const int s_ = b.s0; b.s0 = b.s1; b.s1 = s_;
+          real* t_ = b.acc; b.acc = b.accn; b.accn = t_;
+        }
+        phase = run ? 2 : -1;
+      } else {
+        phase = 8;  // restore the stage-0 terms of the flow sums by re-evaluating f(t, y) (not counted in nfev)
+      }
+    } else {
+      phase = 2;
+    }
+  }
+  if (b.tid == 0 && b.cta == 0) {
+    trace[3] = nfev; trace[4] = nsteps; trace[5] = nrej; trace[2] = status;
+    *last_err_out = last_err;
+  }
+  return status == 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// EpiEnv.step for the envs this group walks (epipolicy_environment.py:39-62), n_days fused
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void step_group(const DevPlan& P, const DevState& S, const StepArgs& a, Gx& b, int group,
+                                           int n_groups) {
+  constexpr int C = spec::C, CLG = spec::CLG, LG = spec::LG, L = spec::L, G = spec::G, F = spec::F, nC = spec::I * spec::L;
+  const size_t nA = (size_t)spec::n_acc * LG, nM = (size_t)spec::n_slot * LG;
+  if (!spec::has_ft_ops) {
+    // the denominator's mixing table does not depend on the env: one copy per CTA, in the padded row layout
+#pragma unroll 1
+    for (int i = b.tid; i < spec::n_lc * F * G * G; i += b.T) {
+      int u0 = i % G, u = (i / G) % G, lv = i / (G * G), lc = lv / F, v = lv - lc * F;  // source layout [lc,F,u,u0]
+      GT(Tden, (lc * G + u0) * GL.trow + v * G + u) = (real)__ldg(P.Tden_constT + i);
+    }
+  }
+  b.crD = (double*)(b.gs + GL.g_crD);
+  b.mvD = (float*)(b.gs + GL.g_mvD);
+  for (int env = group; env < a.N; env += n_groups) {
+    const size_t e = (size_t)env;
+    b.cost = S.cost + e * nC;
+    b.crY = S.crY + e * nC;
+    b.gX = S.X + e * CLG;
+    real* gAcc = (real*)S.acc + e * nA;
+    b.acc = gAcc;
+    b.accn = (real*)(b.gs + GL.g_accN);
+    b.mvY = S.mvY + e * nM;
+    double* gXprev = S.Xprev + e * P.n_chg * LG;
+    int* meta = S.meta + e * 8;
+    b.s0 = 0; b.s1 = 1;
+    if (b.valid) {
+#pragma unroll
+      for (int k = 0; k < C; k++) GXF(k) = (real)b.gX[(size_t)k * LG + b.cell];
+    }
+    for (int i = b.tid; i < P.n_cls; i += b.T) GT(mult_y, i) = S.multY[e * P.n_cls + i];
+    for (int k = b.tid; k < P.NCP; k += b.T) {
+      float v;
+      if (a.cpv) v = a.cpv[e * P.NCP + k];
+      else if (a.init_only) v = P.init_cpv[k];
+      else { int s = P.cp_src[k]; v = s >= 0 ? a.actions[e * P.A + s] : P.cp_fixed[k]; }
+      GT(cpv, k) = v;
+    }
+    for (int i = b.tid; i < P.I; i += b.T)
+      GT(act, i) = a.active ? a.active[e * P.I + i] : (a.init_only ? P.init_active[i] : 1);
+    int t_day = meta[0], ex_y = meta[1];
+    __syncthreads();
+
+    double reward = 0;  // this thread's share: -(cost after - cost before) of its cost entries, summed over the days
+    bool tabs_current = false, fsal_ok = false;
+    const int n_days = a.init_only ? 1 : a.n_days;
+    const int nCl = spec::I * b.nl;
+    for (int day = 0; day < n_days; day++) {
+      bool dyn = true;
+      int ex_bits = prologue(P, b, a.variant, gXprev, ex_y, dyn, tabs_current);
+      if (!a.init_only) {
+        double c0 = 0, c1 = 0;
+        for (int q = b.tid; q < nCl; q += b.T) c0 += b.cost[(size_t)(q / b.nl) * L + b.l0 + q % b.nl];
+        const bool skip0 = EPI_FSAL_DAYS && fsal_ok && !dyn;
+        fsal_ok = rk45_day(P, b, dyn, ex_bits, meta, S.last_err + e, a.dbg_attempts ? a.dbg_attempts + e * 128 : nullptr,
+                           skip0);
+        for (int q = b.tid; q < nCl; q += b.T) c1 += b.cost[(size_t)(q / b.nl) * L + b.l0 + q % b.nl];
+        reward -= c1 - c0;  // -sum(cumulative_cost_next - cumulative_cost_current), epidemic.py:115
+        t_day++;
+      }
+      // today's parameters become yesterday's (State(t+1, next_obs, dest_parameter), epidemic.py:89)
+      __syncthreads();
+      for (int i = b.tid; i < P.n_cls; i += b.T) GT(mult_y, i) = GT(mult_d, i);
+      if (b.valid)
+        for (int s = 0; s < spec::n_slot; s++) b.mvY[(size_t)s * LG + b.cell] = b.mvD[(size_t)s * LG + b.cell];
+      for (int q = b.tid; q < nCl; q += b.T) {
+        const size_t i = (size_t)(q / b.nl) * L + b.l0 + q % b.nl;
+        b.crY[i] = b.crD[i];
+      }
+      ex_y = (ex_bits >> 16) & 0xffff;
+      __syncthreads();
+      if (t_day >= P.horizon) break;  // the reference's EpiEnv.step stops its day loop at done
+    }
+    double rw[1] = {reward};
+    grp_sum<1>(P, b, rw);
+    if (b.valid) {
+#pragma unroll
+      for (int k = 0; k < C; k++) {
+        const double x = b.gX[(size_t)k * LG + b.cell];
+        if (a.obs_out) ((real*)a.obs_out)[e * CLG + (size_t)k * LG + b.cell] = (real)x;
+        if (a.obs_out2) ((real*)a.obs_out2)[e * CLG + (size_t)k * LG + b.cell] = (real)x;
+      }
+      if (b.acc != gAcc)
+        for (int a_ = 0; a_ < spec::n_acc; a_++) gAcc[(size_t)a_ * LG + b.cell] = b.acc[(size_t)a_ * LG + b.cell];
+    }
+    if (b.cta == 0) {
+      for (int i = b.tid; i < P.n_cls; i += b.T) S.multY[e * P.n_cls + i] = GT(mult_y, i);
+      if (b.tid == 0) {
+        meta[0] = t_day; meta[1] = ex_y;
+        if (a.reward_out) a.reward_out[env] = rw[0];
+        if (a.done_out) a.done_out[env] = (uint8_t)(t_day >= P.horizon);
+        if (a.reward_out2) a.reward_out2[env] = rw[0];
+        if (a.done_out2) a.done_out2[env] = (uint8_t)(t_day >= P.horizon);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ Gx bind(const DevPlan& P, const StepArgs& a, char* smem, int tid, int nt, int block) {
+  Gx b;
+  b.tid = tid; b.T = nt;   // nt == GTH
+  b.S = GSS;
+  const int group = block / GSS;
+  b.cta = block - group * GSS;
+  b.l0 = (b.cta * spec::L) / GSS;
+  b.nl = ((b.cta + 1) * spec::L) / GSS - b.l0;
+  const int jl = tid / spec::G;
+  b.u = tid - jl * spec::G;
+  b.valid = jl < b.nl;
+  b.j = b.valid ? b.l0 + jl : b.l0;
+  b.cell = b.j * spec::G + b.u;
+  b.lc = P.lclass[b.j];
+  b.smem = smem;
+  b.tab = smem + GL.s_tab;
+  b.gs = a.grp_scratch + (size_t)group * GL.g_bytes;
+  b.cs = a.grp_cta_scratch + (size_t)block * GL.c_bytes;
+  b.bar = a.grp_bar + (size_t)group * 32;  // one 128-byte line per group
+  b.epoch = 0;
+  b.parity = 0;
+  b.s0 = 0; b.s1 = 1;
+  b.gX = b.cost = b.crY = b.crD = nullptr;
+  b.acc = b.accn = nullptr;
+  b.mvY = b.mvD = nullptr;
+  return b;
+}
+
+#ifndef EPI_HOST_EMU
+// one CTA per SM: the register file divided by the CTA's threads (allocation granularity 8 registers per thread)
+#define EPI_GRP_MAXREG ((65536 / EPI_GRP_THREADS) / 8 * 8 > 255 ? 255 : (65536 / EPI_GRP_THREADS) / 8 * 8)
+__global__ void __maxnreg__(EPI_GRP_MAXREG) grp_kernel(const DevPlan P, const DevState S, const StepArgs a) {
+  extern __shared__ __align__(16) char grp_smem[];
+  Gx b = bind(P, a, grp_smem, threadIdx.x, blockDim.x, blockIdx.x);
+  step_group(P, S, a, b, blockIdx.x / b.S, gridDim.x / b.S);
+}
+#endif
+
+}  // namespace grp
+}  // namespace epi
+#endif  // EPI_SPEC

@@ -728,6 +728,10 @@ struct StepArgs {
   char* small_scratch;    // n_teams * small_bytes when !small_in_smem
   double* dbg_attempts;   // optional [N,64,2]: (h, error_norm) of each attempted RK step of the last day
   double* cr_scratch;     // env kernel: n_ctas * I*L doubles (today's cost rate)
+  // env-group kernel (epi_grp.cuh): per-group scratch, per-CTA scratch, per-group arrive counters (zeroed per launch)
+  char* grp_scratch;
+  char* grp_cta_scratch;
+  unsigned* grp_bar;
 };
 
 // one team, one env at a time: load state, prologue + RK45 for each day, store

@@ -45,6 +45,21 @@ struct EnvLayout {
   int64_t tab_bytes, red_bytes, comm_bytes, big_bytes;
 };
 
+// layout of the env-group kernel (epi_grp.cuh): one env is stepped by a GROUP of S co-resident CTAs, one cell per
+// thread; byte offsets of the [word][thread] columns in shared memory, of the per-env tables, and of the group's
+// global scratch (comm columns, float state copy, last-stage flows, candidate accumulators, reduction partials).
+struct GrpLayout {
+  int enabled, S, n_groups, threads;
+  int lpc;  // locales per CTA (upper bound; CTA c owns locales [c*L/S, (c+1)*L/S))
+  int np;   // doubles per CTA and parity in the reduction-partials array
+  int trow; // row stride (floats) of the mixing tables T[lc][u0][v][u] (F*G padded against bank conflicts)
+  int64_t s_K, s_KS, s_cmB, s_red, s_tab, smem_bytes;
+  int64_t e_mult_y, e_mult_d, e_cpv, e_act, e_expr, e_sel, e_mpy, e_mpg, e_mpt0, e_mpFy, e_mpFg, e_coefS, e_Tnum,
+      e_Tden, e_ft_y, e_ft_gap, tab_bytes;
+  int64_t g_XF, g_cmA, g_cmS, g_fl6, g_accN, g_mvD, g_crD, g_part, g_bytes;  // per group
+  int64_t c_fi_y, c_fi_gap, c_bytes;                                        // per CTA
+};
+
 struct DevPlan {
   // ---- dimensions
   int C, L, G, F, P, I, A, NCP, LG, CLG, nnz, n_lc;
@@ -133,6 +148,7 @@ struct DevPlan {
       o_mvY, o_mvD, o_cost, o_crY, o_crD, o_ysS, o_KS;   // big region (bytes)
   CellLayout cl;
   EnvLayout el;
+  GrpLayout gl;
   int has_src64;  // fp32 mode with move slots: the slots' source compartments are carried in double
 };
 

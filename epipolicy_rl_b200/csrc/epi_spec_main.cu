@@ -6,6 +6,9 @@
 #if EPI_SPEC_BIG
 #include "epi_env.cuh"
 #define EPI_SPEC_KERNEL epi::env::env_kernel<epi::spec::real>
+#if EPI_GRP_THREADS > 0
+#include "epi_grp.cuh"
+#endif
 #elif EPI_SPEC_ROLES > 1
 #include "epi_cellteam.cuh"
 #define EPI_SPEC_KERNEL epi::cteam::cell_team_kernel<epi::spec::real>
@@ -43,4 +46,30 @@ extern "C" int epi_spec_launch(const DevPlan* P, const DevState* S, const epi::S
   kern<<<grid, threads, smem, (cudaStream_t)stream>>>(*P, *S, *a);
   return (int)cudaGetLastError();
 }
+#endif
+
+#if EPI_SPEC_BIG && EPI_GRP_THREADS > 0
+// the env-group kernel (epi_grp.cuh): `grid` = n_groups x S CTAs that must all be resident (they wait on one another)
+#ifdef EPI_HOST_EMU
+extern "C" int epi_spec_launch_grp(const DevPlan* P, const DevState* S, const epi::StepArgs* a, int grid, int threads,
+                                   size_t smem, void*) {
+  const int Sg = P->gl.S, ng = grid / Sg;
+  emu::run_groups(ng, Sg, threads, smem, [&](char* sm, int tid, int block) {
+    epi::grp::Gx b = epi::grp::bind(*P, *a, sm, tid, threads, block);
+    epi::grp::step_group(*P, *S, *a, b, block / Sg, ng);
+  });
+  return 0;
+}
+#else
+extern "C" int epi_spec_launch_grp(const DevPlan* P, const DevState* S, const epi::StepArgs* a, int grid, int threads,
+                                   size_t smem, void* stream) {
+  auto kern = epi::grp::grp_kernel;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  void* args[3] = {(void*)P, (void*)S, (void*)a};
+  e = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(threads), args, smem, (cudaStream_t)stream);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaGetLastError();
+}
+#endif
 #endif

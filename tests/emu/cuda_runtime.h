@@ -25,6 +25,7 @@
 #define __shared__ static
 
 struct EmuDim3 { int x = 0, y = 0, z = 0; };
+struct alignas(16) float4 { float x, y, z, w; };
 static EmuDim3 threadIdx, blockIdx;
 static EmuDim3 blockDim{1, 1, 1}, gridDim{1, 1, 1};
 
@@ -43,10 +44,27 @@ static int warp_width = 1;                                // lanes per emulated 
 static thread_local pthread_barrier_t* warp_barrier = nullptr;
 static thread_local int lane_id = 0;
 static thread_local int* vote_buf = nullptr;
+static thread_local unsigned long long* xchg_buf = nullptr;   // one 8-byte slot per thread of the CTA (shuffles)
+static thread_local pthread_barrier_t* group_barrier = nullptr;  // all threads of a CTA group (epi_grp.cuh)
+inline void group_arrive_wait() { if (group_barrier) pthread_barrier_wait(group_barrier); }
 }  // namespace emu
 inline void __syncwarp() { if (emu::warp_barrier) pthread_barrier_wait(emu::warp_barrier); }
 inline void __syncthreads() { if (emu::warp_barrier) pthread_barrier_wait(emu::warp_barrier); }
-template <class T> inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
+// butterfly exchange inside 32-lane warps of the emulated CTA (all threads of the CTA call it together); threads
+// whose partner lies beyond the CTA keep their own value. Without a lock-stepped CTA: the identity.
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int m) {
+  if (!emu::warp_barrier || !emu::xchg_buf) return v;
+  static_assert(sizeof(T) <= 8, "emulated shuffle: at most 8 bytes");
+  unsigned long long w = 0;
+  memcpy(&w, &v, sizeof(T));
+  emu::xchg_buf[emu::lane_id] = w;
+  pthread_barrier_wait(emu::warp_barrier);
+  const int partner = emu::lane_id ^ m;
+  T r = v;
+  if (partner < emu::warp_width) { unsigned long long x = emu::xchg_buf[partner]; memcpy(&r, &x, sizeof(T)); }
+  pthread_barrier_wait(emu::warp_barrier);
+  return r;
+}
 inline int __any_sync(unsigned, int pred) {
   if (!emu::warp_barrier) return pred;
   emu::vote_buf[emu::lane_id] = pred;
@@ -85,6 +103,44 @@ inline void run_warps(int n_warps, int width, size_t smem_bytes, const std::func
     pthread_barrier_destroy(&bar);
   }
 }
+// run `n_groups` CTA groups one after the other; the S CTAs of a group run TOGETHER, each as `width` lock-stepped host
+// threads with its own shared memory and CTA barrier, plus one barrier over all threads of the group (the group
+// barrier of epi_grp.cuh). body(smem, tid, block) with block = group * S + cta.
+inline void run_groups(int n_groups, int S, int width, size_t smem_bytes, const std::function<void(char*, int, int)>& body) {
+  warp_width = width;
+  for (int g = 0; g < n_groups; g++) {
+    std::vector<std::vector<char>> smem(S, std::vector<char>(smem_bytes + 64, 0));
+    std::vector<std::vector<int>> votes(S, std::vector<int>(width));
+    std::vector<std::vector<unsigned long long>> xch(S, std::vector<unsigned long long>(width));
+    std::vector<pthread_barrier_t> bars(S);
+    pthread_barrier_t gbar;
+    pthread_barrier_init(&gbar, nullptr, (unsigned)(S * width));
+    for (int c = 0; c < S; c++) pthread_barrier_init(&bars[c], nullptr, (unsigned)width);
+    struct Arg { const std::function<void(char*, int, int)>* body; char* smem; int lane, block; pthread_barrier_t *bar, *gbar; int* votes; unsigned long long* xch; };
+    std::vector<Arg> args(S * width);
+    std::vector<pthread_t> th(S * width);
+    pthread_attr_t attr;
+    pthread_attr_init(&attr);
+    pthread_attr_setstacksize(&attr, 1 << 20);
+    for (int c = 0; c < S; c++) {
+      char* base = (char*)(((uintptr_t)smem[c].data() + 15) & ~(uintptr_t)15);
+      for (int l = 0; l < width; l++) {
+        args[c * width + l] = Arg{&body, base, l, g * S + c, &bars[c], &gbar, votes[c].data(), xch[c].data()};
+        pthread_create(&th[c * width + l], &attr, [](void* p) -> void* {
+          Arg* a = (Arg*)p;
+          warp_barrier = a->bar; group_barrier = a->gbar; lane_id = a->lane; vote_buf = a->votes; xchg_buf = a->xch;
+          (*a->body)(a->smem, a->lane, a->block);
+          warp_barrier = nullptr; group_barrier = nullptr; xchg_buf = nullptr;
+          return nullptr;
+        }, &args[c * width + l]);
+      }
+    }
+    for (auto& t : th) pthread_join(t, nullptr);
+    pthread_attr_destroy(&attr);
+    for (int c = 0; c < S; c++) pthread_barrier_destroy(&bars[c]);
+    pthread_barrier_destroy(&gbar);
+  }
+}
 }  // namespace emu
 
 typedef int cudaError_t;
@@ -92,7 +148,7 @@ typedef void* cudaStream_t;
 enum { cudaSuccess = 0 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
 enum { cudaStreamNonBlocking = 1, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
-struct cudaDeviceProp { size_t sharedMemPerBlockOptin = 232448, sharedMemPerMultiprocessor = 233472; int multiProcessorCount = 148; };
+struct cudaDeviceProp { size_t sharedMemPerBlockOptin = 232448, sharedMemPerMultiprocessor = 233472; int multiProcessorCount = 148; int cooperativeLaunch = 1; };
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) { *p = (T*)calloc(n ? n : 1, 1); return *p ? 0 : 2; }
 template <class T> inline cudaError_t cudaMallocHost(T** p, size_t n) { *p = (T*)calloc(n ? n : 1, 1); return *p ? 0 : 2; }
@@ -104,6 +160,7 @@ inline cudaError_t cudaFreeHost(void* p) { free(p); return 0; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return 0; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return 0; }
 inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return 0; }
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return 0; }
 inline cudaError_t cudaSetDevice(int) { return 0; }
 inline cudaError_t cudaDeviceSynchronize() { return 0; }
 inline cudaError_t cudaGetLastError() { return 0; }
