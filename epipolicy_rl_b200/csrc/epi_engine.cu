@@ -12,6 +12,7 @@
 
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <functional>
 #include <map>
 #include <sstream>
@@ -49,6 +50,7 @@ struct HostTabs {
   std::vector<int> ig_c0, ig_w_off, ig_w_c2, ep_off, ep, xg_off, xg_src, ag_off, ag_src;
   std::vector<float> ep_coef, xg_coef, ag_coef;
   std::vector<int> comp_role;
+  std::vector<int> csr_indptr, csc_indptr;
   // prologue tables for the generator
   std::vector<uint8_t> sel_c, sel_l, sel_g;
   std::vector<int> sel_mode, chg_slot, selc_off, selc, cls_off, cls_op, op_expr, expr_off, tok_op, tok_arg, tok_f32;
@@ -581,6 +583,13 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
     P.Tden_constT = h->up(tdT); P.Tden_const64T = h->up(td64T);
   }
   P.Tden_const = h->up(tden); P.Tden_const64 = h->up(tden64); P.mx_csr = h->up(mx_csr); P.mx_csc = h->up(mx_csc);
+  {
+    std::vector<float> tr((size_t)G * d.nnz), tc((size_t)G * d.nnz);
+    for (int g = 0; g < G; g++)
+      for (int k = 0; k < d.nnz; k++) { tr[(size_t)k * G + g] = mx_csr[(size_t)g * d.nnz + k]; tc[(size_t)k * G + g] = mx_csc[(size_t)g * d.nnz + k]; }
+    P.mx_csrT = h->up(tr); P.mx_cscT = h->up(tc);
+    h->tabs.csr_indptr = vec(d.csr_indptr, (size_t)L + 1); h->tabs.csc_indptr = vec(d.csc_indptr, (size_t)L + 1);
+  }
   P.mob_dense_csc = dense_csc.empty() ? nullptr : h->up(dense_csc);
   P.mob_dense_csr = dense_csr.empty() ? nullptr : h->up(dense_csr);
   P.csr_indptr = h->up(vec(d.csr_indptr, L + 1)); P.csr_indices = h->up(vec(d.csr_indices, d.nnz));
@@ -729,6 +738,15 @@ void build_grp_layout(epi_engine* h, int sms, int64_t smem_max) {
     Y.np = P.n_sel + P.n_mv_op > 2 ? P.n_sel + P.n_mv_op : 2;
     Y.s_K = take(rs * 6 * C * threads); Y.s_KS = take(8 * 6 * nS * threads); Y.s_cmB = take(rs * (1 + NG) * threads);
     Y.s_red = take(8 * (32 + (int64_t)(2 * S > P.n_mv_op ? 2 * S : P.n_mv_op)));
+    // the CSC / CSR index lists of the CTA's locales (static: loaded once per kernel)
+    Y.cap_csc = Y.cap_csr = 0;
+    for (int c = 0; c < S; c++) {
+      const int l0 = (int)(((int64_t)c * P.L) / S), l1 = (int)(((int64_t)(c + 1) * P.L) / S);
+      Y.cap_csc = std::max(Y.cap_csc, h->tabs.csc_indptr[l1] - h->tabs.csc_indptr[l0]);
+      Y.cap_csr = std::max(Y.cap_csr, h->tabs.csr_indptr[l1] - h->tabs.csr_indptr[l0]);
+    }
+    Y.s_cscp = take(4 * ((int64_t)lpc + 1)); Y.s_csci = take(4 * (int64_t)Y.cap_csc);
+    Y.s_csrp = take(4 * ((int64_t)lpc + 1)); Y.s_csri = take(4 * (int64_t)Y.cap_csr);
     Y.s_tab = o;
     o = 0;
     Y.e_mult_y = take(4 * (int64_t)P.n_cls); Y.e_mult_d = take(4 * (int64_t)P.n_cls);
@@ -1041,7 +1059,8 @@ std::string gen_spec(const epi_engine* h) {
     // ---- the same program for the env-group kernel (epi_grp.cuh): the flow sums FB += bw f, FE += ew f live in
     // registers; `st`: the flows are also stored (last stage of an attempt)
     o << "constexpr int grp_threads = " << P.gl.threads << ", grp_S = " << P.gl.S << ", grp_groups = " << P.gl.n_groups << ";\n";
-    o << "__device__ __forceinline__ void flows_acc(const real* y, real alive, const float* mp, const real* rs, real* d, real* FB, real* FE, real bw, real ew, real* out, size_t stride, bool st) {\n";
+    // regular edges (need the cell's own state only: they run while the group barrier of the gathers is pending)
+    o << "__device__ __forceinline__ void flows_reg(const real* y, real alive, const float* mp, real* d, real* FB, real* FE, real bw, real ew, real* out, size_t stride, bool st) {\n";
     for (int c = 0; c < P.C; c++) o << "  d[" << c << "] = 0;\n";
     if (h->precision == EPI_FP32) {
       for (auto& dc : rdecl) o << "  real " << dc.first << "; { real dn = 0;" << dc.second << " " << dc.first << " = frcp(dn); }\n";
@@ -1050,12 +1069,6 @@ std::string gen_spec(const epi_engine* h) {
     auto sums = [&](int src) {
       o << " FB[" << src << "] += bw * f; FE[" << src << "] += ew * f; if (st) out[" << src << " * stride] = f;";
     };
-    for (int k = 0; k < P.NG; k++) {
-      o << "  { real f = y[" << T.ig_c0[k] << "] * rs[" << k << "];";
-      sums(P.E + k);
-      scatter(P.E + k);
-      o << " }\n";
-    }
     for (int e = 0; e < P.E; e++) {
       const int* ep = T.ep.data() + T.ep_off[e];
       int n = *ep++;
@@ -1069,6 +1082,15 @@ std::string gen_spec(const epi_engine* h) {
       o << " }\n";
     }
     rcp_of = nullptr;
+    o << "}\n";
+    // infectious groups: yc[k] = the susceptible compartment of group k, rs[k] = its gathered force of infection
+    o << "__device__ __forceinline__ void flows_inf(const real* yc, const real* rs, real* d, real* FB, real* FE, real bw, real ew, real* out, size_t stride, bool st) {\n";
+    for (int k = 0; k < P.NG; k++) {
+      o << "  { real f = yc[" << k << "] * rs[" << k << "];";
+      sums(P.E + k);
+      scatter(P.E + k);
+      o << " }\n";
+    }
     o << "}\n";
     arr("ag_off", T.ag_off); arr("ag_src", T.ag_src);
     o << "__device__ constexpr float ag_coef[" << (T.ag_coef.empty() ? 1 : T.ag_coef.size()) << "] = {";
@@ -1190,7 +1212,7 @@ std::string gen_spec(const epi_engine* h) {
   uint64_t k = 1469598103934665603ull;
   auto mix = [&](const void* p, size_t n) { for (size_t i = 0; i < n; i++) { k ^= ((const unsigned char*)p)[i]; k *= 1099511628211ull; } };
   mix(body.data(), body.size());
-  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 24 /* generator revision */};
+  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 25 /* generator revision */};
   mix(abi, sizeof abi);
   char kb[32];
   snprintf(kb, sizeof kb, "%016llx", (unsigned long long)k);

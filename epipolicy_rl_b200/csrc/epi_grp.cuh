@@ -101,24 +101,30 @@ __device__ __forceinline__ void grp_sync(Gx& b) {
   grp_wait(b);
 }
 
-// block sum (warp shuffles, then the warp partials in fixed order); every thread receives the bit-identical result
-__device__ __forceinline__ double block_sum(const DevPlan& P, const Gx& b, double v) {
+// butterfly over the warp: every lane ends with the same bits (each level adds the same two values, a + b == b + a)
+__device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block sum: warp butterflies, then every warp adds the warp partials the same way; every thread receives the
+// bit-identical result
+__device__ __forceinline__ double block_sum(const DevPlan& P, const Gx& b, double v) {
+  v = warp_sum(v);
   double* red = (double*)(b.smem + GL.s_red);
-  const int w = b.tid >> 5;
   constexpr int nw = GTH >> 5;
-  if ((b.tid & 31) == 0) red[w] = v;
+  if ((b.tid & 31) == 0) red[b.tid >> 5] = v;
   __syncthreads();
-  double r = 0;
-#pragma unroll 1
-  for (int i = 0; i < nw; i++) r += red[i];
+  const int lane = b.tid & 31;
+  double r = lane < nw ? red[lane] : 0.0;
+  r = warp_sum(r);
   __syncthreads();
   return r;
 }
 
-// group sum of n <= 2 values: block sums -> partials in the group scratch -> barrier -> every CTA adds the S partials
-// in the same order (so every thread of the group holds the same bits)
+// group sum of n <= 2 values: block sums -> partials in the group scratch -> barrier -> every warp of every CTA adds
+// the S partials the same way (so every thread of the group holds the same bits and takes the same decision)
 template <int n>
 __device__ __forceinline__ void grp_sum(const DevPlan& P, Gx& b, double (&v)[n]) {
   double* part = (double*)(b.gs + GL.g_part) + (size_t)b.parity * GSS * GL.np;
@@ -129,17 +135,15 @@ __device__ __forceinline__ void grp_sum(const DevPlan& P, Gx& b, double (&v)[n])
     for (int i = 0; i < n; i++) part[(size_t)b.cta * GL.np + i] = v[i];
   }
   grp_sync(b);
-  double* st = (double*)(b.smem + GL.s_red) + 32;
-  for (int q = b.tid; q < GSS * n; q += GTH) st[q] = ldcg(part + (size_t)(q / n) * GL.np + (q % n));
-  __syncthreads();
+  const int lane = b.tid & 31;
 #pragma unroll
   for (int i = 0; i < n; i++) {
     double r = 0;
-#pragma unroll 1
-    for (int c = 0; c < GSS; c++) r += st[c * n + i];
-    v[i] = r;
+#pragma unroll
+    for (int c0 = 0; c0 < GSS; c0 += 32)
+      if (c0 + lane < GSS) r += ldcg(part + (size_t)(c0 + lane) * GL.np + i);
+    v[i] = warp_sum(r);
   }
-  __syncthreads();
   b.parity ^= 1;
 }
 
@@ -180,15 +184,14 @@ __device__ __forceinline__ void fill_tables(const DevPlan& P, const Gx& b, float
 }
 
 // ------------------------------------------------------------------------------------------
-// one right-hand-side evaluation (core_optimize.py:165-222). Stage input y = XF + hh * sum_{j<nj} co[j] K_j is
-// formed here and stays in registers; FB += bw * f, FE += ew * f for every flow f of the evaluation; `st6`: the
-// flows are also stored (last stage of an attempt / f(0, y0): they open the next attempt, first-same-as-last).
+// one right-hand-side evaluation (core_optimize.py:165-222). Stage input y = XF + hh * sum_{j<nj} co[j] K_j;
+// FB += bw * f, FE += ew * f for every flow f of the evaluation; `st6`: the flows are also stored (last stage of an
+// attempt: they open the next attempt, first-same-as-last).
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void rhs(const DevPlan& P, Gx& b, bool dyn, double t, int ex_bits, int phase, int stage, real bw,
-                                    real ew, bool st6, double hh, int nj, real (&y)[spec::C], real (&FB)[spec::NSRC],
-                                    real (&FE)[spec::NSRC]) {
-  constexpr int G = spec::G, F = spec::F, LG = spec::LG, nnz = spec::nnz, NG = spec::NG, n_lc = spec::n_lc, PP = spec::P,
-                C = spec::C, nE = spec::E, nS = spec::has_src64 ? spec::n_slot : 0;
+                                    real ew, bool st6, double hh, int nj, real (&FB)[spec::NSRC], real (&FE)[spec::NSRC]) {
+  constexpr int G = spec::G, F = spec::F, LG = spec::LG, NG = spec::NG, n_lc = spec::n_lc, PP = spec::P, C = spec::C,
+                nE = spec::E, nS = spec::has_src64 ? spec::n_slot : 0;
   const float tf = (float)t;
   const float qf = (float)((-3.0 * t + 4.0) * t);  // utility/utils.py:34-37, rounded like parameter.py:83
   if (dyn) {
@@ -197,9 +200,13 @@ __device__ __forceinline__ void rhs(const DevPlan& P, Gx& b, bool dyn, double t,
     __syncthreads();
   }
   const int kslot = stage == 0 ? b.s0 : (stage == 1 || stage == 6) ? b.s1 : stage;
-  real alive = 0;
+  real* out = (real*)(b.gs + GL.g_fl6) + b.cell;
+  real d[C];
+  real yc[NG > 0 ? NG : 1];                          // the susceptible compartments of the infectious groups
+  real y1[spec::n_slot > 0 ? spec::n_slot : 1], y2[spec::n_slot > 0 ? spec::n_slot : 1];  // move slots: source, target
   double ysS[nS > 0 ? nS : 1];
   // ---- pass 1: stage input, alive (N excludes death and hospitalized, :28-41,:168), weighted infectious sums
+  real y[C], alive = 0;
   if (b.valid) {
 #pragma unroll
     for (int k = 0; k < C; k++) y[k] = 0;
@@ -225,30 +232,60 @@ __device__ __forceinline__ void rhs(const DevPlan& P, Gx& b, bool dyn, double t,
     GCOL(GL.g_cmA, real, 0) = alive;
 #pragma unroll
     for (int k = 0; k < NG; k++) GCOL(GL.g_cmA, real, 1 + k) = xw[k];
-    // the stage input waits in the slot this evaluation will fill (its old content is dead): 15 registers less while
-    // the gathers and the mixing run
+  }
+  if (NG > 0) grp_arrive(b);
+  if (b.valid) {
+    // ---- the regular edges need the cell's own state only: they run while the other CTAs arrive. Their share of dX
+    // waits in the slot this evaluation will fill (its old content is dead), so that the gathers and the mixing run
+    // with the flow sums as the only long-lived registers
+    const float* mp = &GT(mpt0, b.lc * PP * G + b.u);  // parameters from facility 0 only (:48)
+    spec::flows_reg(y, alive, mp, d, FB, FE, bw, ew, out, (size_t)LG, st6);
+#pragma unroll
+    for (int k = 0; k < NG; k++) yc[k] = y[spec::ig_c0[k]];
+#pragma unroll
+    for (int sl = 0; sl < spec::n_slot; sl++) { y1[sl] = y[spec::slot_c1[sl]]; y2[sl] = y[spec::slot_c2[sl]]; }
     if (NG > 0) {
 #pragma unroll
-      for (int k = 0; k < C; k++) SK(kslot, k) = y[k];
+      for (int k = 0; k < C; k++) SK(kslot, k) = d[k];
     }
   }
-  real rs[NG > 0 ? NG : 1];
-#pragma unroll
-  for (int k = 0; k < NG; k++) rs[k] = 0;
   if (NG > 0) {
-    grp_sync(b);
-    // ---- pass 2: CSC gather over source locales (compute_foi_entry inner loop, :105-111) -> shared memory
+    real rs[NG];
+#pragma unroll
+    for (int k = 0; k < NG; k++) rs[k] = 0;
+    grp_wait(b);
+    // ---- pass 2: CSC gather over source locales (compute_foi_entry inner loop, :105-111) -> shared memory.
+    // Index lists from shared memory; four entries at a time: their values and gathered columns are in flight together
     if (b.valid) {
-      real a = 0, xs[NG > 0 ? NG : 1];
+      real a = 0, xs[NG];
 #pragma unroll
       for (int k = 0; k < NG; k++) xs[k] = 0;
       const real* cmA = (const real*)(b.gs + GL.g_cmA);
-      for (int q = __ldg(P.csc_indptr + b.j); q < __ldg(P.csc_indptr + b.j + 1); q++) {
-        const int src = __ldg(P.csc_indices + q) * G + b.u;
-        const real val = (real)__ldg(P.mx_csc + (size_t)b.u * nnz + q);
-        a += ldcg(cmA + src) * val;
+      const int* cp = (const int*)(b.smem + GL.s_cscp);
+      const int* ci = (const int*)(b.smem + GL.s_csci);
+      const int jl = b.j - b.l0, qb = cp[jl], qe = cp[jl + 1];
+      const float* vp = P.mx_cscT + (size_t)__ldg(P.csc_indptr + b.l0) * G + b.u;
+#pragma unroll 1
+      for (int q0 = qb; q0 < qe; q0 += 4) {
+        int src[4];
+        real val[4], g[4][1 + NG];
 #pragma unroll
-        for (int k = 0; k < NG; k++) xs[k] += ldcg(cmA + (size_t)(1 + k) * LG + src) * val;
+        for (int i = 0; i < 4; i++) {
+          const bool on = q0 + i < qe;
+          const int q = on ? q0 + i : qb;
+          src[i] = ci[q] * G + b.u;
+          val[i] = on ? (real)__ldg(vp + (size_t)q * G) : (real)0;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int k = 0; k < 1 + NG; k++) g[i][k] = ldcg(cmA + (size_t)k * LG + src[i]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          a += g[i][0] * val[i];
+#pragma unroll
+          for (int k = 0; k < NG; k++) xs[k] += g[i][1 + k] * val[i];
+        }
       }
       SCMB(0, b.tid) = a;
 #pragma unroll
@@ -257,86 +294,104 @@ __device__ __forceinline__ void rhs(const DevPlan& P, Gx& b, bool dyn, double t,
     __syncthreads();
     // ---- pass 3: G x G facility mixing -> force of infection -> s[k] for (j, u0)  (:112-124, :146-157)
     if (b.valid) {
-      real sk[NG > 0 ? NG : 1];
+      real sk[NG];
 #pragma unroll
       for (int k = 0; k < NG; k++) sk[k] = 0;
       const int row = b.tid - b.u;  // the locale's first column
       const float* Tn = &GT(Tnum, (b.lc * G + b.u) * GL.trow);
       const real* Td = &GT(Tden, (b.lc * G + b.u) * GL.trow);
-      real den[F], num[NG > 0 ? NG : 1][F];
-#pragma unroll
-      for (int v = 0; v < F; v++) {
-        den[v] = 0;
-#pragma unroll
-        for (int k = 0; k < NG; k++) num[k][v] = 0;
-      }
-      if (G % 4 == 0) {
-        // four groups of the locale at a time: their gathered columns in registers (128-bit broadcast reads), against
-        // the F rows of the cell's tables (128-bit reads, conflict-free over the locale's groups)
+      constexpr int VH = (F % 4 == 0 && G % 4 == 0) ? 4 : 1;  // facilities per sweep over the locale's groups
 #pragma unroll 1
-        for (int u4 = 0; u4 < G / 4; u4++) {
-          float4 c4[1 + NG];
+      for (int v0 = 0; v0 < F; v0 += VH) {
+        real den[VH], num[NG][VH];
 #pragma unroll
-          for (int k = 0; k < 1 + NG; k++) c4[k] = *(const float4*)&SCMB(k, row + 4 * u4);
+        for (int v = 0; v < VH; v++) {
+          den[v] = 0;
 #pragma unroll
-          for (int v = 0; v < F; v++) {
-            const float4 tn = *(const float4*)(Tn + v * G + 4 * u4);
-            const float4 td = *(const float4*)(Td + v * G + 4 * u4);
-            den[v] += c4[0].x * td.x; den[v] += c4[0].y * td.y; den[v] += c4[0].z * td.z; den[v] += c4[0].w * td.w;
+          for (int k = 0; k < NG; k++) num[k][v] = 0;
+        }
+        if (G % 4 == 0) {
+          // four groups of the locale at a time: their gathered columns in registers (128-bit broadcast reads),
+          // against VH rows of the cell's tables (128-bit reads, conflict-free over the locale's groups)
+#pragma unroll 1
+          for (int u4 = 0; u4 < G / 4; u4++) {
+            float4 c4[1 + NG];
 #pragma unroll
-            for (int k = 0; k < NG; k++) {
-              num[k][v] += c4[1 + k].x * tn.x; num[k][v] += c4[1 + k].y * tn.y;
-              num[k][v] += c4[1 + k].z * tn.z; num[k][v] += c4[1 + k].w * tn.w;
+            for (int k = 0; k < 1 + NG; k++) c4[k] = *(const float4*)&SCMB(k, row + 4 * u4);
+#pragma unroll
+            for (int v = 0; v < VH; v++) {
+              const float4 tn = *(const float4*)(Tn + (v0 + v) * G + 4 * u4);
+              const float4 td = *(const float4*)(Td + (v0 + v) * G + 4 * u4);
+              den[v] += c4[0].x * td.x; den[v] += c4[0].y * td.y; den[v] += c4[0].z * td.z; den[v] += c4[0].w * td.w;
+#pragma unroll
+              for (int k = 0; k < NG; k++) {
+                num[k][v] += c4[1 + k].x * tn.x; num[k][v] += c4[1 + k].y * tn.y;
+                num[k][v] += c4[1 + k].z * tn.z; num[k][v] += c4[1 + k].w * tn.w;
+              }
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int u = 0; u < G; u++) {
+            real c1[1 + NG];
+#pragma unroll
+            for (int k = 0; k < 1 + NG; k++) c1[k] = SCMB(k, row + u);
+#pragma unroll
+            for (int v = 0; v < VH; v++) {
+              den[v] += c1[0] * Td[(v0 + v) * G + u];
+#pragma unroll
+              for (int k = 0; k < NG; k++) num[k][v] += c1[1 + k] * (real)Tn[(v0 + v) * G + u];
             }
           }
         }
-      } else {
-#pragma unroll 1
-        for (int u = 0; u < G; u++) {
-          real c1[1 + NG];
 #pragma unroll
-          for (int k = 0; k < 1 + NG; k++) c1[k] = SCMB(k, row + u);
+        for (int v = 0; v < VH; v++) {
+          real dn = den[v];
+          if (dn <= (real)1e-15) dn = 1;
+          const real rden = frcp(dn);
 #pragma unroll
-          for (int v = 0; v < F; v++) {
-            den[v] += c1[0] * Td[v * G + u];
-#pragma unroll
-            for (int k = 0; k < NG; k++) num[k][v] += c1[1 + k] * (real)Tn[v * G + u];
-          }
+          for (int k = 0; k < NG; k++)
+            sk[k] += GT(coefS, ((k * n_lc + b.lc) * F + v0 + v) * G + b.u) * (num[k][v] * rden);
         }
-      }
-#pragma unroll
-      for (int v = 0; v < F; v++) {
-        real dn = den[v];
-        if (dn <= (real)1e-15) dn = 1;
-        const real rden = frcp(dn);
-#pragma unroll
-        for (int k = 0; k < NG; k++) sk[k] += GT(coefS, ((k * n_lc + b.lc) * F + v) * G + b.u) * (num[k][v] * rden);
       }
 #pragma unroll
       for (int k = 0; k < NG; k++) GCOL(GL.g_cmS, real, k) = sk[k];
     }
     grp_sync(b);
-    // ---- pass 4a: CSR gather over destination locales (:144-158)
+    // ---- pass 4a: CSR gather over destination locales (:144-158), then the infectious flows
     if (b.valid) {
       const real* cmS = (const real*)(b.gs + GL.g_cmS);
-      for (int q = __ldg(P.csr_indptr + b.j); q < __ldg(P.csr_indptr + b.j + 1); q++) {
-        const int dst = __ldg(P.csr_indices + q) * G + b.u;
-        const real val = (real)__ldg(P.mx_csr + (size_t)b.u * nnz + q);
+      const int* cp = (const int*)(b.smem + GL.s_csrp);
+      const int* ci = (const int*)(b.smem + GL.s_csri);
+      const int jl = b.j - b.l0, qb = cp[jl], qe = cp[jl + 1];
+      const float* vp = P.mx_csrT + (size_t)__ldg(P.csr_indptr + b.l0) * G + b.u;
+#pragma unroll 1
+      for (int q0 = qb; q0 < qe; q0 += 4) {
+        int dst[4];
+        real val[4], g[4][NG];
 #pragma unroll
-        for (int k = 0; k < NG; k++) rs[k] += ldcg(cmS + (size_t)k * LG + dst) * val;
+        for (int i = 0; i < 4; i++) {
+          const bool on = q0 + i < qe;
+          const int q = on ? q0 + i : qb;
+          dst[i] = ci[q] * G + b.u;
+          val[i] = on ? (real)__ldg(vp + (size_t)q * G) : (real)0;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int k = 0; k < NG; k++) g[i][k] = ldcg(cmS + (size_t)k * LG + dst[i]);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int k = 0; k < NG; k++) rs[k] += g[i][k] * val[i];
       }
+#pragma unroll
+      for (int k = 0; k < C; k++) d[k] = SK(kslot, k);
+      spec::flows_inf(yc, rs, d, FB, FE, bw, ew, out, (size_t)LG, st6);
     }
   }
-  // ---- pass 4b: edges, scatter into dX, clamped moves, flow sums
+  // ---- pass 4b: clamped moves, the stage derivative
   if (b.valid) {
-    const float* mp = &GT(mpt0, b.lc * PP * G + b.u);  // parameters from facility 0 only (:48)
-    if (NG > 0) {
-#pragma unroll
-      for (int k = 0; k < C; k++) y[k] = SK(kslot, k);
-    }
-    real d[C];
-    real* out = (real*)(b.gs + GL.g_fl6) + b.cell;
-    spec::flows_acc(y, alive, mp, rs, d, FB, FE, bw, ew, out, (size_t)LG, st6);
 #pragma unroll
     for (int sl = 0; sl < spec::n_slot; sl++) {
       real nv = 0;
@@ -345,12 +400,12 @@ __device__ __forceinline__ void rhs(const DevPlan& P, Gx& b, bool dyn, double t,
         float my = ((ex_bits >> sl) & 1) ? b.mvY[(size_t)sl * LG + b.cell] : 0.0f;
         float md = ((ex_bits >> (16 + sl)) & 1) ? b.mvD[(size_t)sl * LG + b.cell] : 0.0f;
         float v = __fadd_rn(__fmul_rn(__fsub_rn(md, my), qf), my);  // coo.py scale/add in f32
-        double y1 = spec::has_src64 ? ysS[sl] : (double)y[c1], y2 = (double)y[c2];
-        double n1 = y1 + (double)d[c1], n2 = y2 + (double)d[c2];
+        double ya = spec::has_src64 ? ysS[sl] : (double)y1[sl], yb = (double)y2[sl];
+        double n1 = ya + (double)d[c1], n2 = yb + (double)d[c2];
         double nvd = (double)v < n1 ? (double)v : n1;
-        double k1 = (n1 - nvd) - y1;
+        double k1 = (n1 - nvd) - ya;
         d[c1] = (real)k1;
-        d[c2] = (real)((n2 + nvd) - y2);
+        d[c2] = (real)((n2 + nvd) - yb);
         nv = (real)nvd;
         if (spec::has_src64) SKS(kslot, sl) = k1;
       } else if (spec::has_src64) {
@@ -570,9 +625,6 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, Gx& b, bool dyn, int 
   bool run = true, rejected = false;
   auto qd = [](double tt) { return (double)(float)((-3.0 * tt + 4.0) * tt); };
   auto centry = [&](int q) { return (size_t)(q / b.nl) * L + b.l0 + q % b.nl; };
-  real y[C];
-#pragma unroll
-  for (int k = 0; k < C; k++) y[k] = 0;
   // the packed flow sums of the current attempt live in registers for the whole day
   real FB[NSRC], FE[NSRC];
 #pragma unroll
@@ -623,7 +675,7 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, Gx& b, bool dyn, int 
         for (int i = 0; i < NSRC; i++) FE[i] = fl6[(size_t)i * LG];
       }
     } else {
-      rhs(P, b, dyn, t_eval, ex_bits, phase, stage, bw, ew, phase == 7, hh, nj, y, FB, FE);
+      rhs(P, b, dyn, t_eval, ex_bits, phase, stage, bw, ew, phase == 7, hh, nj, FB, FE);
     }
     if (phase == 0) {
       // select_initial_step (common.py:68-134), first half
@@ -712,8 +764,6 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, Gx& b, bool dyn, int 
         real ae = 0;
 #pragma unroll
         for (int k = 0; k < C; k++) {
-          // y[k] is the input of stage 6 = the 5th-order candidate y_new
-          real sc = atolr + fmax(fabs(GXF(k)), fabs(y[k])) * rtolr;
           real e = 0, inc = 0;
 #pragma unroll
           for (int j = 0; j < 7; j++) {
@@ -723,6 +773,9 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, Gx& b, bool dyn, int 
             if (j < 6) inc += kj * rkB(real(0), j);
           }
           dy[k] = inc;
+          // the 5th-order candidate y_new (= the input stage 6 was evaluated at)
+          const real xf = GXF(k), yn = inc * (real)h + xf;
+          real sc = atolr + fmax(fabs(xf), fabs(yn)) * rtolr;
           real a = fdiv(e * (real)h, sc);
           ae += a * a;
         }
@@ -849,6 +902,15 @@ __device__ __forceinline__ void step_group(const DevPlan& P, const DevState& S, 
       GT(Tden, (lc * G + u0) * GL.trow + v * G + u) = (real)__ldg(P.Tden_constT + i);
     }
   }
+  {
+    // the CSC / CSR index lists of this CTA's locales (static), offsets relative to the first locale's row
+    int* cp = (int*)(b.smem + GL.s_cscp); int* ci = (int*)(b.smem + GL.s_csci);
+    int* rp = (int*)(b.smem + GL.s_csrp); int* ri = (int*)(b.smem + GL.s_csri);
+    const int cb = P.csc_indptr[b.l0], rb = P.csr_indptr[b.l0];
+    for (int i = b.tid; i <= b.nl; i += b.T) { cp[i] = P.csc_indptr[b.l0 + i] - cb; rp[i] = P.csr_indptr[b.l0 + i] - rb; }
+    for (int i = b.tid; i < P.csc_indptr[b.l0 + b.nl] - cb; i += b.T) ci[i] = P.csc_indices[cb + i];
+    for (int i = b.tid; i < P.csr_indptr[b.l0 + b.nl] - rb; i += b.T) ri[i] = P.csr_indices[rb + i];
+  }
   b.crD = (double*)(b.gs + GL.g_crD);
   b.mvD = (float*)(b.gs + GL.g_mvD);
   for (int env = group; env < a.N; env += n_groups) {
@@ -965,8 +1027,11 @@ __device__ __forceinline__ Gx bind(const DevPlan& P, const StepArgs& a, char* sm
 }
 
 #ifndef EPI_HOST_EMU
-// one CTA per SM: the register file divided by the CTA's threads (allocation granularity 8 registers per thread)
-#define EPI_GRP_MAXREG ((65536 / EPI_GRP_THREADS) / 8 * 8 > 255 ? 255 : (65536 / EPI_GRP_THREADS) / 8 * 8)
+// one CTA per SM. The register file is four 16 K-register partitions, one per scheduler, and a CTA's warps are dealt
+// round-robin to them: registers per thread <= 16384 / (32 * ceil(warps / 4))  (448 threads -> 128; a kernel compiled
+// for 144 cannot be resident at all, which a cooperative launch reports as "too many blocks")
+#define EPI_GRP_MAXREG_RAW (16384 / (32 * ((EPI_GRP_THREADS / 32 + 3) / 4)) / 8 * 8)
+#define EPI_GRP_MAXREG (EPI_GRP_MAXREG_RAW > 255 ? 255 : EPI_GRP_MAXREG_RAW)
 __global__ void __maxnreg__(EPI_GRP_MAXREG) grp_kernel(const DevPlan P, const DevState S, const StepArgs a) {
   extern __shared__ __align__(16) char grp_smem[];
   Gx b = bind(P, a, grp_smem, threadIdx.x, blockDim.x, blockIdx.x);

@@ -53,7 +53,8 @@ struct GrpLayout {
   int lpc;  // locales per CTA (upper bound; CTA c owns locales [c*L/S, (c+1)*L/S))
   int np;   // doubles per CTA and parity in the reduction-partials array
   int trow; // row stride (floats) of the mixing tables T[lc][u0][v][u] (F*G padded against bank conflicts)
-  int64_t s_K, s_KS, s_cmB, s_red, s_tab, smem_bytes;
+  int64_t s_K, s_KS, s_cmB, s_red, s_cscp, s_csci, s_csrp, s_csri, s_tab, smem_bytes;
+  int cap_csc, cap_csr;  // most CSC / CSR entries any CTA's locales own
   int64_t e_mult_y, e_mult_d, e_cpv, e_act, e_expr, e_sel, e_mpy, e_mpg, e_mpt0, e_mpFy, e_mpFg, e_coefS, e_Tnum,
       e_Tden, e_ft_y, e_ft_gap, tab_bytes;
   int64_t g_XF, g_cmA, g_cmS, g_fl6, g_accN, g_mvD, g_crD, g_part, g_bytes;  // per group
@@ -90,6 +91,7 @@ struct DevPlan {
   const float* mx_csr;       // [G,nnz] combined mobility on the union pattern (core_optimize.py:69-92)
   const float* mx_csc;       // [G,nnz]
   const float *mob_dense_csc, *mob_dense_csr; // [LG,L] dense column / row of every cell when L <= 4 (else null)
+  const float *mx_csrT, *mx_cscT;             // [nnz,G] the same values, groups fastest (env-group kernel: a locale's lanes read one line)
   const int *csr_indptr, *csr_indices, *csc_indptr, *csc_indices;
   // ---- multiplier classes
   const int* cls_off;        // [n_cls+1]
