@@ -581,6 +581,12 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
       td64T[((size_t)lv * G + u) * G + u0] = tden64[((size_t)lv * G + u0) * G + u];
     }
     P.Tden_constT = h->up(tdT); P.Tden_const64T = h->up(td64T);
+    // padded rows for the env-group kernel: row (lc, u0) holds element (v, u) at v*G + u, F*G + 4 floats per row
+    const size_t trow = (size_t)F * G + 4;
+    std::vector<float> tdP((size_t)n_lc * G * trow, 0.0f);
+    for (int lc = 0; lc < n_lc; lc++) for (int v = 0; v < F; v++) for (int u0 = 0; u0 < G; u0++) for (int u = 0; u < G; u++)
+      tdP[((size_t)lc * G + u0) * trow + (size_t)v * G + u] = tden[((((size_t)lc * F + v) * G) + u0) * G + u];
+    P.Tden_constP = h->up(tdP);
   }
   P.Tden_const = h->up(tden); P.Tden_const64 = h->up(tden64); P.mx_csr = h->up(mx_csr); P.mx_csc = h->up(mx_csc);
   {
@@ -727,17 +733,21 @@ void build_grp_layout(epi_engine* h, int sms, int64_t smem_max) {
   const int64_t rs = 4, C = P.C, G = P.G, F = P.F, n_lc = P.n_lc, NG = P.NG;
   const int64_t nS = P.has_src64 ? P.n_slot : 0;
   const int forceS = getenv("EPI_GRP_S") ? atoi(getenv("EPI_GRP_S")) : 0;
-  // shared-memory layout of a CTA for groups of S CTAs; false if it does not fit
-  auto layout = [&](int S) {
+  const int forceR = getenv("EPI_GRP_R") ? atoi(getenv("EPI_GRP_R")) : 0;
+  const int maxw = getenv("EPI_GRP_WARPS") ? atoi(getenv("EPI_GRP_WARPS")) : 16;  // resident warps per SM
+  // shared-memory layout of a CTA for groups of S CTAs, R CTAs per SM; false if it does not fit
+  auto layout = [&](int S, int R) {
     const int lpc = (P.L + S - 1) / S;
     const int threads = (int)(((int64_t)lpc * G + 31) / 32 * 32);
-    if (threads > 512) return false;
+    // registers: the SM's warps are dealt to four 16 K-register partitions; 16 warps per SM leave 128 registers per
+    // thread, 12 warps 168 (the kernel keeps 70 flow sums per cell in registers)
+    if (R * (threads / 32) > maxw) return false;
     int64_t o = 0;
     auto take = [&](int64_t bytes) { int64_t r = o; o = align16(o + bytes); return r; };
     Y.trow = (int)(F * G + 4);
     Y.np = P.n_sel + P.n_mv_op > 2 ? P.n_sel + P.n_mv_op : 2;
     Y.s_K = take(rs * 6 * C * threads); Y.s_KS = take(8 * 6 * nS * threads); Y.s_cmB = take(rs * (1 + NG) * threads);
-    Y.s_red = take(8 * (32 + (int64_t)(2 * S > P.n_mv_op ? 2 * S : P.n_mv_op)));
+    Y.s_red = take(8 * (32 + (int64_t)(P.n_mv_op > 2 ? P.n_mv_op : 2)));
     // the CSC / CSR index lists of the CTA's locales (static: loaded once per kernel)
     Y.cap_csc = Y.cap_csr = 0;
     for (int c = 0; c < S; c++) {
@@ -747,37 +757,46 @@ void build_grp_layout(epi_engine* h, int sms, int64_t smem_max) {
     }
     Y.s_cscp = take(4 * ((int64_t)lpc + 1)); Y.s_csci = take(4 * (int64_t)Y.cap_csc);
     Y.s_csrp = take(4 * ((int64_t)lpc + 1)); Y.s_csri = take(4 * (int64_t)Y.cap_csr);
-    Y.s_tab = o;
+    const int64_t o_cols = o;
     o = 0;
     Y.e_mult_y = take(4 * (int64_t)P.n_cls); Y.e_mult_d = take(4 * (int64_t)P.n_cls);
     Y.e_cpv = take(4 * (int64_t)P.NCP); Y.e_act = take(P.I);
     Y.e_expr = take(8 * (int64_t)P.n_expr); Y.e_sel = take(8 * (int64_t)P.n_sel);
-    Y.e_mpy = take(4 * n_lc * P.P * G); Y.e_mpg = take(4 * n_lc * P.P * G); Y.e_mpt0 = take(4 * n_lc * P.P * G);
-    Y.e_mpFy = take(4 * (int64_t)P.n_igp * n_lc * F * G); Y.e_mpFg = take(4 * (int64_t)P.n_igp * n_lc * F * G);
+    Y.e_mpt0 = take(4 * n_lc * P.P * G);
     Y.e_coefS = take(rs * NG * n_lc * F * G);
-    Y.e_Tnum = take(4 * n_lc * G * Y.trow); Y.e_Tden = take(rs * n_lc * G * Y.trow);
+    Y.e_Tnum = take(4 * n_lc * G * Y.trow);
     Y.e_ft_y = take(4 * n_lc * F * G); Y.e_ft_gap = take(4 * n_lc * F * G);
     Y.tab_bytes = o;
+    // the float copy of the state joins the columns when there is room for it
+    Y.s_XF = o_cols;
+    const int64_t xf_bytes = align16(rs * C * threads);
+    Y.xf_smem = R * (o_cols + xf_bytes + Y.tab_bytes + 1024) <= smem_max + 1024 && !getenv("EPI_GRP_XF_GLOBAL");
+    Y.s_tab = o_cols + (Y.xf_smem ? xf_bytes : 0);
     Y.smem_bytes = Y.s_tab + Y.tab_bytes;
-    Y.lpc = lpc; Y.threads = threads; Y.S = S;
-    return Y.smem_bytes <= smem_max;
+    Y.lpc = lpc; Y.threads = threads; Y.S = S; Y.R = R;
+    // R CTAs share the SM's shared memory (1 KB of it is reserved per resident CTA)
+    return R * (Y.smem_bytes + 1024) <= smem_max + 1024;
   };
-  int S = 0;
-  if (forceS > 0) {
-    if (forceS <= P.L && layout(forceS)) S = forceS;
-  } else {
-    for (int s_ = 1; s_ <= sms && s_ <= P.L; s_++)
-      if (layout(s_)) { S = s_; break; }
-    if (S > 0) {
-      // as many groups as fit at this size, then all the SMs' worth of CTAs per group (fewer cells per CTA)
-      const int ng = sms / S;
-      int S2 = sms / ng;
-      if (S2 > P.L) S2 = P.L;
-      if (!layout(S2)) layout(S);
+  int S = 0, Rsel = 0;
+  for (int R = forceR > 0 ? forceR : 2; R >= 1 && S == 0; R--) {
+    if (forceS > 0) {
+      if (forceS <= P.L && layout(forceS, R)) { S = forceS; Rsel = R; }
+    } else {
+      for (int s_ = 1; s_ <= sms * R && s_ <= P.L; s_++)
+        if (layout(s_, R)) { S = s_; Rsel = R; break; }
+      if (S > 0) {
+        // as many groups as fit at this size, then all the CTA slots' worth of CTAs per group (fewer cells per CTA)
+        const int ng = sms * R / S;
+        int S2 = sms * R / ng;
+        if (S2 > P.L) S2 = P.L;
+        if (!layout(S2, R)) layout(S, R);
+      }
     }
+    if (forceR > 0) break;
   }
   if (S == 0) { Y = GrpLayout{}; return; }
-  Y.n_groups = sms / Y.S;
+  (void)Rsel;
+  Y.n_groups = sms * Y.R / Y.S;
   const int64_t LG = P.LG;
   int64_t o = 0;
   auto take = [&](int64_t bytes) { int64_t r = o; o = (o + bytes + 255) & ~int64_t(255); return r; };
@@ -787,6 +806,9 @@ void build_grp_layout(epi_engine* h, int sms, int64_t smem_max) {
   Y.g_bytes = o;
   o = 0;
   Y.c_fi_y = take(4 * n_lc * F * G * G); Y.c_fi_gap = take(4 * n_lc * F * G * G);
+  Y.c_mpy = take(4 * n_lc * P.P * G); Y.c_mpg = take(4 * n_lc * P.P * G);
+  Y.c_mpFy = take(4 * (int64_t)P.n_igp * n_lc * F * G); Y.c_mpFg = take(4 * (int64_t)P.n_igp * n_lc * F * G);
+  Y.c_Tden = take(P.has_ft_ops ? rs * n_lc * G * Y.trow : 0);
   Y.c_bytes = o;
   Y.enabled = 1;
 }
@@ -1058,7 +1080,7 @@ std::string gen_spec(const epi_engine* h) {
     o << "}\n";
     // ---- the same program for the env-group kernel (epi_grp.cuh): the flow sums FB += bw f, FE += ew f live in
     // registers; `st`: the flows are also stored (last stage of an attempt)
-    o << "constexpr int grp_threads = " << P.gl.threads << ", grp_S = " << P.gl.S << ", grp_groups = " << P.gl.n_groups << ";\n";
+    o << "constexpr int grp_threads = " << P.gl.threads << ", grp_S = " << P.gl.S << ", grp_groups = " << P.gl.n_groups << ", grp_R = " << P.gl.R << ", grp_xf_smem = " << P.gl.xf_smem << ";\n";
     // regular edges (need the cell's own state only: they run while the group barrier of the gathers is pending)
     o << "__device__ __forceinline__ void flows_reg(const real* y, real alive, const float* mp, real* d, real* FB, real* FE, real bw, real ew, real* out, size_t stride, bool st) {\n";
     for (int c = 0; c < P.C; c++) o << "  d[" << c << "] = 0;\n";
@@ -1212,7 +1234,7 @@ std::string gen_spec(const epi_engine* h) {
   uint64_t k = 1469598103934665603ull;
   auto mix = [&](const void* p, size_t n) { for (size_t i = 0; i < n; i++) { k ^= ((const unsigned char*)p)[i]; k *= 1099511628211ull; } };
   mix(body.data(), body.size());
-  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 25 /* generator revision */};
+  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 27 /* generator revision */};
   mix(abi, sizeof abi);
   char kb[32];
   snprintf(kb, sizeof kb, "%016llx", (unsigned long long)k);
@@ -1221,7 +1243,7 @@ std::string gen_spec(const epi_engine* h) {
          "#define EPI_SPEC_PROLOGUE " + (spec_prologue ? "1" : "0") + "\n" +
          "#define EPI_SPEC_ROLES " + std::to_string(P.cl.roles > 0 ? P.cl.roles : 1) + "\n" +
          (P.LG > 32 ? std::string("#define EPI_ENV_MINB ") + (P.el.big_in_smem ? "2" : "4") + "\n" : std::string()) +
-         (P.LG > 32 ? std::string("#define EPI_GRP_THREADS ") + std::to_string(P.gl.enabled ? P.gl.threads : 0) + "\n" : std::string()) + body;
+         (P.LG > 32 ? std::string("#define EPI_GRP_THREADS ") + std::to_string(P.gl.enabled ? P.gl.threads : 0) + "\n#define EPI_GRP_R " + std::to_string(P.gl.enabled ? P.gl.R : 1) + "\n" : std::string()) + body;
 }
 
 void alloc_state(epi_engine* h, DevState& S, int N) {
@@ -1304,7 +1326,7 @@ void choose_launch(epi_engine* h) {
       const int ng = P.gl.n_groups < h->N ? P.gl.n_groups : h->N;
       h->grp_scratch = h->dalloc<char>((size_t)P.gl.g_bytes * ng, false);
       h->grp_cta_scratch = h->dalloc<char>((size_t)P.gl.c_bytes * ng * P.gl.S, false);
-      h->grp_bar = h->dalloc<unsigned>((size_t)32 * ng);
+      h->grp_bar = h->dalloc<unsigned>((size_t)32 * ng + 8 + 1024);  // arrive counters | class counters | per-SM counters
     }
     return;
   }
@@ -1426,7 +1448,7 @@ void launch_grp(epi_engine* h, const DevState& S, epi::StepArgs a, cudaStream_t 
   const GrpLayout& Y = h->plan.gl;
   const int ng = Y.n_groups < a.N ? Y.n_groups : a.N;
   a.grp_scratch = h->grp_scratch; a.grp_cta_scratch = h->grp_cta_scratch; a.grp_bar = h->grp_bar;
-  CK(cudaMemsetAsync(h->grp_bar, 0, sizeof(unsigned) * 32 * (size_t)ng, st));
+  CK(cudaMemsetAsync(h->grp_bar, 0, sizeof(unsigned) * (32 * (size_t)ng + 8 + 1024), st));
   int rc = h->spec_launch_grp(&h->plan, &S, &a, ng * Y.S, Y.threads, (size_t)Y.smem_bytes, (void*)st);
   if (rc != 0) throw CudaFail{std::string("env-group kernel launch: ") + cudaGetErrorString((cudaError_t)rc)};
   h->launches++;

@@ -33,6 +33,11 @@ typedef spec::real real;
 #ifndef EPI_FSAL_DAYS
 #define EPI_FSAL_DAYS 1
 #endif
+// entries of a cell's CSC / CSR row gathered together (their loads are in flight at the same time): 8 where the
+// register budget allows it (<= 12 resident warps per SM), else 4
+#ifndef EPI_GRP_CHUNK
+#define EPI_GRP_CHUNK ((EPI_GRP_R * (EPI_GRP_THREADS / 32)) <= 12 ? 8 : 4)
+#endif
 
 struct Gx {
   int tid, T;        // thread, threads per CTA (= width of a shared-memory column)
@@ -57,18 +62,28 @@ struct Gx {
 #define GTH (spec::grp_threads)
 #define GSS (spec::grp_S)
 #define GT(arr, i) (((T_##arr*)(b.tab + GL.e_##arr))[i])
+#define CT(arr, i) (((T_##arr*)(b.cs + GL.c_##arr))[i])  // per-CTA tables in global memory (read on dyn days only)
 #define SK(slot, k) (((real*)(b.smem + GL.s_K))[((slot) * spec::C + (k)) * GTH + b.tid])
 #define SKS(slot, q) (((double*)(b.smem + GL.s_KS))[((slot) * spec::n_slot + (q)) * GTH + b.tid])
 #define SCMB(k, t) (((real*)(b.smem + GL.s_cmB))[(k) * GTH + (t)])
 #define GCOL(off, T_, i) (((T_*)(b.gs + (off)))[(size_t)(i) * spec::LG + b.cell])
-#define GXF(k) GCOL(GL.g_XF, real, k)
+// the float copy of the state: a shared-memory column when the layout has room for it
+#define GXF(k) (*(spec::grp_xf_smem ? &((real*)(b.smem + GL.s_XF))[(k) * GTH + b.tid] : &GCOL(GL.g_XF, real, k)))
 
 #ifdef EPI_HOST_EMU
 __device__ __forceinline__ real ldcg(const real* p) { return *p; }
 __device__ __forceinline__ double ldcg(const double* p) { return *p; }
+__device__ __forceinline__ real ldcg_ord(const real* p) { return *p; }
 #else
 __device__ __forceinline__ float ldcg(const float* p) { return __ldcg(p); }
 __device__ __forceinline__ double ldcg(const double* p) { return __ldcg(p); }
+// the gathers: volatile, so that the loads of a chunk are issued in program order, all of them before the first
+// multiply-add that consumes one (otherwise the register allocator serialises load -> use -> load)
+__device__ __forceinline__ float ldcg_ord(const float* p) {
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
 #endif
 
 // ---- group barrier: all S CTAs of the group; global writes before it are visible to every CTA after it
@@ -87,9 +102,11 @@ __device__ __forceinline__ void grp_arrive(Gx& b) {
 __device__ __forceinline__ void grp_wait(Gx& b) {
 #ifndef EPI_HOST_EMU
   if (b.tid == 0) {
+    // relaxed polls (an acquire load invalidates the L1 on every iteration), one fence once the count is there;
+    // everything another CTA wrote is read with ld.cg below
     unsigned v;
     do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(b.bar) : "memory");
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(b.bar) : "memory");
     } while ((int)(v - b.epoch) < 0);
     __threadfence();
   }
@@ -154,7 +171,7 @@ __device__ __forceinline__ void fill_tables(const DevPlan& P, const Gx& b, float
   constexpr int G = spec::G, F = spec::F, NG = spec::NG, n_lc = spec::n_lc, PP = spec::P;
   const float* fi_y = (const float*)(b.cs + GL.c_fi_y);
   const float* fi_gap = (const float*)(b.cs + GL.c_fi_gap);
-  for (int i = b.tid; i < n_lc * PP * G; i += b.T) GT(mpt0, i) = lerp_rn(GT(mpy, i), GT(mpg, i), tf);
+  for (int i = b.tid; i < n_lc * PP * G; i += b.T) GT(mpt0, i) = lerp_rn(CT(mpy, i), CT(mpg, i), tf);
   for (int i = b.tid; i < n_lc * F * G * G; i += b.T) {
     int u = i % G, u0 = (i / G) % G, lv = i / (G * G), lc = lv / F, v = lv - lc * F;
     float ft = lerp_rn(GT(ft_y, lv * G + u), GT(ft_gap, lv * G + u), tf);
@@ -162,21 +179,21 @@ __device__ __forceinline__ void fill_tables(const DevPlan& P, const Gx& b, float
     float fa = lerp_rn(fi_y[a], fi_gap[a], tf), fb = lerp_rn(fi_y[bb], fi_gap[bb], tf);
     const int it = (lc * G + u0) * GL.trow + v * G + u;
     GT(Tnum, it) = __fmul_rn(__fmul_rn(ft, fa), fb);  // f32 product (core_optimize.py:114)
-    if (spec::has_ft_ops) GT(Tden, it) = (real)ft * (real)__ldg(P.fi0 + a) * (real)__ldg(P.fi0 + bb);
+    if (spec::has_ft_ops) CT(Tden, it) = (real)ft * (real)__ldg(P.fi0 + a) * (real)__ldg(P.fi0 + bb);
   }
   constexpr int FG = F * G, nFG = n_lc * FG;
   for (int i = b.tid; i < NG * nFG; i += b.T) {
     int k = i / nFG, r = i - k * nFG;  // r = (lc*F + v)*G + u0
     real cf = (real)lerp_rn(GT(ft_y, r), GT(ft_gap, r), tf);
     int pi = __ldg(P.ig_p0i + k);
-    cf *= (real)lerp_rn(GT(mpFy, pi * nFG + r), GT(mpFg, pi * nFG + r), tf);
+    cf *= (real)lerp_rn(CT(mpFy, pi * nFG + r), CT(mpFg, pi * nFG + r), tf);
     for (int q = __ldg(P.ig_np_off + k); q < __ldg(P.ig_np_off + k + 1); q++) {
       pi = __ldg(P.ig_npi + q);
-      cf *= (real)lerp_rn(GT(mpFy, pi * nFG + r), GT(mpFg, pi * nFG + r), tf);
+      cf *= (real)lerp_rn(CT(mpFy, pi * nFG + r), CT(mpFg, pi * nFG + r), tf);
     }
     for (int q = __ldg(P.ig_dp_off + k); q < __ldg(P.ig_dp_off + k + 1); q++) {
       pi = __ldg(P.ig_dpi + q);
-      float m = lerp_rn(GT(mpFy, pi * nFG + r), GT(mpFg, pi * nFG + r), tf);
+      float m = lerp_rn(CT(mpFy, pi * nFG + r), CT(mpFg, pi * nFG + r), tf);
       if (fabsf(m) > 0) cf /= (real)m;
     }
     GT(coefS, i) = cf;
@@ -191,7 +208,7 @@ __device__ __forceinline__ void fill_tables(const DevPlan& P, const Gx& b, float
 __device__ __forceinline__ void rhs(const DevPlan& P, Gx& b, bool dyn, double t, int ex_bits, int phase, int stage, real bw,
                                     real ew, bool st6, double hh, int nj, real (&FB)[spec::NSRC], real (&FE)[spec::NSRC]) {
   constexpr int G = spec::G, F = spec::F, LG = spec::LG, NG = spec::NG, n_lc = spec::n_lc, PP = spec::P, C = spec::C,
-                nE = spec::E, nS = spec::has_src64 ? spec::n_slot : 0;
+                nE = spec::E, nS = spec::has_src64 ? spec::n_slot : 0, CH = EPI_GRP_CHUNK;
   const float tf = (float)t;
   const float qf = (float)((-3.0 * t + 4.0) * t);  // utility/utils.py:34-37, rounded like parameter.py:83
   if (dyn) {
@@ -266,22 +283,22 @@ __device__ __forceinline__ void rhs(const DevPlan& P, Gx& b, bool dyn, double t,
       const int jl = b.j - b.l0, qb = cp[jl], qe = cp[jl + 1];
       const float* vp = P.mx_cscT + (size_t)__ldg(P.csc_indptr + b.l0) * G + b.u;
 #pragma unroll 1
-      for (int q0 = qb; q0 < qe; q0 += 4) {
-        int src[4];
-        real val[4], g[4][1 + NG];
+      for (int q0 = qb; q0 < qe; q0 += CH) {
+        int src[CH];
+        real val[CH], g[CH][1 + NG];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < CH; i++) {
           const bool on = q0 + i < qe;
           const int q = on ? q0 + i : qb;
           src[i] = ci[q] * G + b.u;
           val[i] = on ? (real)__ldg(vp + (size_t)q * G) : (real)0;
         }
 #pragma unroll
-        for (int i = 0; i < 4; i++)
+        for (int i = 0; i < CH; i++)
 #pragma unroll
-          for (int k = 0; k < 1 + NG; k++) g[i][k] = ldcg(cmA + (size_t)k * LG + src[i]);
+          for (int k = 0; k < 1 + NG; k++) g[i][k] = ldcg_ord(cmA + (size_t)k * LG + src[i]);
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < CH; i++) {
           a += g[i][0] * val[i];
 #pragma unroll
           for (int k = 0; k < NG; k++) xs[k] += g[i][1 + k] * val[i];
@@ -299,7 +316,9 @@ __device__ __forceinline__ void rhs(const DevPlan& P, Gx& b, bool dyn, double t,
       for (int k = 0; k < NG; k++) sk[k] = 0;
       const int row = b.tid - b.u;  // the locale's first column
       const float* Tn = &GT(Tnum, (b.lc * G + b.u) * GL.trow);
-      const real* Td = &GT(Tden, (b.lc * G + b.u) * GL.trow);
+      // the denominator's table: env-independent without FT ops (one padded copy in global memory, L1 / L2 hits),
+      // else this CTA's copy of the time-t table
+      const real* Td = (spec::has_ft_ops ? (const real*)(b.cs + GL.c_Tden) : (const real*)P.Tden_constP) + (b.lc * G + b.u) * GL.trow;
       constexpr int VH = (F % 4 == 0 && G % 4 == 0) ? 4 : 1;  // facilities per sweep over the locale's groups
 #pragma unroll 1
       for (int v0 = 0; v0 < F; v0 += VH) {
@@ -366,22 +385,22 @@ __device__ __forceinline__ void rhs(const DevPlan& P, Gx& b, bool dyn, double t,
       const int jl = b.j - b.l0, qb = cp[jl], qe = cp[jl + 1];
       const float* vp = P.mx_csrT + (size_t)__ldg(P.csr_indptr + b.l0) * G + b.u;
 #pragma unroll 1
-      for (int q0 = qb; q0 < qe; q0 += 4) {
-        int dst[4];
-        real val[4], g[4][NG];
+      for (int q0 = qb; q0 < qe; q0 += CH) {
+        int dst[CH];
+        real val[CH], g[CH][NG];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < CH; i++) {
           const bool on = q0 + i < qe;
           const int q = on ? q0 + i : qb;
           dst[i] = ci[q] * G + b.u;
           val[i] = on ? (real)__ldg(vp + (size_t)q * G) : (real)0;
         }
 #pragma unroll
-        for (int i = 0; i < 4; i++)
+        for (int i = 0; i < CH; i++)
 #pragma unroll
-          for (int k = 0; k < NG; k++) g[i][k] = ldcg(cmS + (size_t)k * LG + dst[i]);
+          for (int k = 0; k < NG; k++) g[i][k] = ldcg_ord(cmS + (size_t)k * LG + dst[i]);
 #pragma unroll
-        for (int i = 0; i < 4; i++)
+        for (int i = 0; i < CH; i++)
 #pragma unroll
           for (int k = 0; k < NG; k++) rs[k] += g[i][k] * val[i];
       }
@@ -539,8 +558,8 @@ __device__ __forceinline__ int prologue(const DevPlan& P, Gx& b, int variant, do
       float m0 = __ldg(P.mp0 + idx);
       int cls = __ldg(P.mp_cls + idx);
       float yv = __fmul_rn(m0, GT(mult_y, cls)), dv = __fmul_rn(m0, GT(mult_d, cls));
-      GT(mpy, i) = yv;
-      GT(mpg, i) = __fsub_rn(dv, yv);
+      CT(mpy, i) = yv;
+      CT(mpg, i) = __fsub_rn(dv, yv);
     }
     const int nFG = P.n_lc * F * G;
     for (int i = b.tid; i < P.n_igp * nFG; i += b.T) {
@@ -549,8 +568,8 @@ __device__ __forceinline__ int prologue(const DevPlan& P, Gx& b, int variant, do
       float m0 = __ldg(P.mp0 + idx);
       int cls = __ldg(P.mp_cls + idx);
       float yv = __fmul_rn(m0, GT(mult_y, cls)), dv = __fmul_rn(m0, GT(mult_d, cls));
-      GT(mpFy, i) = yv;
-      GT(mpFg, i) = __fsub_rn(dv, yv);
+      CT(mpFy, i) = yv;
+      CT(mpFg, i) = __fsub_rn(dv, yv);
     }
   }
   // 5. move table of today (nb_move, executor.py:166-234; different compartment, same locale)
@@ -894,14 +913,6 @@ __device__ __forceinline__ void step_group(const DevPlan& P, const DevState& S, 
                                            int n_groups) {
   constexpr int C = spec::C, CLG = spec::CLG, LG = spec::LG, L = spec::L, G = spec::G, F = spec::F, nC = spec::I * spec::L;
   const size_t nA = (size_t)spec::n_acc * LG, nM = (size_t)spec::n_slot * LG;
-  if (!spec::has_ft_ops) {
-    // the denominator's mixing table does not depend on the env: one copy per CTA, in the padded row layout
-#pragma unroll 1
-    for (int i = b.tid; i < spec::n_lc * F * G * G; i += b.T) {
-      int u0 = i % G, u = (i / G) % G, lv = i / (G * G), lc = lv / F, v = lv - lc * F;  // source layout [lc,F,u,u0]
-      GT(Tden, (lc * G + u0) * GL.trow + v * G + u) = (real)__ldg(P.Tden_constT + i);
-    }
-  }
   {
     // the CSC / CSR index lists of this CTA's locales (static), offsets relative to the first locale's row
     int* cp = (int*)(b.smem + GL.s_cscp); int* ci = (int*)(b.smem + GL.s_csci);
@@ -1027,15 +1038,38 @@ __device__ __forceinline__ Gx bind(const DevPlan& P, const StepArgs& a, char* sm
 }
 
 #ifndef EPI_HOST_EMU
-// one CTA per SM. The register file is four 16 K-register partitions, one per scheduler, and a CTA's warps are dealt
+// EPI_GRP_R CTAs per SM. The register file is four 16 K-register partitions, one per scheduler, and a CTA's warps are dealt
 // round-robin to them: registers per thread <= 16384 / (32 * ceil(warps / 4))  (448 threads -> 128; a kernel compiled
 // for 144 cannot be resident at all, which a cooperative launch reports as "too many blocks")
-#define EPI_GRP_MAXREG_RAW (16384 / (32 * ((EPI_GRP_THREADS / 32 + 3) / 4)) / 8 * 8)
+#define EPI_GRP_MAXREG_RAW (16384 / (32 * ((EPI_GRP_R * (EPI_GRP_THREADS / 32) + 3) / 4)) / 8 * 8)
 #define EPI_GRP_MAXREG (EPI_GRP_MAXREG_RAW > 255 ? 255 : EPI_GRP_MAXREG_RAW)
 __global__ void __maxnreg__(EPI_GRP_MAXREG) grp_kernel(const DevPlan P, const DevState S, const StepArgs a) {
   extern __shared__ __align__(16) char grp_smem[];
-  Gx b = bind(P, a, grp_smem, threadIdx.x, blockDim.x, blockIdx.x);
-  step_group(P, S, a, b, blockIdx.x / b.S, gridDim.x / b.S);
+  int vb = blockIdx.x;
+#if EPI_GRP_R > 1
+  {
+    // R CTAs share an SM: they must belong to DIFFERENT groups to fill each other's barrier and gather stalls, and the
+    // hardware's block placement is not ours to choose. The k-th CTA to arrive on an SM joins class k; the CTAs of a
+    // class are numbered in arrival order and cut into groups of S (all n_groups * S CTAs are resident: cooperative
+    // launch, exactly R per SM). Counters: a.grp_bar + 32 * n_groups ... (zeroed per launch).
+    __shared__ int s_vb;
+    if (threadIdx.x == 0) s_vb = blockIdx.x;
+    // (a launch with fewer groups than the device holds leaves SMs half empty: any numbering will do)
+    if (threadIdx.x == 0 && (int)gridDim.x == GL.n_groups * GSS) {
+      const int n_groups = gridDim.x / GSS, per_class = gridDim.x / EPI_GRP_R;
+      unsigned* ctr = a.grp_bar + (size_t)32 * n_groups;
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      const unsigned cls = atomicAdd(ctr + 8 + smid, 1u) % EPI_GRP_R;
+      const unsigned r = atomicAdd(ctr + cls, 1u);
+      s_vb = (int)(cls * per_class + r);
+    }
+    __syncthreads();
+    vb = s_vb;
+  }
+#endif
+  Gx b = bind(P, a, grp_smem, threadIdx.x, blockDim.x, vb);
+  step_group(P, S, a, b, vb / GSS, gridDim.x / GSS);
 }
 #endif
 

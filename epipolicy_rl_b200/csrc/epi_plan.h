@@ -50,15 +50,16 @@ struct EnvLayout {
 // global scratch (comm columns, float state copy, last-stage flows, candidate accumulators, reduction partials).
 struct GrpLayout {
   int enabled, S, n_groups, threads;
+  int R;    // CTAs per SM (2: CTAs of two different groups share an SM and fill each other's barrier / gather stalls)
   int lpc;  // locales per CTA (upper bound; CTA c owns locales [c*L/S, (c+1)*L/S))
   int np;   // doubles per CTA and parity in the reduction-partials array
   int trow; // row stride (floats) of the mixing tables T[lc][u0][v][u] (F*G padded against bank conflicts)
-  int64_t s_K, s_KS, s_cmB, s_red, s_cscp, s_csci, s_csrp, s_csri, s_tab, smem_bytes;
+  int64_t s_K, s_KS, s_cmB, s_red, s_cscp, s_csci, s_csrp, s_csri, s_XF, s_tab, smem_bytes;
+  int xf_smem;  // the float copy of the state lives in shared memory (else in the group scratch)
   int cap_csc, cap_csr;  // most CSC / CSR entries any CTA's locales own
-  int64_t e_mult_y, e_mult_d, e_cpv, e_act, e_expr, e_sel, e_mpy, e_mpg, e_mpt0, e_mpFy, e_mpFg, e_coefS, e_Tnum,
-      e_Tden, e_ft_y, e_ft_gap, tab_bytes;
+  int64_t e_mult_y, e_mult_d, e_cpv, e_act, e_expr, e_sel, e_mpt0, e_coefS, e_Tnum, e_ft_y, e_ft_gap, tab_bytes;
   int64_t g_XF, g_cmA, g_cmS, g_fl6, g_accN, g_mvD, g_crD, g_part, g_bytes;  // per group
-  int64_t c_fi_y, c_fi_gap, c_bytes;                                        // per CTA
+  int64_t c_fi_y, c_fi_gap, c_mpy, c_mpg, c_mpFy, c_mpFg, c_Tden, c_bytes;  // per CTA (tables only the day prologue / a dyn day reads)
 };
 
 struct DevPlan {
@@ -87,6 +88,7 @@ struct DevPlan {
   const float* Tden_const;   // [n_lc,F,G,G] ft*fi0*fi0^T with the default (normalised) ft, when !has_ft_ops
   const double* Tden_const64;
   const float* Tden_constT;  // the same, transposed [n_lc,F,u,u0] (env kernel)
+  const float* Tden_constP;  // the same as rows [n_lc,u0][F*G + 4]: element (v,u) of cell group u0 at v*G+u (env-group kernel)
   const double* Tden_const64T;
   const float* mx_csr;       // [G,nnz] combined mobility on the union pattern (core_optimize.py:69-92)
   const float* mx_csc;       // [G,nnz]
