@@ -728,7 +728,7 @@ void build_grp_layout(epi_engine* h, int sms, int64_t smem_max) {
   Y = GrpLayout{};
   const char* ev = getenv("EPI_GRP");  // "0": never; "2": also when the env fits one CTA's shared memory (tests)
   const int mode = ev ? atoi(ev) : 1;
-  if (mode == 0 || h->precision != EPI_FP32 || P.LG <= 32 || P.G > 32 || P.F > 32) return;
+  if (mode == 0 || h->precision != EPI_FP32 || P.LG <= 32 || P.G > 32 || P.F > 32 || P.C > 32 || P.n_sel > 32 || P.n_mv_op > 32) return;
   if (P.el.big_in_smem && mode < 2) return;
   const int64_t rs = 4, C = P.C, G = P.G, F = P.F, n_lc = P.n_lc, NG = P.NG;
   const int64_t nS = P.has_src64 ? P.n_slot : 0;
@@ -747,16 +747,19 @@ void build_grp_layout(epi_engine* h, int sms, int64_t smem_max) {
     Y.trow = (int)(F * G + 4);
     Y.np = P.n_sel + P.n_mv_op > 2 ? P.n_sel + P.n_mv_op : 2;
     Y.s_K = take(rs * 6 * C * threads); Y.s_KS = take(8 * 6 * nS * threads); Y.s_cmB = take(rs * (1 + NG) * threads);
-    Y.s_red = take(8 * (32 + (int64_t)(P.n_mv_op > 2 ? P.n_mv_op : 2)));
-    // the CSC / CSR index lists of the CTA's locales (static: loaded once per kernel)
-    Y.cap_csc = Y.cap_csr = 0;
-    for (int c = 0; c < S; c++) {
-      const int l0 = (int)(((int64_t)c * P.L) / S), l1 = (int)(((int64_t)(c + 1) * P.L) / S);
-      Y.cap_csc = std::max(Y.cap_csc, h->tabs.csc_indptr[l1] - h->tabs.csc_indptr[l0]);
-      Y.cap_csr = std::max(Y.cap_csr, h->tabs.csr_indptr[l1] - h->tabs.csr_indptr[l0]);
+    Y.s_red = take(8 * (32 + (int64_t)(P.n_mv_op > 2 ? P.n_mv_op : 2)) + 16);  // + (chunks of this CTA's longest CSC / CSR row)
+    // the CSC / CSR rows of the CTA's locales, padded to the longest row (ELL): source / destination locale per
+    // (entry, locale) in shared memory, the mobility value per (entry, thread) in the CTA's global scratch
+    {
+      int mc = 0, mr = 0;
+      for (int l = 0; l < P.L; l++) {
+        mc = std::max(mc, h->tabs.csc_indptr[l + 1] - h->tabs.csc_indptr[l]);
+        mr = std::max(mr, h->tabs.csr_indptr[l + 1] - h->tabs.csr_indptr[l]);
+      }
+      const int ch = R * (threads / 32) <= 12 ? 8 : 4;  // EPI_GRP_CHUNK (epi_grp.cuh)
+      Y.nqc = (mc + ch - 1) / ch * ch; Y.nqr = (mr + ch - 1) / ch * ch;
     }
-    Y.s_cscp = take(4 * ((int64_t)lpc + 1)); Y.s_csci = take(4 * (int64_t)Y.cap_csc);
-    Y.s_csrp = take(4 * ((int64_t)lpc + 1)); Y.s_csri = take(4 * (int64_t)Y.cap_csr);
+    Y.s_eci = take(4 * (int64_t)lpc * Y.nqc); Y.s_eri = take(4 * (int64_t)lpc * Y.nqr);
     const int64_t o_cols = o;
     o = 0;
     Y.e_mult_y = take(4 * (int64_t)P.n_cls); Y.e_mult_d = take(4 * (int64_t)P.n_cls);
@@ -766,8 +769,14 @@ void build_grp_layout(epi_engine* h, int sms, int64_t smem_max) {
     Y.e_coefS = take(rs * NG * n_lc * F * G);
     Y.e_Tnum = take(4 * n_lc * G * Y.trow);
     Y.e_ft_y = take(4 * n_lc * F * G); Y.e_ft_gap = take(4 * n_lc * F * G);
+    Y.e_selinfo = take(8 * (int64_t)(P.n_sel > 0 ? P.n_sel : 1));  // (compartment mask, mode) per select
     Y.tab_bytes = o;
-    // the float copy of the state joins the columns when there is room for it
+    // when there is room: first a shared-memory copy of the denominator's mixing table (read 2 F G / 4 times per cell
+    // and evaluation), then the float copy of the state (read C times)
+    const int64_t td_bytes = align16(rs * n_lc * G * Y.trow);
+    Y.tden_smem = R * (o_cols + Y.tab_bytes + td_bytes + 1024) <= smem_max + 1024 && !getenv("EPI_GRP_TDEN_GLOBAL");
+    Y.e_Tden = Y.tab_bytes;
+    if (Y.tden_smem) Y.tab_bytes += td_bytes;
     Y.s_XF = o_cols;
     const int64_t xf_bytes = align16(rs * C * threads);
     Y.xf_smem = R * (o_cols + xf_bytes + Y.tab_bytes + 1024) <= smem_max + 1024 && !getenv("EPI_GRP_XF_GLOBAL");
@@ -778,7 +787,9 @@ void build_grp_layout(epi_engine* h, int sms, int64_t smem_max) {
     return R * (Y.smem_bytes + 1024) <= smem_max + 1024;
   };
   int S = 0, Rsel = 0;
-  for (int R = forceR > 0 ? forceR : 2; R >= 1 && S == 0; R--) {
+  // (two CTAs of different groups per SM were measured and do not pay: the step is a latency chain per env, and the
+  // number of envs in flight is set by the shared memory either way; EPI_GRP_R=2 keeps the variant reachable)
+  for (int R = forceR > 0 ? forceR : 1; R >= 1 && S == 0; R--) {
     if (forceS > 0) {
       if (forceS <= P.L && layout(forceS, R)) { S = forceS; Rsel = R; }
     } else {
@@ -797,6 +808,7 @@ void build_grp_layout(epi_engine* h, int sms, int64_t smem_max) {
   if (S == 0) { Y = GrpLayout{}; return; }
   (void)Rsel;
   Y.n_groups = sms * Y.R / Y.S;
+  Y.dyn_assign = Y.R > 1 && Y.n_groups * Y.S == sms * Y.R;
   const int64_t LG = P.LG;
   int64_t o = 0;
   auto take = [&](int64_t bytes) { int64_t r = o; o = (o + bytes + 255) & ~int64_t(255); return r; };
@@ -809,6 +821,7 @@ void build_grp_layout(epi_engine* h, int sms, int64_t smem_max) {
   Y.c_mpy = take(4 * n_lc * P.P * G); Y.c_mpg = take(4 * n_lc * P.P * G);
   Y.c_mpFy = take(4 * (int64_t)P.n_igp * n_lc * F * G); Y.c_mpFg = take(4 * (int64_t)P.n_igp * n_lc * F * G);
   Y.c_Tden = take(P.has_ft_ops ? rs * n_lc * G * Y.trow : 0);
+  Y.c_evc = take(4 * (int64_t)Y.nqc * Y.threads); Y.c_evr = take(4 * (int64_t)Y.nqr * Y.threads);
   Y.c_bytes = o;
   Y.enabled = 1;
 }
@@ -1078,18 +1091,19 @@ std::string gen_spec(const epi_engine* h) {
     }
     rcp_of = nullptr;
     o << "}\n";
+    if (P.gl.enabled) {
     // ---- the same program for the env-group kernel (epi_grp.cuh): the flow sums FB += bw f, FE += ew f live in
     // registers; `st`: the flows are also stored (last stage of an attempt)
-    o << "constexpr int grp_threads = " << P.gl.threads << ", grp_S = " << P.gl.S << ", grp_groups = " << P.gl.n_groups << ", grp_R = " << P.gl.R << ", grp_xf_smem = " << P.gl.xf_smem << ";\n";
+    o << "constexpr int grp_threads = " << P.gl.threads << ", grp_S = " << P.gl.S << ", grp_groups = " << P.gl.n_groups << ", grp_R = " << P.gl.R << ", grp_xf_smem = " << P.gl.xf_smem << ", grp_tden_smem = " << P.gl.tden_smem << ", grp_lpc = " << P.gl.lpc << ", grp_nqc = " << P.gl.nqc << ", grp_nqr = " << P.gl.nqr << ";\n";
     // regular edges (need the cell's own state only: they run while the group barrier of the gathers is pending)
-    o << "__device__ __forceinline__ void flows_reg(const real* y, real alive, const float* mp, real* d, real* FB, real* FE, real bw, real ew, real* out, size_t stride, bool st) {\n";
+    o << "__device__ __forceinline__ void flows_reg(const real* y, real alive, const float* mp, real* d, float2* FBE, float2 bwew, real* out, size_t stride, bool st) {\n";
     for (int c = 0; c < P.C; c++) o << "  d[" << c << "] = 0;\n";
     if (h->precision == EPI_FP32) {
       for (auto& dc : rdecl) o << "  real " << dc.first << "; { real dn = 0;" << dc.second << " " << dc.first << " = frcp(dn); }\n";
       rcp_of = &rmap;
     }
     auto sums = [&](int src) {
-      o << " FB[" << src << "] += bw * f; FE[" << src << "] += ew * f; if (st) out[" << src << " * stride] = f;";
+      o << " FBE[" << src << "] = ffma2(float2{f, f}, bwew, FBE[" << src << "]); if (st) out[" << src << " * stride] = f;";
     };
     for (int e = 0; e < P.E; e++) {
       const int* ep = T.ep.data() + T.ep_off[e];
@@ -1106,7 +1120,7 @@ std::string gen_spec(const epi_engine* h) {
     rcp_of = nullptr;
     o << "}\n";
     // infectious groups: yc[k] = the susceptible compartment of group k, rs[k] = its gathered force of infection
-    o << "__device__ __forceinline__ void flows_inf(const real* yc, const real* rs, real* d, real* FB, real* FE, real bw, real ew, real* out, size_t stride, bool st) {\n";
+    o << "__device__ __forceinline__ void flows_inf(const real* yc, const real* rs, real* d, float2* FBE, float2 bwew, real* out, size_t stride, bool st) {\n";
     for (int k = 0; k < P.NG; k++) {
       o << "  { real f = yc[" << k << "] * rs[" << k << "];";
       sums(P.E + k);
@@ -1114,6 +1128,7 @@ std::string gen_spec(const epi_engine* h) {
       o << " }\n";
     }
     o << "}\n";
+    }
     arr("ag_off", T.ag_off); arr("ag_src", T.ag_src);
     o << "__device__ constexpr float ag_coef[" << (T.ag_coef.empty() ? 1 : T.ag_coef.size()) << "] = {";
     if (T.ag_coef.empty()) o << "0";
@@ -1234,7 +1249,7 @@ std::string gen_spec(const epi_engine* h) {
   uint64_t k = 1469598103934665603ull;
   auto mix = [&](const void* p, size_t n) { for (size_t i = 0; i < n; i++) { k ^= ((const unsigned char*)p)[i]; k *= 1099511628211ull; } };
   mix(body.data(), body.size());
-  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 27 /* generator revision */};
+  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 30 /* generator revision */};
   mix(abi, sizeof abi);
   char kb[32];
   snprintf(kb, sizeof kb, "%016llx", (unsigned long long)k);

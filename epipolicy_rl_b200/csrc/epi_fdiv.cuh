@@ -4,6 +4,12 @@
 // slow-path branch, and the error-norm code of the RK45 controller alone holds ~150 of them.
 #pragma once
 namespace epi {
+// packed pair of fp32 multiply-adds: one FFMA2 on sm_100a (Blackwell's 2-wide fp32 instruction), two fmaf on the host
+#ifdef EPI_HOST_EMU
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return float2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
+#else
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+#endif
 __device__ __forceinline__ double fdiv(double a, double b) { return a / b; }
 __device__ __forceinline__ double ctrl_pow(double, double x, double p) { return pow(x, p); }
 // a cost component's term of the scaled RMS norm, x / sc, and the norm's square root: double in the parity mode;

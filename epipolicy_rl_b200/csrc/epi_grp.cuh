@@ -23,6 +23,9 @@
 #pragma once
 #include "epi_kernels.cuh"
 #include "epi_rk.cuh"
+#ifdef EPI_GRP_TIMING
+#include <stdio.h>
+#endif
 
 #ifdef EPI_SPEC
 namespace epi {
@@ -39,7 +42,18 @@ typedef spec::real real;
 #define EPI_GRP_CHUNK ((EPI_GRP_R * (EPI_GRP_THREADS / 32)) <= 12 ? 8 : 4)
 #endif
 
+// -DEPI_GRP_TIMING: thread 0 of every CTA accumulates the cycles it spends in each section of the step (critical-path
+// breakdown; printed by CTA 0 of group 0 when the kernel ends). Debug builds only.
+#ifdef EPI_GRP_TIMING
+#define TSEC(i) do { if (b.tid == 0) { long long now_ = clock64(); b.tacc[b.tcur] += now_ - b.tlast; b.tlast = now_; b.tcur = (i); } } while (0)
+#else
+#define TSEC(i) do { } while (0)
+#endif
+
 struct Gx {
+#ifdef EPI_GRP_TIMING
+  long long* tacc; long long tlast; int tcur;
+#endif
   int tid, T;        // thread, threads per CTA (= width of a shared-memory column)
   int cta, S;        // CTA inside the group, CTAs per group
   int l0, nl;        // first locale / number of locales of this CTA
@@ -51,6 +65,8 @@ struct Gx {
   unsigned epoch;    // arrivals expected at the next barrier
   int parity;        // reduction-partials buffer in use
   int s0, s1;        // K slots of stage 0 and of stages 1 / 6
+  unsigned selmask, mvmask;  // selects / MOVE ops whose locale and group masks cover this thread's cell (static)
+  int nq_w;          // chunks' worth of entries of the longest CSC (low half) / CSR (high half) row in this warp
   // current env
   double *gX, *cost, *crY, *crD;
   real *acc, *accn;  // accumulator column and candidate column (swap roles on an accepted step)
@@ -86,29 +102,27 @@ __device__ __forceinline__ float ldcg_ord(const float* p) {
 }
 #endif
 
-// ---- group barrier: all S CTAs of the group; global writes before it are visible to every CTA after it
+// ---- group barrier: all S CTAs of the group; global writes before it are visible (in L2) to every CTA after it.
+// Arrive = release-add on the group's counter (the release orders the CTA's writes, which thread 0 has observed through
+// the CTA barrier, before the count); wait = relaxed polls by thread 0, then the CTA barrier. No acquire fence and so
+// no L1 invalidation (an acquire costs CCTL.IVALL: every spill slot, table and index list would be re-fetched from L2
+// after every barrier): everything another CTA writes is read with ld.global.cg, i.e. from L2, the point of coherence.
 __device__ __forceinline__ void grp_arrive(Gx& b) {
   __syncthreads();
   b.epoch += (unsigned)b.S;
 #ifdef EPI_HOST_EMU
   emu::group_arrive_wait();
 #else
-  if (b.tid == 0) {
-    __threadfence();
-    atomicAdd(b.bar, 1u);
-  }
+  if (b.tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(b.bar) : "memory");
 #endif
 }
 __device__ __forceinline__ void grp_wait(Gx& b) {
 #ifndef EPI_HOST_EMU
   if (b.tid == 0) {
-    // relaxed polls (an acquire load invalidates the L1 on every iteration), one fence once the count is there;
-    // everything another CTA wrote is read with ld.cg below
     unsigned v;
     do {
       asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(b.bar) : "memory");
     } while ((int)(v - b.epoch) < 0);
-    __threadfence();
   }
 #endif
   __syncthreads();
@@ -206,22 +220,26 @@ __device__ __forceinline__ void fill_tables(const DevPlan& P, const Gx& b, float
 // attempt: they open the next attempt, first-same-as-last).
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void rhs(const DevPlan& P, Gx& b, bool dyn, double t, int ex_bits, int phase, int stage, real bw,
-                                    real ew, bool st6, double hh, int nj, real (&FB)[spec::NSRC], real (&FE)[spec::NSRC]) {
+                                    real ew, bool st6, double hh, int nj, float2 (&FBE)[spec::NSRC]) {
   constexpr int G = spec::G, F = spec::F, LG = spec::LG, NG = spec::NG, n_lc = spec::n_lc, PP = spec::P, C = spec::C,
                 nE = spec::E, nS = spec::has_src64 ? spec::n_slot : 0, CH = EPI_GRP_CHUNK;
   const float tf = (float)t;
   const float qf = (float)((-3.0 * t + 4.0) * t);  // utility/utils.py:34-37, rounded like parameter.py:83
   if (dyn) {
+    TSEC(13);
     __syncthreads();  // the previous evaluation's readers of the time-t tables are done
     fill_tables(P, b, tf);
     __syncthreads();
+    TSEC(0);
   }
   const int kslot = stage == 0 ? b.s0 : (stage == 1 || stage == 6) ? b.s1 : stage;
+  const float2 bwew = float2{bw, ew};
   real* out = (real*)(b.gs + GL.g_fl6) + b.cell;
   real d[C];
   real yc[NG > 0 ? NG : 1];                          // the susceptible compartments of the infectious groups
   real y1[spec::n_slot > 0 ? spec::n_slot : 1], y2[spec::n_slot > 0 ? spec::n_slot : 1];  // move slots: source, target
   double ysS[nS > 0 ? nS : 1];
+  TSEC(1);
   // ---- pass 1: stage input, alive (N excludes death and hospitalized, :28-41,:168), weighted infectious sums
   real y[C], alive = 0;
   if (b.valid) {
@@ -250,13 +268,15 @@ __device__ __forceinline__ void rhs(const DevPlan& P, Gx& b, bool dyn, double t,
 #pragma unroll
     for (int k = 0; k < NG; k++) GCOL(GL.g_cmA, real, 1 + k) = xw[k];
   }
+  TSEC(2);
   if (NG > 0) grp_arrive(b);
+  TSEC(3);
   if (b.valid) {
     // ---- the regular edges need the cell's own state only: they run while the other CTAs arrive. Their share of dX
     // waits in the slot this evaluation will fill (its old content is dead), so that the gathers and the mixing run
     // with the flow sums as the only long-lived registers
     const float* mp = &GT(mpt0, b.lc * PP * G + b.u);  // parameters from facility 0 only (:48)
-    spec::flows_reg(y, alive, mp, d, FB, FE, bw, ew, out, (size_t)LG, st6);
+    spec::flows_reg(y, alive, mp, d, FBE, bwew, out, (size_t)LG, st6);
 #pragma unroll
     for (int k = 0; k < NG; k++) yc[k] = y[spec::ig_c0[k]];
 #pragma unroll
@@ -270,33 +290,33 @@ __device__ __forceinline__ void rhs(const DevPlan& P, Gx& b, bool dyn, double t,
     real rs[NG];
 #pragma unroll
     for (int k = 0; k < NG; k++) rs[k] = 0;
+    TSEC(4);
     grp_wait(b);
+    TSEC(5);
     // ---- pass 2: CSC gather over source locales (compute_foi_entry inner loop, :105-111) -> shared memory.
-    // Index lists from shared memory; four entries at a time: their values and gathered columns are in flight together
-    if (b.valid) {
+    // The CTA's rows are padded to a common length (ELL; padding gathers the own locale with weight 0): the source
+    // locale of (entry, locale) comes from shared memory, the weight of (entry, thread) from the CTA's global table,
+    // CH entries at a time with all their loads in flight together
+    const int jl = b.valid ? b.j - b.l0 : 0;
+    {
       real a = 0, xs[NG];
 #pragma unroll
       for (int k = 0; k < NG; k++) xs[k] = 0;
-      const real* cmA = (const real*)(b.gs + GL.g_cmA);
-      const int* cp = (const int*)(b.smem + GL.s_cscp);
-      const int* ci = (const int*)(b.smem + GL.s_csci);
-      const int jl = b.j - b.l0, qb = cp[jl], qe = cp[jl + 1];
-      const float* vp = P.mx_cscT + (size_t)__ldg(P.csc_indptr + b.l0) * G + b.u;
+      const real* cmA = (const real*)(b.gs + GL.g_cmA) + b.u;
+      const int* ei = (const int*)(b.smem + GL.s_eci) + jl;
+      const float* ev = (const float*)(b.cs + GL.c_evc) + b.tid;
+      const int nq = b.nq_w & 0xffff;
 #pragma unroll 1
-      for (int q0 = qb; q0 < qe; q0 += CH) {
-        int src[CH];
+      for (int q0 = 0; q0 < nq; q0 += CH) {
         real val[CH], g[CH][1 + NG];
 #pragma unroll
         for (int i = 0; i < CH; i++) {
-          const bool on = q0 + i < qe;
-          const int q = on ? q0 + i : qb;
-          src[i] = ci[q] * G + b.u;
-          val[i] = on ? (real)__ldg(vp + (size_t)q * G) : (real)0;
+          const int src = ei[(q0 + i) * spec::grp_lpc] * G;
+          val[i] = ev[(q0 + i) * GTH];
+#pragma unroll
+          for (int k = 0; k < 1 + NG; k++) g[i][k] = ldcg_ord(cmA + (size_t)k * LG + src);
         }
-#pragma unroll
-        for (int i = 0; i < CH; i++)
-#pragma unroll
-          for (int k = 0; k < 1 + NG; k++) g[i][k] = ldcg_ord(cmA + (size_t)k * LG + src[i]);
+        __syncwarp();
 #pragma unroll
         for (int i = 0; i < CH; i++) {
           a += g[i][0] * val[i];
@@ -308,6 +328,7 @@ __device__ __forceinline__ void rhs(const DevPlan& P, Gx& b, bool dyn, double t,
 #pragma unroll
       for (int k = 0; k < NG; k++) SCMB(1 + k, b.tid) = xs[k];
     }
+    TSEC(6);
     __syncthreads();
     // ---- pass 3: G x G facility mixing -> force of infection -> s[k] for (j, u0)  (:112-124, :146-157)
     if (b.valid) {
@@ -316,22 +337,26 @@ __device__ __forceinline__ void rhs(const DevPlan& P, Gx& b, bool dyn, double t,
       for (int k = 0; k < NG; k++) sk[k] = 0;
       const int row = b.tid - b.u;  // the locale's first column
       const float* Tn = &GT(Tnum, (b.lc * G + b.u) * GL.trow);
-      // the denominator's table: env-independent without FT ops (one padded copy in global memory, L1 / L2 hits),
-      // else this CTA's copy of the time-t table
-      const real* Td = (spec::has_ft_ops ? (const real*)(b.cs + GL.c_Tden) : (const real*)P.Tden_constP) + (b.lc * G + b.u) * GL.trow;
+      // the denominator's table: this CTA's time-t table with FT ops (global scratch); else env-independent: the
+      // shared-memory copy when the layout has one, or the padded copy in global memory (L1 / L2 hits)
+      const real* Td = (spec::has_ft_ops ? (const real*)(b.cs + GL.c_Tden)
+                        : spec::grp_tden_smem ? (const real*)(b.tab + GL.e_Tden) : (const real*)P.Tden_constP) +
+                       (b.lc * G + b.u) * GL.trow;
       constexpr int VH = (F % 4 == 0 && G % 4 == 0) ? 4 : 1;  // facilities per sweep over the locale's groups
 #pragma unroll 1
       for (int v0 = 0; v0 < F; v0 += VH) {
         real den[VH], num[NG][VH];
-#pragma unroll
-        for (int v = 0; v < VH; v++) {
-          den[v] = 0;
-#pragma unroll
-          for (int k = 0; k < NG; k++) num[k][v] = 0;
-        }
         if (G % 4 == 0) {
           // four groups of the locale at a time: their gathered columns in registers (128-bit broadcast reads),
-          // against VH rows of the cell's tables (128-bit reads, conflict-free over the locale's groups)
+          // against VH rows of the cell's tables (128-bit reads, conflict-free over the locale's groups); packed
+          // multiply-adds (FFMA2): even and odd groups accumulate in the two halves of a register pair
+          float2 den2[VH], num2[NG][VH];
+#pragma unroll
+          for (int v = 0; v < VH; v++) {
+            den2[v] = float2{0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < NG; k++) num2[k][v] = float2{0.f, 0.f};
+          }
 #pragma unroll 1
           for (int u4 = 0; u4 < G / 4; u4++) {
             float4 c4[1 + NG];
@@ -341,15 +366,28 @@ __device__ __forceinline__ void rhs(const DevPlan& P, Gx& b, bool dyn, double t,
             for (int v = 0; v < VH; v++) {
               const float4 tn = *(const float4*)(Tn + (v0 + v) * G + 4 * u4);
               const float4 td = *(const float4*)(Td + (v0 + v) * G + 4 * u4);
-              den[v] += c4[0].x * td.x; den[v] += c4[0].y * td.y; den[v] += c4[0].z * td.z; den[v] += c4[0].w * td.w;
+              den2[v] = ffma2(float2{c4[0].x, c4[0].y}, float2{td.x, td.y}, den2[v]);
+              den2[v] = ffma2(float2{c4[0].z, c4[0].w}, float2{td.z, td.w}, den2[v]);
 #pragma unroll
               for (int k = 0; k < NG; k++) {
-                num[k][v] += c4[1 + k].x * tn.x; num[k][v] += c4[1 + k].y * tn.y;
-                num[k][v] += c4[1 + k].z * tn.z; num[k][v] += c4[1 + k].w * tn.w;
+                num2[k][v] = ffma2(float2{c4[1 + k].x, c4[1 + k].y}, float2{tn.x, tn.y}, num2[k][v]);
+                num2[k][v] = ffma2(float2{c4[1 + k].z, c4[1 + k].w}, float2{tn.z, tn.w}, num2[k][v]);
               }
             }
           }
+#pragma unroll
+          for (int v = 0; v < VH; v++) {
+            den[v] = den2[v].x + den2[v].y;
+#pragma unroll
+            for (int k = 0; k < NG; k++) num[k][v] = num2[k][v].x + num2[k][v].y;
+          }
         } else {
+#pragma unroll
+          for (int v = 0; v < VH; v++) {
+            den[v] = 0;
+#pragma unroll
+            for (int k = 0; k < NG; k++) num[k][v] = 0;
+          }
 #pragma unroll 1
           for (int u = 0; u < G; u++) {
             real c1[1 + NG];
@@ -376,39 +414,39 @@ __device__ __forceinline__ void rhs(const DevPlan& P, Gx& b, bool dyn, double t,
 #pragma unroll
       for (int k = 0; k < NG; k++) GCOL(GL.g_cmS, real, k) = sk[k];
     }
+    TSEC(7);
     grp_sync(b);
+    TSEC(8);
     // ---- pass 4a: CSR gather over destination locales (:144-158), then the infectious flows
-    if (b.valid) {
-      const real* cmS = (const real*)(b.gs + GL.g_cmS);
-      const int* cp = (const int*)(b.smem + GL.s_csrp);
-      const int* ci = (const int*)(b.smem + GL.s_csri);
-      const int jl = b.j - b.l0, qb = cp[jl], qe = cp[jl + 1];
-      const float* vp = P.mx_csrT + (size_t)__ldg(P.csr_indptr + b.l0) * G + b.u;
+    {
+      const real* cmS = (const real*)(b.gs + GL.g_cmS) + b.u;
+      const int* ei = (const int*)(b.smem + GL.s_eri) + jl;
+      const float* ev = (const float*)(b.cs + GL.c_evr) + b.tid;
+      const int nq = b.nq_w >> 16;
 #pragma unroll 1
-      for (int q0 = qb; q0 < qe; q0 += CH) {
-        int dst[CH];
+      for (int q0 = 0; q0 < nq; q0 += CH) {
         real val[CH], g[CH][NG];
 #pragma unroll
         for (int i = 0; i < CH; i++) {
-          const bool on = q0 + i < qe;
-          const int q = on ? q0 + i : qb;
-          dst[i] = ci[q] * G + b.u;
-          val[i] = on ? (real)__ldg(vp + (size_t)q * G) : (real)0;
+          const int dst = ei[(q0 + i) * spec::grp_lpc] * G;
+          val[i] = ev[(q0 + i) * GTH];
+#pragma unroll
+          for (int k = 0; k < NG; k++) g[i][k] = ldcg_ord(cmS + (size_t)k * LG + dst);
         }
-#pragma unroll
-        for (int i = 0; i < CH; i++)
-#pragma unroll
-          for (int k = 0; k < NG; k++) g[i][k] = ldcg_ord(cmS + (size_t)k * LG + dst[i]);
+        __syncwarp();
 #pragma unroll
         for (int i = 0; i < CH; i++)
 #pragma unroll
           for (int k = 0; k < NG; k++) rs[k] += g[i][k] * val[i];
       }
+    }
+    if (b.valid) {
 #pragma unroll
       for (int k = 0; k < C; k++) d[k] = SK(kslot, k);
-      spec::flows_inf(yc, rs, d, FB, FE, bw, ew, out, (size_t)LG, st6);
+      spec::flows_inf(yc, rs, d, FBE, bwew, out, (size_t)LG, st6);
     }
   }
+  TSEC(9);
   // ---- pass 4b: clamped moves, the stage derivative
   if (b.valid) {
 #pragma unroll
@@ -430,13 +468,13 @@ __device__ __forceinline__ void rhs(const DevPlan& P, Gx& b, bool dyn, double t,
       } else if (spec::has_src64) {
         SKS(kslot, sl) = (double)d[c1];
       }
-      FB[nE + NG + sl] += bw * nv;
-      FE[nE + NG + sl] += ew * nv;
+      FBE[nE + NG + sl] = ffma2(float2{nv, nv}, bwew, FBE[nE + NG + sl]);
       if (st6) out[(size_t)(nE + NG + sl) * LG] = nv;
     }
 #pragma unroll
     for (int k = 0; k < C; k++) SK(kslot, k) = d[k];
   }
+  TSEC(0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -452,15 +490,16 @@ __device__ __forceinline__ int prologue(const DevPlan& P, Gx& b, int variant, do
   for (int k = 0; k < C; k++) x[k] = b.valid ? b.gX[(size_t)k * LG + b.cell] : 0.0;
   // 1. select sums (executor.py:346-359, ['Value'].sum()) and departing populations (executor.py:181-183)
   double* part = (double*)(b.gs + GL.g_part) + (size_t)b.parity * GSS * GL.np;
+  const int2* selinfo = (const int2*)(b.tab + GL.e_selinfo);  // (compartment mask, mode) per select, cached per kernel
   for (int s = 0; s < P.n_sel; s++) {
     double v = 0;
-    const int mode = P.sel_mode[s];
-    if (b.valid && P.sel_l[s * L + b.j] && P.sel_g[s * G + b.u]) {
+    if ((b.selmask >> s) & 1u) {
+      const int2 si = selinfo[s];
 #pragma unroll
       for (int k = 0; k < C; k++)
-        if (P.sel_c[s * C + k]) {
-          if (mode == 0) v += x[k];
-          else if (mode == 1) v += P.X0[(size_t)k * LG + b.cell];
+        if ((si.x >> k) & 1) {
+          if (si.y == 0) v += x[k];
+          else if (si.y == 1) v += P.X0[(size_t)k * LG + b.cell];
           else v += x[k] - Xprev_g[(size_t)P.chg_slot_of_comp[k] * LG + b.cell];
         }
     }
@@ -469,7 +508,7 @@ __device__ __forceinline__ int prologue(const DevPlan& P, Gx& b, int variant, do
   }
   for (int mo = 0; mo < P.n_mv_op; mo++) {
     double v = 0;
-    if (b.valid && P.mv_g[mo * G + b.u] && P.mv_l1[mo * L + b.j])
+    if ((b.mvmask >> mo) & 1u)
       for (int q = P.mv_c1_off[mo]; q < P.mv_c1_off[mo + 1]; q++) {
         const int c1 = P.mv_c1[q];
 #pragma unroll
@@ -585,7 +624,7 @@ __device__ __forceinline__ int prologue(const DevPlan& P, Gx& b, int variant, do
     const double depart_sum = dep[mo];
     if (live && depart_sum > 0) {
       double value = GT(expr, P.op_expr[o]);
-      if (b.valid && P.mv_g[mo * G + b.u] && P.mv_l1[mo * L + b.j]) {
+      if ((b.mvmask >> mo) & 1u) {
         auto xv = [&](int c) {
           double r = 0;
 #pragma unroll
@@ -645,9 +684,9 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, Gx& b, bool dyn, int 
   auto qd = [](double tt) { return (double)(float)((-3.0 * tt + 4.0) * tt); };
   auto centry = [&](int q) { return (size_t)(q / b.nl) * L + b.l0 + q % b.nl; };
   // the packed flow sums of the current attempt live in registers for the whole day
-  real FB[NSRC], FE[NSRC];
+  float2 FBE[NSRC];  // (.x, .y) = (FB, FE): one packed multiply-add (FFMA2) updates both
 #pragma unroll
-  for (int i = 0; i < NSRC; i++) FB[i] = FE[i] = 0;
+  for (int i = 0; i < NSRC; i++) FBE[i] = float2{0.f, 0.f};
   const real* fl6 = (const real*)(b.gs + GL.g_fl6) + b.cell;
 
   int phase = 0;
@@ -677,26 +716,27 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, Gx& b, bool dyn, int 
     if (phase == 0) {
       bw = 0; ew = 1;
 #pragma unroll
-      for (int i = 0; i < NSRC; i++) FE[i] = 0;
+      for (int i = 0; i < NSRC; i++) FBE[i].y = 0;
     } else if (phase == 1) {
       bw = 1; ew = 0;
 #pragma unroll
-      for (int i = 0; i < NSRC; i++) FB[i] = 0;
+      for (int i = 0; i < NSRC; i++) FBE[i].x = 0;
     } else if (phase == 8) {
 #pragma unroll
-      for (int i = 0; i < NSRC; i++) FB[i] = FE[i] = 0;
+      for (int i = 0; i < NSRC; i++) FBE[i] = float2{0.f, 0.f};
     }
     if (phase == 0 && skip0) {
       // f(0, y0) of this day is the previous day's last stage (same state, same parameters): its derivatives sit in
       // slot s0 already, its flows in the last-stage column
       if (b.valid) {
 #pragma unroll
-        for (int i = 0; i < NSRC; i++) FE[i] = fl6[(size_t)i * LG];
+        for (int i = 0; i < NSRC; i++) FBE[i].y = fl6[(size_t)i * LG];
       }
     } else {
-      rhs(P, b, dyn, t_eval, ex_bits, phase, stage, bw, ew, phase == 7, hh, nj, FB, FE);
+      rhs(P, b, dyn, t_eval, ex_bits, phase, stage, bw, ew, phase == 7, hh, nj, FBE);
     }
     if (phase == 0) {
+      TSEC(11);
       // select_initial_step (common.py:68-134), first half
       double s01[2] = {0, 0};
       if (b.valid) {
@@ -711,7 +751,7 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, Gx& b, bool dyn, int 
         for (int a_ = 0; a_ < n_acc; a_++) {
           real g0 = 0;
 #pragma unroll
-          for (int q = spec::ag_off[a_]; q < spec::ag_off[a_ + 1]; q++) g0 += FE[spec::ag_src[q]] * (real)spec::ag_coef[q];
+          for (int q = spec::ag_off[a_]; q < spec::ag_off[a_ + 1]; q++) g0 += FBE[spec::ag_src[q]].y * (real)spec::ag_coef[q];
           real yv = b.acc[(size_t)a_ * LG + b.cell], sc = atolr + fabs(yv) * rtolr;
           real a = fdiv(yv, sc), bq = fdiv(g0, sc);
           a0 += a * a; a1 += bq * bq;
@@ -724,7 +764,9 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, Gx& b, bool dyn, int 
         double a = norm_term(real(0), yv, sc), bq = norm_term(real(0), b.crY[i], sc);  // q(0) = 0
         s01[0] += a * a; s01[1] += bq * bq;
       }
+      TSEC(10);
       grp_sum<2>(P, b, s01);
+      TSEC(0);
       d0 = ctrl_sqrt(real(0), s01[0] * inv_n);
       d1 = ctrl_sqrt(real(0), s01[1] * inv_n);
       h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
@@ -732,6 +774,7 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, Gx& b, bool dyn, int 
       nfev++;
       phase = 1;
     } else if (phase == 1) {
+      TSEC(11);
       double s2[1] = {0};
       const double q0 = qd(h0);
       if (b.valid) {
@@ -747,7 +790,7 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, Gx& b, bool dyn, int 
           real g = 0;
 #pragma unroll
           for (int q = spec::ag_off[a_]; q < spec::ag_off[a_ + 1]; q++)
-            g += (FB[spec::ag_src[q]] - FE[spec::ag_src[q]]) * (real)spec::ag_coef[q];
+            g += (FBE[spec::ag_src[q]].x - FBE[spec::ag_src[q]].y) * (real)spec::ag_coef[q];
           real sc = atolr + fabs(b.acc[(size_t)a_ * LG + b.cell]) * rtolr;
           real a = fdiv(g, sc);
           a2 += a * a;
@@ -757,16 +800,17 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, Gx& b, bool dyn, int 
       // stage-0 contributions of the first attempt
 #pragma unroll
       for (int i = 0; i < NSRC; i++) {
-        const real f = FE[i];
-        FB[i] = rkB(real(0), 0) * f;
-        FE[i] = rkE(real(0), 0) * f;
+        const real f = FBE[i].y;
+        FBE[i] = float2{rkB(real(0), 0) * f, rkE(real(0), 0) * f};
       }
       for (int q = b.tid; q < nCl; q += b.T) {
         const size_t i = centry(q);
         double sc = atol + fabs(b.cost[i]) * rtol, a = norm_term(real(0), (b.crD[i] - b.crY[i]) * q0, sc);
         s2[0] += a * a;
       }
+      TSEC(10);
       grp_sum<1>(P, b, s2);
+      TSEC(0);
       double d2 = ctrl_sqrt(real(0), s2[0] * inv_n) / h0;
       double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : ctrl_pow(real(0), 0.01 / fmax(d1, d2), 0.2);
       h_abs = fmin(fmin(100 * h0, h1), 1.0);
@@ -775,6 +819,7 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, Gx& b, bool dyn, int 
     } else if (phase < 7) {
       phase++;
     } else if (phase == 7) {
+      TSEC(11);
       // error norm over ALL n_flat components (common.py:63-65, rk.py:146-148), accept / reject
       double e2[1] = {0}, qs[7];
       nfev += 6;
@@ -803,8 +848,8 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, Gx& b, bool dyn, int 
           real vB = 0, vE = 0;
 #pragma unroll
           for (int q = spec::ag_off[a_]; q < spec::ag_off[a_ + 1]; q++) {
-            vB += FB[spec::ag_src[q]] * (real)spec::ag_coef[q];
-            vE += FE[spec::ag_src[q]] * (real)spec::ag_coef[q];
+            vB += FBE[spec::ag_src[q]].x * (real)spec::ag_coef[q];
+            vE += FBE[spec::ag_src[q]].y * (real)spec::ag_coef[q];
           }
           real yv = b.acc[(size_t)a_ * LG + b.cell], yn = yv + (real)h * vB;
           real sc = atolr + fmax(fabs(yv), fabs(yn)) * rtolr, a = fdiv(vE * (real)h, sc);
@@ -828,7 +873,9 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, Gx& b, bool dyn, int 
         double sc = atol + fmax(fabs(yv), fabs(yn)) * rtol, a = norm_term(real(0), se * h, sc);
         e2[0] += a * a;
       }
+      TSEC(10);
       grp_sum<1>(P, b, e2);
+      TSEC(0);
       double err = ctrl_sqrt(real(0), e2[0] * inv_n);
       last_err = err;
       if (dbg && b.tid == 0 && b.cta == 0 && n_att < 64) { dbg[2 * n_att] = h; dbg[2 * n_att + 1] = err; }
@@ -845,6 +892,7 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, Gx& b, bool dyn, int 
         nrej++;
       }
       if (accepted) {
+        TSEC(12);
         // commit: y = y_new, f = f_new (the state is advanced in double in both modes)
         if (b.valid) {
           double xs[nS > 0 ? nS : 1];
@@ -872,8 +920,7 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, Gx& b, bool dyn, int 
 #pragma unroll
           for (int i = 0; i < NSRC; i++) {
             const real f = fl6[(size_t)i * LG];
-            FB[i] = rkB(real(0), 0) * f;
-            FE[i] = rkE(real(0), 0) * f;
+            FBE[i] = float2{rkB(real(0), 0) * f, rkE(real(0), 0) * f};
           }
         }
         for (int q = b.tid; q < nCl; q += b.T) {
@@ -891,6 +938,7 @@ __device__ __forceinline__ bool rk45_day(const DevPlan& P, Gx& b, bool dyn, int 
           const int s_ = b.s0; b.s0 = b.s1; b.s1 = s_;
           real* t_ = b.acc; b.acc = b.accn; b.accn = t_;
         }
+        TSEC(0);
         phase = run ? 2 : -1;
       } else {
         phase = 8;  // restore the stage-0 terms of the flow sums by re-evaluating f(t, y) (not counted in nfev)
@@ -914,13 +962,55 @@ __device__ __forceinline__ void step_group(const DevPlan& P, const DevState& S, 
   constexpr int C = spec::C, CLG = spec::CLG, LG = spec::LG, L = spec::L, G = spec::G, F = spec::F, nC = spec::I * spec::L;
   const size_t nA = (size_t)spec::n_acc * LG, nM = (size_t)spec::n_slot * LG;
   {
-    // the CSC / CSR index lists of this CTA's locales (static), offsets relative to the first locale's row
-    int* cp = (int*)(b.smem + GL.s_cscp); int* ci = (int*)(b.smem + GL.s_csci);
-    int* rp = (int*)(b.smem + GL.s_csrp); int* ri = (int*)(b.smem + GL.s_csri);
-    const int cb = P.csc_indptr[b.l0], rb = P.csr_indptr[b.l0];
-    for (int i = b.tid; i <= b.nl; i += b.T) { cp[i] = P.csc_indptr[b.l0 + i] - cb; rp[i] = P.csr_indptr[b.l0 + i] - rb; }
-    for (int i = b.tid; i < P.csc_indptr[b.l0 + b.nl] - cb; i += b.T) ci[i] = P.csc_indices[cb + i];
-    for (int i = b.tid; i < P.csr_indptr[b.l0 + b.nl] - rb; i += b.T) ri[i] = P.csr_indices[rb + i];
+    // the CSC / CSR rows of this CTA's locales in padded (ELL) form, built once per kernel: source / destination
+    // locale of (entry q, locale) in shared memory, mobility value of (entry q, thread) in the CTA's global scratch;
+    // padding entries point at the own locale with weight 0
+    int* eci = (int*)(b.smem + GL.s_eci); int* eri = (int*)(b.smem + GL.s_eri);
+    float* evc = (float*)(b.cs + GL.c_evc); float* evr = (float*)(b.cs + GL.c_evr);
+    for (int i = b.tid; i < spec::grp_nqc * spec::grp_lpc; i += b.T) {
+      const int q = i / spec::grp_lpc, jl = i - q * spec::grp_lpc, j = jl < b.nl ? b.l0 + jl : b.l0;
+      const int beg = P.csc_indptr[j], len = jl < b.nl ? P.csc_indptr[j + 1] - beg : 0;
+      eci[i] = q < len ? P.csc_indices[beg + q] : j;
+    }
+    for (int i = b.tid; i < spec::grp_nqr * spec::grp_lpc; i += b.T) {
+      const int q = i / spec::grp_lpc, jl = i - q * spec::grp_lpc, j = jl < b.nl ? b.l0 + jl : b.l0;
+      const int beg = P.csr_indptr[j], len = jl < b.nl ? P.csr_indptr[j + 1] - beg : 0;
+      eri[i] = q < len ? P.csr_indices[beg + q] : j;
+    }
+    {
+      const int cb = P.csc_indptr[b.j], cl = b.valid ? P.csc_indptr[b.j + 1] - cb : 0;
+      for (int q = 0; q < spec::grp_nqc; q++) evc[q * GTH + b.tid] = q < cl ? P.mx_cscT[(size_t)(cb + q) * spec::G + b.u] : 0.0f;
+      const int rb = P.csr_indptr[b.j], rl = b.valid ? P.csr_indptr[b.j + 1] - rb : 0;
+      for (int q = 0; q < spec::grp_nqr; q++) evr[q * GTH + b.tid] = q < rl ? P.mx_csrT[(size_t)(rb + q) * spec::G + b.u] : 0.0f;
+    }
+    {
+      // entries (a multiple of the chunk) that cover the longest CSC / CSR row among this WARP's cells
+      int mc = b.valid ? P.csc_indptr[b.j + 1] - P.csc_indptr[b.j] : 0, mr = b.valid ? P.csr_indptr[b.j + 1] - P.csr_indptr[b.j] : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const int oc = __shfl_xor_sync(0xffffffffu, mc, o), orr = __shfl_xor_sync(0xffffffffu, mr, o);
+        mc = oc > mc ? oc : mc; mr = orr > mr ? orr : mr;
+      }
+      mc = (mc + EPI_GRP_CHUNK - 1) / EPI_GRP_CHUNK * EPI_GRP_CHUNK;
+      mr = (mr + EPI_GRP_CHUNK - 1) / EPI_GRP_CHUNK * EPI_GRP_CHUNK;
+      b.nq_w = mc | (mr << 16);
+    }
+    // selects / MOVE ops covering this thread's cell, and each select's compartment mask and mode
+    b.selmask = b.mvmask = 0;
+    if (b.valid) {
+      for (int s_ = 0; s_ < P.n_sel; s_++)
+        if (P.sel_l[s_ * spec::L + b.j] && P.sel_g[s_ * spec::G + b.u]) b.selmask |= 1u << s_;
+      for (int mo = 0; mo < P.n_mv_op; mo++)
+        if (P.mv_g[mo * spec::G + b.u] && P.mv_l1[mo * spec::L + b.j]) b.mvmask |= 1u << mo;
+    }
+    for (int s_ = b.tid; s_ < P.n_sel; s_ += b.T) {
+      int cm = 0;
+      for (int k = 0; k < spec::C; k++) cm |= P.sel_c[s_ * spec::C + k] ? 1 << k : 0;
+      ((int2*)(b.tab + GL.e_selinfo))[s_] = int2{cm, P.sel_mode[s_]};
+    }
+    if (!spec::has_ft_ops && spec::grp_tden_smem)
+      for (int i = b.tid; i < spec::n_lc * spec::G * GL.trow; i += b.T) ((real*)(b.tab + GL.e_Tden))[i] = (real)__ldg(P.Tden_constP + i);
+    __syncthreads();
   }
   b.crD = (double*)(b.gs + GL.g_crD);
   b.mvD = (float*)(b.gs + GL.g_mvD);
@@ -959,7 +1049,9 @@ __device__ __forceinline__ void step_group(const DevPlan& P, const DevState& S, 
     const int nCl = spec::I * b.nl;
     for (int day = 0; day < n_days; day++) {
       bool dyn = true;
+      TSEC(14);
       int ex_bits = prologue(P, b, a.variant, gXprev, ex_y, dyn, tabs_current);
+      TSEC(0);
       if (!a.init_only) {
         double c0 = 0, c1 = 0;
         for (int q = b.tid; q < nCl; q += b.T) c0 += b.cost[(size_t)(q / b.nl) * L + b.l0 + q % b.nl];
@@ -984,7 +1076,9 @@ __device__ __forceinline__ void step_group(const DevPlan& P, const DevState& S, 
       if (t_day >= P.horizon) break;  // the reference's EpiEnv.step stops its day loop at done
     }
     double rw[1] = {reward};
+    TSEC(10);
     grp_sum<1>(P, b, rw);
+    TSEC(0);
     if (b.valid) {
 #pragma unroll
       for (int k = 0; k < C; k++) {
@@ -1055,7 +1149,7 @@ __global__ void __maxnreg__(EPI_GRP_MAXREG) grp_kernel(const DevPlan P, const De
     __shared__ int s_vb;
     if (threadIdx.x == 0) s_vb = blockIdx.x;
     // (a launch with fewer groups than the device holds leaves SMs half empty: any numbering will do)
-    if (threadIdx.x == 0 && (int)gridDim.x == GL.n_groups * GSS) {
+    if (threadIdx.x == 0 && GL.dyn_assign && (int)gridDim.x == GL.n_groups * GSS) {
       const int n_groups = gridDim.x / GSS, per_class = gridDim.x / EPI_GRP_R;
       unsigned* ctr = a.grp_bar + (size_t)32 * n_groups;
       unsigned smid;
@@ -1069,7 +1163,21 @@ __global__ void __maxnreg__(EPI_GRP_MAXREG) grp_kernel(const DevPlan P, const De
   }
 #endif
   Gx b = bind(P, a, grp_smem, threadIdx.x, blockDim.x, vb);
+#ifdef EPI_GRP_TIMING
+  __shared__ long long s_tacc[16];
+  b.tacc = s_tacc; b.tlast = clock64(); b.tcur = 0;
+  if (threadIdx.x == 0) for (int i = 0; i < 16; i++) s_tacc[i] = 0;
+  __syncthreads();
+#endif
   step_group(P, S, a, b, vb / GSS, gridDim.x / GSS);
+#ifdef EPI_GRP_TIMING
+  TSEC(0);
+  if (threadIdx.x == 0 && (vb == 0 || vb == 5)) {
+    printf("grp timing cta %d:", vb);
+    for (int i = 0; i < 15; i++) printf(" s%d=%.3fms", i, (double)b.tacc[i] / 1.9e6);
+    printf("\n");
+  }
+#endif
 }
 #endif
 

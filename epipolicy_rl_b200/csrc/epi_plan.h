@@ -54,12 +54,14 @@ struct GrpLayout {
   int lpc;  // locales per CTA (upper bound; CTA c owns locales [c*L/S, (c+1)*L/S))
   int np;   // doubles per CTA and parity in the reduction-partials array
   int trow; // row stride (floats) of the mixing tables T[lc][u0][v][u] (F*G padded against bank conflicts)
-  int64_t s_K, s_KS, s_cmB, s_red, s_cscp, s_csci, s_csrp, s_csri, s_XF, s_tab, smem_bytes;
+  int64_t s_K, s_KS, s_cmB, s_red, s_eci, s_eri, s_XF, s_tab, smem_bytes;
+  int dyn_assign;  // R > 1 and the grid fills every SM exactly R times: CTAs pick their group by arrival order per SM
+  int tden_smem;   // the denominator's mixing table has a copy in shared memory (else it is read from global memory)
   int xf_smem;  // the float copy of the state lives in shared memory (else in the group scratch)
-  int cap_csc, cap_csr;  // most CSC / CSR entries any CTA's locales own
-  int64_t e_mult_y, e_mult_d, e_cpv, e_act, e_expr, e_sel, e_mpt0, e_coefS, e_Tnum, e_ft_y, e_ft_gap, tab_bytes;
+  int nqc, nqr;  // longest CSC / CSR row, rounded up to the gather chunk: rows are padded to it (ELL layout per CTA)
+  int64_t e_mult_y, e_mult_d, e_cpv, e_act, e_expr, e_sel, e_mpt0, e_coefS, e_Tnum, e_Tden, e_ft_y, e_ft_gap, e_selinfo, tab_bytes;
   int64_t g_XF, g_cmA, g_cmS, g_fl6, g_accN, g_mvD, g_crD, g_part, g_bytes;  // per group
-  int64_t c_fi_y, c_fi_gap, c_mpy, c_mpg, c_mpFy, c_mpFg, c_Tden, c_bytes;  // per CTA (tables only the day prologue / a dyn day reads)
+  int64_t c_fi_y, c_fi_gap, c_mpy, c_mpg, c_mpFy, c_mpFg, c_Tden, c_evc, c_evr, c_bytes;  // per CTA (tables only the day prologue / a dyn day reads)
 };
 
 struct DevPlan {

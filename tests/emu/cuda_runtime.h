@@ -26,6 +26,8 @@
 
 struct EmuDim3 { int x = 0, y = 0, z = 0; };
 struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(8) float2 { float x, y; };
+struct alignas(8) int2 { int x, y; };
 static EmuDim3 threadIdx, blockIdx;
 static EmuDim3 blockDim{1, 1, 1}, gridDim{1, 1, 1};
 
