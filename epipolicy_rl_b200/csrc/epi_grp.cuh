@@ -38,6 +38,11 @@ typedef spec::real real;
 #endif
 // entries of a cell's CSC / CSR row gathered together (their loads are in flight at the same time): 8 where the
 // register budget allows it (<= 12 resident warps per SM), else 4
+// two locales per half-warp in the mixing pass (half the table traffic, twice the accumulators): needs the 168-register
+// budget of <= 12 resident warps per SM
+#ifndef EPI_GRP_MIX2
+#define EPI_GRP_MIX2 ((EPI_GRP_R * (EPI_GRP_THREADS / 32)) <= 12)
+#endif
 #ifndef EPI_GRP_CHUNK
 #define EPI_GRP_CHUNK ((EPI_GRP_R * (EPI_GRP_THREADS / 32)) <= 12 ? 8 : 4)
 #endif
@@ -331,7 +336,82 @@ __device__ __forceinline__ void rhs(const DevPlan& P, Gx& b, bool dyn, double t,
     TSEC(6);
     __syncthreads();
     // ---- pass 3: G x G facility mixing -> force of infection -> s[k] for (j, u0)  (:112-124, :146-157)
-    if (b.valid) {
+    // Every cell needs the whole table row of its group (F x G values of Tnum and of Tden): read per cell, the tables
+    // cross the shared-memory port once per locale and the pass is bound by it. With G == 16 a warp holds two locales
+    // (lanes 0-15 / 16-31): each half-warp instead takes HALF of the facilities for BOTH locales, so every table value
+    // read feeds two cells; the two halves exchange their partial sums with one shuffle per infectious group.
+    if (G == 16 && F % 2 == 0 && GTH % 32 == 0 && EPI_GRP_MIX2) {
+      constexpr int FH = F / 2;
+      const int lane = b.tid & 31, half = lane >> 4, u0 = lane & 15;
+      const int rowA = (b.tid & ~31), rowB = rowA + 16;           // first column of the warp's two locales
+      // (tables are per locale class; both locales of a warp almost always share it, the general case reads both rows)
+      const int lca = __shfl_sync(0xffffffffu, b.lc, 0), lcb = __shfl_sync(0xffffffffu, b.lc, 16);
+      const float* TnA = &GT(Tnum, (lca * G + u0) * GL.trow) + half * FH * G;
+      const float* TnB = &GT(Tnum, (lcb * G + u0) * GL.trow) + half * FH * G;
+      const real* TdBase = (spec::has_ft_ops ? (const real*)(b.cs + GL.c_Tden)
+                            : spec::grp_tden_smem ? (const real*)(b.tab + GL.e_Tden) : (const real*)P.Tden_constP);
+      const real* TdA = TdBase + (lca * G + u0) * GL.trow + half * FH * G;
+      const real* TdB = TdBase + (lcb * G + u0) * GL.trow + half * FH * G;
+      const bool same = lca == lcb;
+      float2 denA[FH], denB[FH], numA[NG][FH], numB[NG][FH];
+#pragma unroll
+      for (int v = 0; v < FH; v++) {
+        denA[v] = denB[v] = float2{0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < NG; k++) numA[k][v] = numB[k][v] = float2{0.f, 0.f};
+      }
+#pragma unroll 1
+      for (int u4 = 0; u4 < G / 4; u4++) {
+        float4 cA[1 + NG], cB[1 + NG];
+#pragma unroll
+        for (int k = 0; k < 1 + NG; k++) {
+          cA[k] = *(const float4*)&SCMB(k, rowA + 4 * u4);
+          cB[k] = *(const float4*)&SCMB(k, rowB + 4 * u4);
+        }
+#pragma unroll
+        for (int v = 0; v < FH; v++) {
+          const float4 tn = *(const float4*)(TnA + v * G + 4 * u4);
+          const float4 td = *(const float4*)(TdA + v * G + 4 * u4);
+          const float4 tnb = same ? tn : *(const float4*)(TnB + v * G + 4 * u4);
+          const float4 tdb = same ? td : *(const float4*)(TdB + v * G + 4 * u4);
+          denA[v] = ffma2(float2{cA[0].x, cA[0].y}, float2{td.x, td.y}, denA[v]);
+          denA[v] = ffma2(float2{cA[0].z, cA[0].w}, float2{td.z, td.w}, denA[v]);
+          denB[v] = ffma2(float2{cB[0].x, cB[0].y}, float2{tdb.x, tdb.y}, denB[v]);
+          denB[v] = ffma2(float2{cB[0].z, cB[0].w}, float2{tdb.z, tdb.w}, denB[v]);
+#pragma unroll
+          for (int k = 0; k < NG; k++) {
+            numA[k][v] = ffma2(float2{cA[1 + k].x, cA[1 + k].y}, float2{tn.x, tn.y}, numA[k][v]);
+            numA[k][v] = ffma2(float2{cA[1 + k].z, cA[1 + k].w}, float2{tn.z, tn.w}, numA[k][v]);
+            numB[k][v] = ffma2(float2{cB[1 + k].x, cB[1 + k].y}, float2{tnb.x, tnb.y}, numB[k][v]);
+            numB[k][v] = ffma2(float2{cB[1 + k].z, cB[1 + k].w}, float2{tnb.z, tnb.w}, numB[k][v]);
+          }
+        }
+      }
+      real skA[NG], skB[NG];
+#pragma unroll
+      for (int k = 0; k < NG; k++) skA[k] = skB[k] = 0;
+#pragma unroll
+      for (int v = 0; v < FH; v++) {
+        real dA = denA[v].x + denA[v].y, dB = denB[v].x + denB[v].y;
+        if (dA <= (real)1e-15) dA = 1;
+        if (dB <= (real)1e-15) dB = 1;
+        const real rA = frcp(dA), rB = frcp(dB);
+#pragma unroll
+        for (int k = 0; k < NG; k++) {
+          skA[k] += GT(coefS, ((k * n_lc + lca) * F + half * FH + v) * G + u0) * ((numA[k][v].x + numA[k][v].y) * rA);
+          skB[k] += GT(coefS, ((k * n_lc + lcb) * F + half * FH + v) * G + u0) * ((numB[k][v].x + numB[k][v].y) * rB);
+        }
+      }
+      // lanes 0-15 own locale A's cells, lanes 16-31 locale B's: each sends the other half's partial and keeps its own
+#pragma unroll
+      for (int k = 0; k < NG; k++) {
+        const real mine = half ? skB[k] : skA[k], theirs = half ? skA[k] : skB[k];
+        const real got = __shfl_xor_sync(0xffffffffu, theirs, 16);
+        // facilities in a fixed order: the lower half first
+        const real sk = half ? got + mine : mine + got;
+        if (b.valid) GCOL(GL.g_cmS, real, k) = sk;
+      }
+    } else if (b.valid) {
       real sk[NG];
 #pragma unroll
       for (int k = 0; k < NG; k++) sk[k] = 0;
@@ -520,11 +600,20 @@ __device__ __forceinline__ int prologue(const DevPlan& P, Gx& b, int variant, do
   }
   grp_sync(b);
   double* dep = (double*)(b.smem + GL.s_red) + 32;  // departing populations, [n_mv_op]
-  for (int i = b.tid; i < P.n_sel + P.n_mv_op; i += b.T) {
+  // one warp per total: the lanes fetch the S partials together (one L2 round trip instead of S), the butterfly adds
+  // them the same way in every CTA
+  for (int i0 = 0; i0 < P.n_sel + P.n_mv_op; i0 += GTH >> 5) {
+    const int i = i0 + (b.tid >> 5), lane = b.tid & 31;
+    const bool on = i < P.n_sel + P.n_mv_op;
     double r = 0;
-    for (int c = 0; c < b.S; c++) r += ldcg(part + (size_t)c * GL.np + i);
-    if (i < P.n_sel) GT(sel, i) = r;
-    else dep[i - P.n_sel] = r;
+#pragma unroll
+    for (int c0 = 0; c0 < GSS; c0 += 32)
+      if (on && c0 + lane < GSS) r += ldcg(part + (size_t)(c0 + lane) * GL.np + i);
+    r = warp_sum(r);
+    if (on && lane == 0) {
+      if (i < P.n_sel) GT(sel, i) = r;
+      else dep[i - P.n_sel] = r;
+    }
   }
   b.parity ^= 1;
   __syncthreads();

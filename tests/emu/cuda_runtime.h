@@ -67,6 +67,18 @@ template <class T> inline T __shfl_xor_sync(unsigned, T v, int m) {
   pthread_barrier_wait(emu::warp_barrier);
   return r;
 }
+template <class T> inline T __shfl_sync(unsigned, T v, int src) {
+  if (!emu::warp_barrier || !emu::xchg_buf) return v;
+  unsigned long long w = 0;
+  memcpy(&w, &v, sizeof(T));
+  emu::xchg_buf[emu::lane_id] = w;
+  pthread_barrier_wait(emu::warp_barrier);
+  const int partner = (emu::lane_id & ~31) + src;
+  T r = v;
+  if (partner < emu::warp_width) { unsigned long long x = emu::xchg_buf[partner]; memcpy(&r, &x, sizeof(T)); }
+  pthread_barrier_wait(emu::warp_barrier);
+  return r;
+}
 inline int __any_sync(unsigned, int pred) {
   if (!emu::warp_barrier) return pred;
   emu::vote_buf[emu::lane_id] = pred;
