@@ -51,6 +51,9 @@ struct HostTabs {
   std::vector<float> ep_coef, xg_coef, ag_coef;
   std::vector<int> comp_role;
   std::vector<int> csr_indptr, csc_indptr;
+  // per-locale-class default parameters and multiplier classes (epi_get_plan: the reporter rebuilds a day's parameters)
+  std::vector<int> lclass, mp_cls, ft_cls;
+  std::vector<float> mp0, ft0;
   // prologue tables for the generator
   std::vector<uint8_t> sel_c, sel_l, sel_g;
   std::vector<int> sel_mode, chg_slot, selc_off, selc, cls_off, cls_op, op_expr, expr_off, tok_op, tok_arg, tok_f32;
@@ -573,6 +576,7 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
   std::vector<uint8_t> dummy8(1, 0);
   P.alive_coef = h->up(vec(d.alive_coef, C)); P.X0 = h->up(vec(d.X0, (size_t)C * LG)); P.lclass = h->up(lclass);
   P.mp0 = h->up(mp0); P.ft0 = h->up(ft0); P.fi0 = h->up(fi0); P.mp_cls = h->up(mp_cls); P.ft_cls = h->up(ft_cls); P.fi_cls = h->up(fi_cls);
+  h->tabs.lclass = lclass; h->tabs.mp_cls = mp_cls; h->tabs.ft_cls = ft_cls; h->tabs.mp0 = mp0; h->tabs.ft0 = ft0;
   {
     std::vector<float> tdT(tden.size());
     std::vector<double> td64T(tden64.size());
@@ -1823,6 +1827,45 @@ int epi_set_state(epi_t* h, int what, const void* in, size_t bytes) {
       case 7: need(N * P.n_cls * 4); CK(cudaMemcpy(h->S.multY, in, bytes, cudaMemcpyHostToDevice)); break;
       case 8: need(N * P.n_slot * (size_t)P.LG * 4); if (bytes) CK(cudaMemcpy(h->S.mvY, in, bytes, cudaMemcpyHostToDevice)); break;
       default: throw Invalid{"state selector not settable"};
+    }
+  });
+}
+
+int epi_get_state_dev(epi_t* h, int what, void* out_dev, size_t bytes, void* cuda_stream) {
+  if (!h || !out_dev) return EPI_E_INVALID;
+  return guarded(h, [&] {
+    CK(cudaSetDevice(h->device));
+    const DevPlan& P = h->plan;
+    const size_t N = h->N, rs = h->real_size(), LG = P.LG, nC = (size_t)P.I * P.L;
+    auto need = [&](size_t n) { if (bytes != n) throw Invalid{"buffer size mismatch: expected " + std::to_string(n) + " bytes"}; };
+    const void* src = nullptr;
+    switch (what) {
+      case 0: need(N * P.CLG * 8); src = h->S.X; break;
+      case 1: need(N * nC * 8); src = h->S.cost; break;
+      case 7: need(N * P.n_cls * 4); src = h->S.multY; break;
+      case 10: need(N * P.n_acc * LG * rs); src = h->S.acc; break;
+      default: throw Invalid{"state selector has no device copy"};
+    }
+    if (bytes) CK(cudaMemcpyAsync(out_dev, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)cuda_stream));
+  });
+}
+
+int epi_get_plan(const epi_t* h, int what, void* out_host, size_t bytes) {
+  if (!h || !out_host) return EPI_E_INVALID;
+  return guarded(h, [&] {
+    const HostTabs& T = h->tabs;
+    auto put = [&](const void* p, size_t n) {
+      if (bytes != n) throw Invalid{"buffer size mismatch: expected " + std::to_string(n) + " bytes"};
+      memcpy(out_host, p, n);
+    };
+    switch (what) {
+      case 0: put(h->acc_flat_host.data(), h->acc_flat_host.size() * 4); break;
+      case 1: put(T.lclass.data(), T.lclass.size() * 4); break;
+      case 2: put(T.mp0.data(), T.mp0.size() * 4); break;
+      case 3: put(T.mp_cls.data(), T.mp_cls.size() * 4); break;
+      case 4: put(T.ft0.data(), T.ft0.size() * 4); break;
+      case 5: put(T.ft_cls.data(), T.ft_cls.size() * 4); break;
+      default: throw Invalid{"unknown plan table"};
     }
   });
 }

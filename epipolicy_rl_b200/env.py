@@ -4,6 +4,7 @@
                   reference class, one environment, float64 numpy observations (so SB3's
                   DummyVecEnv/Monitor, baselines.py and plots.py can use it unchanged).
 `BatchedEpiEnv` — N environments stepped by one fused launch; torch CUDA tensors in and out.
+`EpiVecEnv`     — the batched environment behind stable-baselines3's VecEnv surface (numpy, auto-reset).
 
 Construction takes either an `EpiDesc` (no reference needed at run time) or a reference session dict
 (then the reference's own parser / make_static build the Static and export.py flattens it).
@@ -66,6 +67,96 @@ class BatchedEpiEnv:
 
     def close(self):
         self.epi.close()
+
+
+try:  # pragma: no cover - stable_baselines3 is not in this image; with it the adapter below is a real VecEnv
+    from stable_baselines3.common.vec_env import VecEnv as _VecEnvBase
+except Exception:  # noqa: BLE001
+    _VecEnvBase = object
+
+
+class EpiVecEnv(_VecEnvBase):
+    """The batched environment behind stable-baselines3's VecEnv surface, so that the reference's
+    runner.py:62-155 can train on N GPU-resident envs instead of its DummyVecEnv of one: numpy in and out,
+    `step_async` / `step_wait`, auto-reset with the terminal observation in `infos[i]["terminal_observation"]`,
+    `num_envs`, `get_attr / set_attr / env_method / env_is_wrapped / seed` as VecEnv defines them. One host round trip
+    per gym step of ALL envs (the engine's pinned host buffers); the in-repo learner (learner.py) avoids even that.
+
+    `batched`: a BatchedEpiEnv, or any object with `.epi` offering step_host(actions) -> (obs, reward, done) numpy
+    views, reset(mask=None), obs_dim / action_dim, and `.action_space / .observation_space`."""
+
+    def __init__(self, batched):
+        self.batched, self.epi = batched, batched.epi
+        self.num_envs = int(getattr(batched, "n_envs", getattr(self.epi, "n_envs", 1)))
+        self.observation_space, self.action_space = batched.observation_space, batched.action_space
+        if _VecEnvBase is not object:  # pragma: no cover
+            super().__init__(self.num_envs, self.observation_space, self.action_space)
+        self._actions = None
+        self.render_mode = None
+
+    def _obs_now(self):
+        o = self.epi.obs
+        return np.asarray(o.double().cpu().numpy() if hasattr(o, "cpu") else o, np.float64)
+
+    def reset(self):
+        self.epi.reset()
+        return self._obs_now().copy()
+
+    def step_async(self, actions):
+        a = np.asarray(actions, np.float32).reshape(self.num_envs, -1)
+        if a.shape[1] < self.epi.action_dim:
+            raise ValueError(f"actions have {a.shape[1]} entries per env, the scenario has {self.epi.action_dim} free control parameters")
+        self._actions = np.ascontiguousarray(a[:, :self.epi.action_dim])  # the reference ignores the surplus entries
+
+    def step_wait(self):
+        obs, rew, done = self.epi.step_host(self._actions, PERIOD)
+        obs, rew, done = np.array(obs, np.float64), np.array(rew, np.float64), np.array(done).astype(bool)
+        infos = [{} for _ in range(self.num_envs)]
+        if done.any():
+            for i in np.nonzero(done)[0]:
+                infos[i]["terminal_observation"] = obs[i].copy()
+            self.epi.reset(_mask_for(self.epi, done))
+            fresh = self._obs_now()
+            obs[done] = fresh[done]
+        return obs, rew, done, infos
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def close(self):
+        if hasattr(self.batched, "close"):
+            self.batched.close()
+
+    def get_attr(self, attr_name, indices=None):
+        return [getattr(self.batched, attr_name)] * len(self._indices(indices))
+
+    def set_attr(self, attr_name, value, indices=None):
+        setattr(self.batched, attr_name, value)
+
+    def env_method(self, method_name, *method_args, indices=None, **method_kwargs):
+        return [getattr(self.batched, method_name)(*method_args, **method_kwargs)] * len(self._indices(indices))
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        return [False] * len(self._indices(indices))
+
+    def seed(self, seed=None):
+        return [None] * self.num_envs  # the simulator is deterministic
+
+    def render(self, mode="human"):
+        print("Rendering")
+
+    def _indices(self, indices):
+        if indices is None:
+            return list(range(self.num_envs))
+        return [indices] if isinstance(indices, int) else list(indices)
+
+
+def _mask_for(epi, done):
+    """reset mask in the form the engine takes (a torch tensor for the GPU engine, numpy for host-side doubles)"""
+    if hasattr(epi, "device"):
+        return torch.from_numpy(done.astype(np.uint8))
+    return done.astype(np.uint8)
 
 
 try:  # pragma: no cover - gym is not in this image; with it the twin is a real gym.Env (SB3's Monitor checks)

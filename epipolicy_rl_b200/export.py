@@ -438,17 +438,38 @@ def export_static(epi) -> EpiDesc:
     return d.finalize()
 
 
-def reporter_meta(st) -> dict:
-    """What reporter.py needs from the Static: the hashed incidence edges (core_utils.py:243-254) as (c1, c2) pairs
-    and the INF-tagged compartments (get_matrix_with_tag, core_optimize.py:10-16)."""
-    from epipolicy.utility.singleton import INF_TAG
+def reporter_meta(st, session=None) -> dict:
+    """What reporter.py / reporter_device.py need from the Static (and, for the reporting locations, the session):
+    the hashed incidence edges (core_utils.py:243-254) as (c1, c2) pairs - sorted, and in the reference dict's own
+    iteration order -, the INF / SUS / DIE compartment tag weights (get_matrix_with_tag, core_optimize.py:10-16), the
+    infectious edges with their parameter lists (obj/edge.py:51-67), the leaf locales of every reporting location
+    (session["locales"] through static.locale_hierarchy, core/reporter.py:102-103) and the generation-interval
+    weights of utility/utils.py:9-19."""
+    from epipolicy.utility.singleton import DIE_TAG, INF_TAG, SUS_TAG
+    from epipolicy.utility.utils import Ws, get_normalized_string
     C = st.compartment_count
-    inf = [0.0] * C
-    if st.has_property_name("compartment_tag", INF_TAG):
-        ti = st.get_property_index("compartment_tag", INF_TAG)
-        inf = [float(st.compartment_tags[c, ti]) for c in range(C)]
-    return {"incidence_edges": [[int(h) // C, int(h) % C] for h in sorted(int(h) for h in st.hashed_incidence_edges)],
-            "inf_comps": inf}
+
+    def tagw(tag):
+        if st.has_property_name("compartment_tag", tag):
+            ti = st.get_property_index("compartment_tag", tag)
+            return [float(st.compartment_tags[c, ti]) for c in range(C)]
+        return [0.0] * C
+    meta = {"incidence_edges": [[int(h) // C, int(h) % C] for h in sorted(int(h) for h in st.hashed_incidence_edges)],
+            "incidence_edges_order": [[int(h) // C, int(h) % C] for h in st.hashed_incidence_edges],
+            "inf_comps": tagw(INF_TAG), "sus_comps": tagw(SUS_TAG), "die_comps": tagw(DIE_TAG),
+            "has_die_tag": bool(st.has_property_name("compartment_tag", DIE_TAG)),
+            "infectious_edges": [{"sus": int(e.susceptible_comp_index), "beta": int(e.transmission_rate_index),
+                                  "comps": [[int(c), float(v)] for c, v in e.compartment_map.items()],
+                                  "numer": [int(p) for p in e.numer_param_index_list],
+                                  "denom": [int(p) for p in e.denom_param_index_list]}
+                                 for e in st.infectious_edges.values()],
+            "infectivity": [float(w) for w in Ws]}
+    if session is not None:
+        sess = session.get("session", session)
+        meta["locations"] = [sorted(int(l) for l in st.locale_hierarchy[get_normalized_string(loc["name"])])
+                             for loc in sess["locales"]]
+        meta["location_names"] = [loc["name"] for loc in sess["locales"]]
+    return meta
 
 
 def export_initial_parameter(epi) -> dict:

@@ -7,9 +7,18 @@ runner.py:116-119, Gaussian policy clipped to the Box(0,1) action space, GAE(gam
 value and entropy terms, gradient clipping (algorithm as in the reference's in-house optimizer/ppo.py:88-353;
 reward scaling as optimizer/env.py:19-36). Everything stays on the device.
 
-Multi-GPU (dist.py): every rank steps its own env shard with a policy replica; ONE all-gather per gym step
-delivers (obs | reward | done) of all shards to every rank, the learner rank (0) additionally receives the
-actions / log-probs / values through the same packed record, runs the PPO update and broadcasts the weights.
+Multi-GPU (dist.py): every rank steps its own env shard with a policy replica and keeps its rollout on its own
+device; ONE all-gather per update delivers the packed rollout records (obs | action | log-prob | value | reward | done)
+of all shards, the learner rank (0) runs the PPO update and broadcasts the weights.
+
+Determinism across layouts: the exploration noise of env e at step t is a function of (seed, update, t, e) only - every
+rank draws the noise of ALL envs from the same generator state and keeps its shard's slice - so a W-rank run collects
+exactly the rollout a 1-rank run over the same W*N envs collects (tests/test_learner.py), and ranks never duplicate
+each other's rollouts.
+
+On a CUDA device the whole rollout (n_steps x [policy forward, epi_step, episode bookkeeping, masked reset]) is captured
+once into a CUDA graph and replayed per update: the per-step host work of an eager PyTorch loop is what kept the
+learner at a fifth of the simulator's speed in round 1.
 """
 from __future__ import annotations
 
@@ -36,9 +45,15 @@ class ActorCritic(nn.Module):
         return torch.distributions.Normal(torch.sigmoid(self.pi(obs)), self.log_std.exp())
 
     @torch.no_grad()
-    def act(self, obs, deterministic: bool = False):
+    def act(self, obs, deterministic: bool = False, eps=None):
+        """eps: standard-normal noise [N, A] supplied by the caller (reproducible across rank layouts), else sampled"""
         d = self.dist(obs)
-        a = d.mean if deterministic else d.sample()
+        if deterministic:
+            a = d.mean
+        elif eps is not None:
+            a = d.mean + d.stddev * eps
+        else:
+            a = d.sample()
         return a, d.log_prob(a).sum(-1), self.v(obs).squeeze(-1)
 
     def evaluate(self, obs, act):
@@ -66,20 +81,28 @@ class BatchedPPO:
     def __init__(self, env, obs_dim: int, act_dim: int, obs_scale, n_steps: int = 16, n_epochs: int = 4,
                  minibatches: int = 4, gamma: float = 0.999, lam: float = 0.99, clip: float = 0.2,
                  lr: float = 3e-4, vf_coef: float = 0.974, ent_coef: float = 5.3e-8, max_grad_norm: float = 2.0,
-                 reward_scale: float = 1e-7, device="cuda", seed: int = 10, gather=None):
-        torch.manual_seed(seed)
+                 reward_scale: float = 1e-7, device="cuda", seed: int = 10, gather=None, use_graph: bool | None = None):
         self.env, self.dev = env, torch.device(device)
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        torch.manual_seed(seed)  # identical replicas on every rank (same init, weights broadcast after every update)
         self.ac = ActorCritic(obs_dim, act_dim).to(self.dev)
         self.opt = torch.optim.Adam(self.ac.parameters(), lr=lr)
         self.obs_scale = torch.as_tensor(obs_scale, dtype=torch.float32, device=self.dev)
         self.n_steps, self.n_epochs, self.minibatches = n_steps, n_epochs, minibatches
         self.gamma, self.lam, self.clip = gamma, lam, clip
         self.vf_coef, self.ent_coef, self.max_grad_norm, self.reward_scale = vf_coef, ent_coef, max_grad_norm, reward_scale
-        self.gather = gather  # callable(local tensors...) -> gathered tensors on every rank, or None (single GPU)
-        self.rank = dist.get_rank() if dist.is_initialized() else 0
-        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.gather = gather
+        self.obs_dim, self.act_dim = obs_dim, act_dim
+        # exploration noise: one generator per learner, same state on every rank, advanced by whole-fleet draws
+        self._noise = torch.Generator(device=self.dev).manual_seed(seed + 7919)
+        # minibatch permutations of the learner rank only
+        self._perm = torch.Generator(device=self.dev).manual_seed(seed + 104729)
         self._obs = None
         self.ep_return = None
+        self._buf = None
+        self._graph, self._graph_failed, self._warm = None, False, False
+        self.use_graph = (self.dev.type == "cuda") if use_graph is None else use_graph
         # finished episodes of this rank's shard, kept on the device (no host sync inside the rollout)
         self._fin_sum = torch.zeros((), dtype=torch.float64, device=self.dev)
         self._fin_cnt = torch.zeros((), dtype=torch.int64, device=self.dev)
@@ -94,44 +117,95 @@ class BatchedPPO:
         return obs.to(torch.float32) / self.obs_scale
 
     def _all(self, x):
-        """all-gather along the env axis (dim 0 of a [N_local, ...] tensor)"""
+        """all-gather along the env axis: x [..., N_local, F...] with the env axis at dim `-2 or 0` flattened by the
+        caller; here x is [N_local, ...] and the result [world * N_local, ...] (rank-major = global env order)"""
         if self.world == 1:
             return x
-        out = [torch.empty_like(x) for _ in range(self.world)]
-        dist.all_gather(out, x.contiguous())
-        return torch.cat(out, 0)
+        x = x.contiguous()
+        out = torch.empty((self.world,) + tuple(x.shape), dtype=x.dtype, device=x.device)
+        if x.is_cuda:
+            dist.all_gather_into_tensor(out.view(-1), x.view(-1))
+        else:
+            dist.all_gather(list(out.unbind(0)), x)
+        return out.reshape((-1,) + tuple(x.shape[1:]))
 
-    def collect(self):
-        """n_steps gym steps of every env; returns the rollout as [T, N_total, ...] tensors on every rank."""
-        if self._obs is None:
-            self._obs = self.env.reset().clone()
-            self.ep_return = torch.zeros(self._obs.shape[0], dtype=torch.float64, device=self.dev)
-        O, A, LP, V, R, D = [], [], [], [], [], []
-        for _ in range(self.n_steps):
+    # ---- rollout ----------------------------------------------------------------------------------
+    def _alloc(self, n):
+        T, D, A, dev = self.n_steps, self.obs_dim, self.act_dim, self.dev
+        f32 = dict(dtype=torch.float32, device=dev)
+        self._buf = dict(O=torch.zeros((T, n, D), **f32), A=torch.zeros((T, n, A), **f32), LP=torch.zeros((T, n), **f32),
+                         V=torch.zeros((T, n), **f32), R=torch.zeros((T, n), **f32), D=torch.zeros((T, n), **f32),
+                         eps=torch.zeros((T, n, A), **f32), last_v=torch.zeros(n, **f32))
+
+    def _rollout_body(self):
+        """n_steps gym steps of this rank's envs into the static rollout buffers; no host synchronisation (this is
+        the region a CUDA graph captures)"""
+        B = self._buf
+        for t in range(self.n_steps):
             o = self._norm(self._obs)
-            a, lp, v = self.ac.act(o)
+            a, lp, v = self.ac.act(o, eps=B["eps"][t])
             obs, rew, done, _ = self.env.step(a.clamp(0.0, 1.0).contiguous())
             self.ep_return += rew
             d = done.to(torch.bool)
             # episode bookkeeping and the masked restart stay on the device: no `if d.any()` host round trip per step
             self._fin_sum += torch.where(d, self.ep_return, torch.zeros_like(self.ep_return)).sum()
             self._fin_cnt += d.sum()
-            self.ep_return = torch.where(d, torch.zeros_like(self.ep_return), self.ep_return)
-            r32 = rew.to(torch.float32) * self.reward_scale  # before the restart: reward may alias an engine buffer
-            d32 = d.to(torch.float32)
+            self.ep_return.copy_(torch.where(d, torch.zeros_like(self.ep_return), self.ep_return))
+            B["O"][t].copy_(o); B["A"][t].copy_(a); B["LP"][t].copy_(lp); B["V"][t].copy_(v)
+            B["R"][t].copy_(rew.to(torch.float32) * self.reward_scale)  # before the restart: reward aliases an engine buffer
+            B["D"][t].copy_(d.to(torch.float32))
             self.env.reset(done)  # restarts the envs whose flag is set (a launch that touches nothing otherwise)
-            obs = self.env.epi.obs
-            if self.world == 1:
-                O.append(o); A.append(a); LP.append(lp); V.append(v); R.append(r32); D.append(d32)
+            self._obs.copy_(self.env.epi.obs)
+        B["last_v"].copy_(self.ac.act(self._norm(self._obs), deterministic=True)[2])
+
+    def collect(self):
+        """n_steps gym steps of every env; returns the rollout as [T, N_total, ...] tensors on every rank."""
+        if self._obs is None:
+            self._obs = self.env.reset().clone()
+            n = self._obs.shape[0]
+            self.ep_return = torch.zeros(n, dtype=torch.float64, device=self.dev)
+            self._alloc(n)
+        B, n = self._buf, self._obs.shape[0]
+        # the fleet's noise for this rollout, this rank's slice of it (see the module docstring)
+        eps = torch.randn((self.n_steps, self.world * n, self.act_dim), generator=self._noise, device=self.dev)
+        B["eps"].copy_(eps[:, self.rank * n:(self.rank + 1) * n])
+        if self.use_graph and not self._graph_failed and self._warm:
+            if self._graph is None:
+                self._capture()
+            if self._graph is not None:
+                self._graph.replay()
             else:
-                # one packed exchange per gym step: what the learner needs from every shard
-                rec = self._all(torch.cat([o, a, lp[:, None], v[:, None], r32[:, None], d32[:, None]], 1))
-                nd, na = o.shape[1], a.shape[1]
-                O.append(rec[:, :nd]); A.append(rec[:, nd:nd + na]); LP.append(rec[:, nd + na]); V.append(rec[:, nd + na + 1])
-                R.append(rec[:, nd + na + 2]); D.append(rec[:, nd + na + 3])
-            self._obs = obs.clone()
-        last_v = self._all(self.ac.act(self._norm(self._obs))[2])
-        return (torch.stack(O), torch.stack(A), torch.stack(LP), torch.stack(V), torch.stack(R), torch.stack(D), last_v)
+                self._rollout_body()
+        else:
+            self._rollout_body()  # the first rollout runs eagerly: it is also the warm-up a graph capture needs
+            self._warm = True
+        if self.world == 1:
+            return tuple(B[k] for k in ("O", "A", "LP", "V", "R", "D", "last_v"))
+        # ONE exchange per update: the packed rollout record of every shard (rank-major = global env order)
+        T, D, A = self.n_steps, self.obs_dim, self.act_dim
+        rec = torch.cat([B["O"], B["A"], B["LP"][..., None], B["V"][..., None], B["R"][..., None], B["D"][..., None]], -1)
+        rec = torch.cat([rec.reshape(-1), B["last_v"]])
+        allr = self._all(rec[None])  # [world, T*n*(D+A+4) + n]
+        body = allr[:, :T * n * (D + A + 4)].reshape(self.world, T, n, D + A + 4).permute(1, 0, 2, 3).reshape(T, self.world * n, D + A + 4)
+        last_v = allr[:, T * n * (D + A + 4):].reshape(-1)
+        return (body[..., :D], body[..., D:D + A], body[..., D + A], body[..., D + A + 1], body[..., D + A + 2],
+                body[..., D + A + 3], last_v)
+
+    def _capture(self):
+        """capture the rollout into a CUDA graph (the first, eager rollout was the warm-up: allocator, cuBLAS handles,
+        specialised kernels are in place); capturing does not execute, the caller replays. Any failure leaves the eager
+        path in charge."""
+        try:
+            torch.cuda.synchronize(self.dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._rollout_body()
+            self._graph = g
+        except Exception as e:  # noqa: BLE001
+            import sys
+            print(f"[epi-b200] rollout graph capture failed ({type(e).__name__}: {e}); eager rollout", file=sys.stderr)
+            self._graph, self._graph_failed = None, True
+            torch.cuda.synchronize(self.dev)
 
     def update(self, batch):
         O, A, LP, V, R, D, last_v = batch
@@ -142,7 +216,7 @@ class BatchedPPO:
         stats = {}
         if self.rank == 0:
             for _ in range(self.n_epochs):
-                perm = torch.randperm(n, device=self.dev)
+                perm = torch.randperm(n, device=self.dev, generator=self._perm)
                 for idx in perm.chunk(self.minibatches):
                     lp, ent, v = self.ac.evaluate(O[idx], A[idx])
                     ratio = (lp - LP[idx]).exp()
@@ -246,11 +320,11 @@ class BatchedSAC:
                  lr: float = 3e-3, batch_size: int = 256, buffer_size: int = 1 << 20, learning_starts: int = 0,
                  gradient_steps: int = 4, target_entropy: float | None = None, reward_scale: float = 1e-7,
                  device="cuda", seed: int = 10):
-        torch.manual_seed(seed)
         self.env, self.dev = env, torch.device(device)
         self.obs_scale = torch.as_tensor(obs_scale, dtype=torch.float32, device=self.dev)
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
+        torch.manual_seed(seed)  # identical networks on every rank ...
         self.actor = SquashedGaussianActor(obs_dim, act_dim).to(self.dev)
         self.q1, self.q2 = _mlp(obs_dim + act_dim, 1).to(self.dev), _mlp(obs_dim + act_dim, 1).to(self.dev)
         self.q1_t, self.q2_t = _mlp(obs_dim + act_dim, 1).to(self.dev), _mlp(obs_dim + act_dim, 1).to(self.dev)

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libepi_b200.so")
 EPI_FP64, EPI_FP32 = 0, 1
 EXPORTS = ["epi_create", "epi_destroy", "epi_last_error", "epi_info", "epi_reset", "epi_step", "epi_step_plan",
            "epi_step_host", "epi_get_state", "epi_set_state", "epi_launch_count", "epi_spec_source", "epi_spec_source_desc",
-           "epi_spec_attach", "epi_host_buffers", "epi_bind_mirror"]
+           "epi_spec_attach", "epi_host_buffers", "epi_bind_mirror", "epi_get_state_dev", "epi_get_plan"]
 
 
 class EpiInfo(ctypes.Structure):
@@ -80,4 +80,8 @@ def bind(L):
     L.epi_bind_mirror.argtypes = [P, P, P, P]
     L.epi_spec_attach.restype = I
     L.epi_spec_attach.argtypes = [P, ctypes.c_char_p]
+    L.epi_get_state_dev.restype = I
+    L.epi_get_state_dev.argtypes = [P, I, P, SZ, P]
+    L.epi_get_plan.restype = I
+    L.epi_get_plan.argtypes = [P, I, P, SZ]
     return L

@@ -101,6 +101,19 @@ int epi_host_buffers(epi_t* h, float** actions, void** obs, double** reward, uin
 int epi_get_state(epi_t* h, int what, void* out_host, size_t bytes);
 int epi_set_state(epi_t* h, int what, const void* in_host, size_t bytes);
 
+/* Device-side copies of the state (stream-ordered, no host round trip) for consumers that stay on the GPU - the
+ * reporter quantities of core/reporter.py:45-204 for all envs (epipolicy_rl_b200/reporter_device.py). `what`:
+ *   0 X double [n_envs, obs_dim]   1 cumulative_cost double [n_envs, I*L]   7 class multipliers float [n_envs, n_cls]
+ *   10 live cumulative_move / gain / lost components, real [n_envs, n_acc, L*G] (component a sits at offset
+ *      plan table 0 [a] * L*G of the reference's flat observable, obj/observable.py:24-25) */
+int epi_get_state_dev(epi_t* h, int what, void* out_dev, size_t bytes, void* cuda_stream);
+/* Static tables of the compiled scenario (host buffers, sizes checked): 0 acc_flat int32 [n_acc]; 1 locale class of
+ * every locale int32 [L]; 2 default model parameters float [n_lc, P, F, G]; 3 their multiplier classes int32;
+ * 4 default facility_timespent float [n_lc, F, G]; 5 their multiplier classes int32. With table 7 of the state
+ * (class multipliers, class 0 = identity) they give a state's parameters: value * mult[class]
+ * (obj/parameter.py:53-66). */
+int epi_get_plan(const epi_t* h, int what, void* out_host, size_t bytes);
+
 /* Scenario specialisation of the cell kernel (the reference JIT-compiles its RHS with numba; this is the
  * analogue). epi_spec_source writes a generated CUDA header (NUL-terminated, `*need` = bytes required)
  * holding the scenario's per-cell program as straight-line code; the caller compiles

@@ -128,23 +128,29 @@ def test_sirv_b_1024_envs_vs_oracle(prec):
 
 @pytest.mark.parametrize("prec", ["fp64", "fp32"])
 def test_covid_c_batch_vs_oracle(prec):
-    """BASELINE.json configs[2] spot check: 64 of the 4096 COVID_C envs against the oracle."""
-    from oracle.oracle import rollout
+    """BASELINE.json configs[2] spot check: 64 of the 4096 COVID_C envs against the oracle over the FULL horizon
+    (53 gym steps, the last one cut at day 365): every gym step's observation and reward of the sampled envs, the
+    done flags, and the episode totals."""
+    from oracle.oracle import Oracle
     d, _ = load("COVID_C")
-    n, steps = 4096, 8
+    n, steps = 4096, (d.horizon + 6) // 7
     g = torch.Generator().manual_seed(1234)
     acts = torch.rand((steps, n, d.A), generator=g)
-    eng = _engine(d, n, prec)
-    rew = np.zeros(n)
-    for s in range(steps):
-        obs, r, _ = eng.step(acts[s].cuda(), 7)
-        rew += r.cpu().numpy()
     idx = np.arange(0, n, 64)
-    total, fin = rollout(d, acts[:, idx].permute(1, 0, 2).numpy())
-    e = x_err(obs[idx].double().cpu().numpy(), fin, d)
-    print(f"COVID_C x4096 {prec}: X err on 64 envs {e:.2e}")
-    assert e <= TOL[prec]
-    assert abs(rew[idx].sum() - total) <= TOL[prec] * abs(total)
+    oracles = [Oracle(d) for _ in idx]
+    eng = _engine(d, n, prec)
+    worst = worst_r = 0.0
+    for s in range(steps):
+        obs, r, done = eng.step(acts[s].cuda(), 7)
+        o_gpu, r_gpu, d_gpu = obs[idx].double().cpu().numpy(), r.cpu().numpy()[idx], done.cpu().numpy()[idx]
+        for k, (e, o) in enumerate(zip(idx, oracles)):
+            o_obs, o_rew, o_done = o.step(acts[s, e].numpy(), 7)
+            worst = max(worst, x_err(o_gpu[k], o_obs, d))
+            worst_r = max(worst_r, abs(r_gpu[k] - o_rew) / abs(o_rew))
+            assert bool(d_gpu[k]) == o_done == (s == steps - 1)
+    print(f"COVID_C x4096 {prec}: 64 envs x {steps} gym steps, worst X err {worst:.2e}, worst reward err {worst_r:.2e}")
+    assert worst <= TOL[prec] and worst_r <= TOL[prec]
+    assert (eng.get_state("day") == d.horizon).all()
     eng.close()
 
 
@@ -276,6 +282,43 @@ def test_batched_ppo_runs_on_device():
     assert len(hist) == 2 and all(np.isfinite(h["mean_step_reward"]) and h["mean_step_reward"] < 0 for h in hist)
     assert np.isfinite(hist[-1]["v_loss"])
     env.close()
+
+
+def test_ppo_graph_rollout_equals_eager_rollout_and_gae_on_device():
+    """learner numerics on the GPU: (1) the rollout replayed from the captured CUDA graph is the rollout the eager loop
+    collects (same seeds, same envs: bit for bit), update after update; (2) GAE on the device against a naive fp64
+    loop on the host."""
+    from epipolicy_rl_b200.env import BatchedEpiEnv
+    from epipolicy_rl_b200.learner import BatchedPPO, gae
+    d, _ = load("COVID_A")
+    pop = np.broadcast_to(d.pop.reshape(1, d.L, d.G), (d.C, d.L, d.G)).reshape(-1)
+    runs = []
+    for use_graph in (True, False):
+        env = BatchedEpiEnv(d, 192, device=0, precision="fp32")
+        ppo = BatchedPPO(env, env.epi.obs_dim, d.A, obs_scale=pop, n_steps=6, n_epochs=1, device="cuda:0", seed=3,
+                         use_graph=use_graph)
+        out = []
+        for u in range(3):
+            batch = ppo.collect()
+            out.append([x.clone() for x in batch])
+            ppo.update(batch)
+        assert (ppo._graph is not None) == use_graph, "the rollout graph must be in use when asked for"
+        runs.append(out)
+        env.close()
+    for u in range(3):
+        for a, b in zip(runs[0][u], runs[1][u]):
+            assert torch.equal(a, b), f"update {u}: graph and eager rollouts differ"
+    O, A, LP, V, R, D, last_v = runs[0][2]
+    adv, ret = gae(R, V, D, last_v, 0.999, 0.99)
+    r64, v64, d64, l64 = (x.double().cpu() for x in (R, V, D, last_v))
+    T, N = r64.shape
+    ref = torch.zeros((T, N), dtype=torch.float64)
+    run, nxt = torch.zeros(N, dtype=torch.float64), l64
+    for t in reversed(range(T)):
+        nt = 1.0 - d64[t]
+        run = (r64[t] + 0.999 * nxt * nt - v64[t]) + 0.999 * 0.99 * nt * run
+        ref[t], nxt = run, v64[t]
+    assert torch.allclose(adv.double().cpu(), ref, rtol=1e-4, atol=1e-5)
 
 
 @pytest.mark.parametrize("prec", ["fp64", "fp32"])

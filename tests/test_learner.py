@@ -58,6 +58,96 @@ def test_ppo_learns_on_toy_env():
     assert hist[-1]["mean_step_reward"] > hist[0]["mean_step_reward"] + 0.02
 
 
+class DetEnv:
+    """deterministic batched env whose envs are told apart by their GLOBAL index only: env e of a fleet behaves the same
+    whichever rank owns it (the property the GPU engine's identical-scenario envs have)"""
+
+    def __init__(self, n, first, total):
+        self.n, self.epi = n, self
+        self.idx = torch.arange(first, first + n, dtype=torch.float32)
+        self.total = total
+        self.reset()
+
+    def _obs(self):
+        return torch.stack([self.s, self.s ** 2, self.idx / self.total], 1)
+
+    def reset(self, mask=None):
+        m = torch.ones(self.n, dtype=torch.bool) if mask is None else mask.to(torch.bool)
+        if mask is None:
+            self.s, self.t = (self.idx + 1) / (2 * self.total), torch.zeros(self.n)
+        else:
+            self.s = torch.where(m, (self.idx + 1) / (2 * self.total), self.s)
+            self.t = torch.where(m, torch.zeros(self.n), self.t)
+        self.obs = self._obs()
+        return self.obs
+
+    def step(self, a):
+        r = -((a - self.s[:, None]) ** 2).sum(-1).double()
+        self.s = 0.9 * self.s + 0.1 * a.mean(-1) + 0.01
+        self.t = self.t + 1
+        self.obs = self._obs()
+        return self.obs, r, (self.t >= 5).to(torch.uint8), {}
+
+
+def _det_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 6
+    env = DetEnv(n, rank * n, world * n)
+    ppo = BatchedPPO(env, 3, 2, obs_scale=np.ones(3), n_steps=7, n_epochs=1, lr=1e-3, reward_scale=1.0, device="cpu", seed=5)
+    batches = []
+    for _ in range(2):  # two updates: the noise generator and the broadcast weights stay in step
+        batch = ppo.collect()
+        batches.append([x.clone() for x in batch])
+        ppo.update(batch)
+    if rank == 0:
+        torch.save(batches, os.path.join(out, "multi.pt"))
+    dist.destroy_process_group()
+
+
+def test_two_rank_rollout_equals_one_rank_rollout(tmp_path):
+    """identical envs on every rank (as the GPU engine's are): the W-rank fleet collects exactly what one rank over
+    all W*N envs collects - per-env noise is a function of the global env index - and no two shards coincide"""
+    port = 29450 + os.getpid() % 100
+    mp.spawn(_det_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    multi = torch.load(tmp_path / "multi.pt")
+    env = DetEnv(12, 0, 12)
+    ppo = BatchedPPO(env, 3, 2, obs_scale=np.ones(3), n_steps=7, n_epochs=1, lr=1e-3, reward_scale=1.0, device="cpu", seed=5)
+    for u in range(2):
+        batch = ppo.collect()
+        for a, b in zip(batch, multi[u]):
+            assert a.shape == b.shape
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), u
+        acts = multi[u][1]
+        assert not torch.allclose(acts[:, :6], acts[:, 6:])  # the two shards explore differently
+        ppo.update(batch)
+
+
+def test_gae_matches_naive_fp64_loop_with_episode_ends():
+    T, N = 16, 7
+    g = torch.Generator().manual_seed(4)
+    rew, val, last = torch.randn((T, N), generator=g), torch.randn((T, N), generator=g), torch.randn(N, generator=g)
+    done = (torch.rand((T, N), generator=g) < 0.2).float()
+    done[-1, 0] = 1.0
+    adv, ret = gae(rew, val, done, last, 0.999, 0.99)
+    r64, v64, d64, l64 = rew.double(), val.double(), done.double(), last.double()
+    ref = torch.zeros((T, N), dtype=torch.float64)
+    for n in range(N):
+        for t in range(T):
+            # naive definition: sum over l of (gamma*lambda)^l * delta_{t+l}, cut at the episode end
+            acc, w = 0.0, 1.0
+            for l in range(t, T):
+                nxt = l64[n] if l == T - 1 else v64[l + 1, n]
+                nt = 1.0 - d64[l, n]
+                acc += w * (r64[l, n] + 0.999 * nxt * nt - v64[l, n])
+                if d64[l, n] > 0:
+                    break
+                w *= 0.999 * 0.99
+            ref[t, n] = acc
+    assert torch.allclose(adv.double(), ref, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(ret, adv + val)
+
+
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)

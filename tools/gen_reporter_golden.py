@@ -1,6 +1,8 @@
 """Golden vectors for the reporter quantities from the UNMODIFIED reference, run in this
 container: the scenario's own schedule for T days through Epidemic.step, then the reference Reporter's
-compute_history / compute_incidences / compute_comp_news (core/reporter.py:34-51).
+compute_history / compute_incidences / compute_comp_news (core/reporter.py:34-51) and its R-number chain
+(average infectious duration, location / window statistics, instantaneous, basic and case reproduction numbers,
+core/reporter.py:54-204, default configuration).
 
   PYTHONDONTWRITEBYTECODE=1 PYTHONPATH=tools/gym_shim:/root/reference:. python tools/gen_reporter_golden.py [names...]
 
@@ -33,11 +35,26 @@ def main(names, T=28):
         rep.compute_history()
         rep.compute_incidences()
         rep.compute_comp_news()
-        meta = reporter_meta(epi.static)
+        # the R-number chain with the reference's default configuration (utility/singleton.py:30-34)
+        rep.compute_average_infectious_duration()
+        rep.compute_location_statistics()
+        rep.compute_window_statistics()
+        rep.compute_instantaneous_reproductive_number()
+        rep.compute_basic_reproductive_number()
+        rep.compute_case_reproductive_number()
+        meta = reporter_meta(epi.static, session)
         np.savez_compressed(os.path.join(OUT, f"reporter_{name}.npz"), incidences=np.asarray(rep.incidences),
                             comp_news=np.asarray(rep.comp_news),
                             incidence_edges=np.array(meta["incidence_edges"], np.int32).reshape(-1, 2),
-                            inf_comps=np.array(meta["inf_comps"]), T=T)
+                            inf_comps=np.array(meta["inf_comps"]), T=T,
+                            average_infectious_duration=np.asarray(rep.average_infectious_duration),
+                            window_infectious_duration=np.asarray(rep.window_infectious_duration),
+                            location_window_incidence=np.asarray(rep.location_window_incidence),
+                            location_window_infectious_count=np.asarray(rep.location_window_infectious_count),
+                            location_instant_R=np.asarray(rep.location_instant_R),
+                            location_basic_R=np.asarray(rep.location_basic_R),
+                            location_case_R=np.asarray(rep.location_case_R),
+                            location_avg_model_parameters=np.asarray(rep.location_avg_model_parameters))
         dpath = os.path.join(SCN, f"desc_{name}.npz")
         d = EpiDesc.load(dpath)
         d.meta["reporter"] = meta
