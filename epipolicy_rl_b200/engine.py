@@ -124,13 +124,42 @@ class BatchedEpidemic:
                                       self.reward.data_ptr(), self.done.data_ptr(), self._stream()))
         return self.obs, self.reward, self.done
 
+    # ---------------------------------------------------------------------------------
+    def plan_tables(self) -> dict:
+        """static tables of the compiled scenario (epi_get_plan): positions of the live accumulators in the reference's
+        flat observable, locale classes, per-class default parameters / facility_timespent and their multiplier classes"""
+        d, n_lc = self.desc, self.info.n_lc
+        spec = {"acc_flat": (0, (self.info.n_acc,), np.int32), "lclass": (1, (d.L,), np.int32),
+                "mp0": (2, (n_lc, d.P, d.F, d.G), np.float32), "mp_cls": (3, (n_lc, d.P, d.F, d.G), np.int32),
+                "ft0": (4, (n_lc, d.F, d.G), np.float32), "ft_cls": (5, (n_lc, d.F, d.G), np.int32)}
+        out = {}
+        for k, (code, shape, dt) in spec.items():
+            a = np.empty(shape, dt)
+            self._ck(self.L.epi_get_plan(self._h, code, a.ctypes.data, a.nbytes))
+            out[k] = a
+        return out
+
+    def state_dev(self, what: str) -> torch.Tensor:
+        """stream-ordered device copy of a piece of the state (no host round trip): "X" [N, C*L*G] f64, "cost" [N, I*L] f64,
+        "mult" [N, n_cls] f32, "acc" [N, n_acc, L*G] in the engine's precision (the live cumulative components)"""
+        d, N = self.desc, self.n_envs
+        code, shape, dt = {"X": (0, (N, self.obs_dim), torch.float64), "cost": (1, (N, d.I * d.L), torch.float64),
+                           "mult": (7, (N, self.info.n_cls), torch.float32),
+                           "acc": (10, (N, self.info.n_acc, d.L * d.G), self.dtype)}[what]
+        t = torch.empty(shape, dtype=dt, device=self.device)
+        self._ck(self.L.epi_get_state_dev(self._h, code, t.data_ptr(), t.numel() * t.element_size(), self._stream()))
+        return t
+
     def run(self, cpv: torch.Tensor, active: torch.Tensor | None = None, record_obs: bool = True,
-            schedule_programs: bool = True):
+            schedule_programs: bool = True, report: bool = False):
         """Epidemic.run (core/epidemic.py:118-134) for a batch of what-if schedules: reset, then one day per launch
         with day t's Acts taken from the schedule. cpv: [T, N, NCP] (or [T, NCP], broadcast to all envs) full
         control-parameter vectors; active: [T, N, I] / [T, I] flags of the interventions that have an Act on
         day t (None: all). Returns {"reward": [T, N] float64, "done": [N] uint8, "obs": [T, N, C*L*G]} on the device
-        (obs only if record_obs; the reporter quantities of the reference are not rebuilt here)."""
+        (obs only if record_obs). report=True adds "report": the reference Reporter's quantities for every env -
+        incidences, average infectious duration, windowed statistics, instantaneous / basic / case reproduction numbers
+        per reporting location (core/reporter.py:45-204) - computed on the device from stream-ordered copies of the
+        state, the live cumulative components and the class multipliers of every day (reporter_device.py)."""
         c = cpv.to(device=self.device, dtype=torch.float32)
         T = c.shape[0]
         if c.dim() == 2:
@@ -143,6 +172,11 @@ class BatchedEpidemic:
         if c.shape[1] != self.n_envs or (a is not None and a.shape[:2] != c.shape[:2]):
             raise ValueError("schedule must be [T, N, NCP] / [T, NCP] with matching active flags")
         self.reset()
+        rep = None
+        if report:
+            from .reporter_device import DeviceReporter
+            rep = DeviceReporter(self.desc, self.plan_tables(), self.device)
+            rep.record(self.state_dev("X"), self.state_dev("acc"), self.state_dev("mult"))
         rew = torch.empty((T, self.n_envs), dtype=torch.float64, device=self.device)
         obs = torch.empty((T, self.n_envs, self.obs_dim), dtype=self.dtype, device=self.device) if record_obs else None
         for t in range(T):
@@ -150,7 +184,11 @@ class BatchedEpidemic:
             rew[t].copy_(r)
             if record_obs:
                 obs[t].copy_(o)
+            if rep is not None:
+                rep.record(self.state_dev("X"), self.state_dev("acc"), self.state_dev("mult"))
         out = {"reward": rew, "done": self.done}
+        if rep is not None:
+            out["report"] = rep.compute()
         if record_obs:
             out["obs"] = obs
         return out

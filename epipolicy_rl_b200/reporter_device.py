@@ -13,6 +13,8 @@ Restated literally, including two things worth knowing about the reference:
     IN PLACE: `add = self.location_avg_model_parameters[t, idx]` is a view, `add *= ...` and `true_divide(add, ..)`
     (out = a) write through it, so later edges of the same day see the already scaled row (core/reporter.py:181-186).
     The restatement keeps the aliasing.
+  * `location_cumulative_moves[t, :, :, loc]` is assigned, not accumulated, in the loop over the location's locales
+    (core/reporter.py:112): the basic R's edge weights see the LAST leaf locale only. Kept.
   * the windowed sums are running sums of window differences (core/reporter.py:132-150), kept as written.
 
 `desc.meta["reporter"]` holds what comes from the reference Static / session (export.reporter_meta): incidence
@@ -60,6 +62,10 @@ class DeviceReporter:
             for l in ls:
                 M[i, l] += 1.0
         self.M = M
+        self.M_last = torch.zeros_like(M)
+        for i, ls in enumerate(self.locations):
+            if ls:
+                self.M_last[i, ls[-1]] = 1.0   # leaf locales are inserted in ascending order (core_utils.py:44-53)
         # position of every live accumulator in the dense layouts
         self.acc_flat = np.asarray(plan["acc_flat"], np.int64)                # offset / (L*G) in the flat observable
         self.plan = {k: torch.as_tensor(np.asarray(v), device=self.dev) for k, v in plan.items() if k != "acc_flat"}
@@ -125,7 +131,9 @@ class DeviceReporter:
         # location statistics (core/reporter.py:82-130; the pieces the R numbers use)
         loc_inc = torch.einsum("il,tnlg->tnig", self.M, inc)          # [T+1, N, nloc, G]
         loc_cnt = torch.einsum("il,tnclg->tncig", self.M, X)          # [T+1, N, C, nloc, G]
-        loc_mv = torch.einsum("il,tnabl->tnabi", self.M, mv.sum(-1))  # [T+1, N, C, C, nloc]
+        # location_cumulative_moves: the reference ASSIGNS inside its loop over the location's locales
+        # (core/reporter.py:112, `=` not `+=`): what remains is the last leaf locale's moves, summed over the groups
+        loc_mv = torch.einsum("il,tnabl->tnabi", self.M_last, mv.sum(-1))  # [T+1, N, C, C, nloc]
         alive = X.sum(2) - tag(X, self.die)                           # get_matrix_without_tag(.., DIE)  [T+1, N, L, G]
         lclass = self.plan["lclass"].long()
         n_lc = int(lclass.max().item()) + 1

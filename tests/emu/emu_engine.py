@@ -70,9 +70,22 @@ class EmuEngine:
         d, N = self.desc, self.n_envs
         spec = {"X": (0, (N, d.C, d.L, d.G), np.float64), "cost": (1, (N, d.I, d.L), np.float64),
                 "day": (2, (N,), np.int32), "flat": (3, (N, d.n_flat), np.float64), "trace": (4, (N, 4), np.int32),
-                "last_err": (5, (N,), np.float64), "attempts": (9, (N, 64, 2), np.float64)}[what]
+                "last_err": (5, (N,), np.float64), "attempts": (9, (N, 64, 2), np.float64),
+                "mult": (7, (N, self.info.n_cls), np.float32)}[what]
         out = np.empty(spec[1], spec[2])
         self._ck(self.L.epi_get_state(self._h, spec[0], out.ctypes.data, out.nbytes))
+        return out
+
+    def plan_tables(self):
+        d, n_lc = self.desc, self.info.n_lc
+        spec = {"acc_flat": (0, (self.info.n_acc,), np.int32), "lclass": (1, (d.L,), np.int32),
+                "mp0": (2, (n_lc, d.P, d.F, d.G), np.float32), "mp_cls": (3, (n_lc, d.P, d.F, d.G), np.int32),
+                "ft0": (4, (n_lc, d.F, d.G), np.float32), "ft_cls": (5, (n_lc, d.F, d.G), np.int32)}
+        out = {}
+        for k, (code, shape, dt) in spec.items():
+            a = np.empty(shape, dt)
+            self._ck(self.L.epi_get_plan(self._h, code, a.ctypes.data, a.nbytes))
+            out[k] = a
         return out
 
     def attach_spec(self):

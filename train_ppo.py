@@ -2,10 +2,10 @@
 """End-to-end PPO / SAC on GPU-batched epidemic environments (BASELINE.json configs[4]: COVID_A, envs sharded over the
 GPUs of one box, one NCCL all-gather per update delivers every shard's rollout to the learner rank).
 
-  python train_ppo.py [--scenario COVID_A] [--envs 4096] [--updates 20] [--algo ppo|sac] [--log profiles/ppo.jsonl]
+  python train_ppo.py [--scenario COVID_A] [--envs 4096] [--updates 20] [--algo ppo|sac] [--jsonl profiles/ppo.jsonl]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 train_ppo.py ...
 
-Prints one JSON line per update (rank 0; also appended to --log) and a final summary with env-steps/s including the
+Prints one JSON line per update (rank 0; also appended to --jsonl) and a final summary with env-steps/s including the
 learner, the env-only rate of the same fleet, and the mean step reward of the trained policy against the random, "lax"
 and "aggressive" baselines of the reference's baselines.py:31-50.
 """
@@ -39,7 +39,7 @@ def main():
     ap.add_argument("--precision", default="fp32")
     ap.add_argument("--algo", default="ppo", choices=["ppo", "sac"], help="runner.py --algo")
     ap.add_argument("--no-graph", action="store_true", help="eager rollout instead of the captured CUDA graph")
-    ap.add_argument("--log", default="", help="append the per-update JSON lines and the summary to this file")
+    ap.add_argument("--jsonl", default="", help="append the per-update JSON lines and the summary to this file")
     args = ap.parse_args()
     import __graft_entry__ as g
     g.build()
@@ -58,7 +58,7 @@ def main():
     env = BatchedEpiEnv(desc, args.envs, device=local, precision=args.precision)
     pop = np.broadcast_to(desc.pop.reshape(1, desc.L, desc.G), (desc.C, desc.L, desc.G)).reshape(-1)
     dev = torch.device(f"cuda:{local}")
-    logf = open(args.log, "a") if (args.log and rank == 0) else None
+    logf = open(args.jsonl, "a") if (args.jsonl and rank == 0) else None
 
     def emit(rec):
         if rank == 0:
