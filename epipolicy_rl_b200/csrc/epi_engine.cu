@@ -22,7 +22,6 @@
 #include "../../include/epi_b200.h"
 #include "epi_kernels.cuh"
 #include "epi_cell.cuh"
-#include "epi_cellteam.cuh"
 #include "epi_env.cuh"
 
 namespace {
@@ -514,19 +513,11 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
   for (auto& v : xg) { for (auto& pr : v) { xg_src.push_back(pr.first); xg_coef.push_back(pr.second); } xg_off.push_back((int)xg_src.size()); }
   for (auto& v : ag) { for (auto& pr : v) { ag_src.push_back(pr.first); ag_coef.push_back(pr.second); } ag_off.push_back((int)ag_src.size()); }
 
-  // roles of the cell-team kernel (epi_cellteam.cuh): R warps share one group of envs when there is enough
-  // per-cell work to split; the two compartments of a move slot stay together on role 0
+  // (a role-split "cell-team" variant - R warps per env group, epi_cellteam.cuh in round 1 - measured 2.1-2.3 ms per
+  // COVID_C gym step against the cell kernel's 1.24 ms at the time and was removed in round 2)
   {
-    // Measured on B200 (COVID_C x 4096, fp32): R = 2/3/4 -> 2.28/2.12/2.11 ms per gym step against 1.24 ms for
-    // R = 1: the barrier-separated role phases have too little ILP each and the per-warp control overhead does
-    // not divide by R. The role split therefore stays an experiment behind EPI_ROLES; default is the cell kernel.
-    int R = 1;
-    if (const char* ov = getenv("EPI_ROLES")) { int v = atoi(ov); if (v >= 1 && v <= 4) R = v; }
-    if (LG > 32) R = 1;
-    P.cl.roles = R;
-    std::vector<int> comp_role(C);
-    for (int c = 0; c < C; c++) comp_role[c] = c % R;
-    for (int s = 0; s < n_slot; s++) comp_role[slots[s].first] = comp_role[slots[s].second] = 0;
+    P.cl.roles = 1;
+    std::vector<int> comp_role(C, 0);
     h->tabs.comp_role = comp_role;
     P.comp_role = h->up(comp_role);
   }
@@ -988,80 +979,6 @@ std::string gen_spec(const epi_engine* h) {
   }
   o << "}\n";
 
-  // ---- per-role pieces of the cell-team kernel (epi_cellteam.cuh); columns are strided by LW
-  if (P.LG <= 32 && P.cl.roles > 1) {
-    const int R = P.cl.roles;
-    o << "__device__ __forceinline__ real phaseA_q(int q, const real* ys) {\n  real x = 0;\n  switch (q) {\n  case 0:\n";
-    for (int c = 0; c < P.C; c++)
-      if (T.alive_coef[c] != 0.0) o << "    x += ys[" << c << " * LW] * " << hexd(T.alive_coef[c]) << ";\n";
-    o << "    break;\n";
-    for (int k = 0; k < P.NG; k++) {
-      o << "  case " << k + 1 << ":\n";
-      for (int q = T.ig_w_off[k]; q < T.ig_w_off[k + 1]; q++) o << "    x += " << hexd(T.ig_w[q]) << " * ys[" << T.ig_w_c2[q] << " * LW];\n";
-      o << "    break;\n";
-    }
-    o << "  }\n  return x;\n}\n";
-    auto valr = [&](int fac) {
-      int kind = fac >> 24, idx = fac & 0xffffff;
-      std::ostringstream v;
-      if (kind == 0) v << "(real)mp[" << idx * P.G << "]";
-      else if (kind == 1) v << "alive";
-      else v << "y" << idx;
-      return v.str();
-    };
-    o << "__device__ __forceinline__ void flows_role(int role, const real* ys, real alive, const float* mp, real* fl) {\n  switch (role) {\n";
-    for (int r = 0; r < R; r++) {
-      o << "  case " << r << ": {\n";
-      std::vector<char> used(P.C, 0);
-      for (int e = r; e < P.E; e += R)
-        for (int k = T.ep_off[e]; k < T.ep_off[e + 1]; k++) {
-          // factor words are the only entries >= 1<<24 (kind 1, 2) or small parameter ids; walk the program properly
-        }
-      // collect the compartments this role's edges read
-      for (int e = r; e < P.E; e += R) {
-        const int* ep = T.ep.data() + T.ep_off[e];
-        int n = *ep++;
-        for (int q = 0; q < n; q++) { int f = *ep++; if ((f >> 24) == 2) used[f & 0xffffff] = 1; }
-        int ns = *ep++;
-        for (int sidx = 0; sidx < ns; sidx++) { ep++; int nf = *ep++; for (int q = 0; q < nf; q++) { int f = *ep++; if ((f >> 24) == 2) used[f & 0xffffff] = 1; } }
-      }
-      for (int c = 0; c < P.C; c++) if (used[c]) o << "    const real y" << c << " = ys[" << c << " * LW];\n";
-      for (int e = r; e < P.E; e += R) {
-        const int* ep = T.ep.data() + T.ep_off[e];
-        int n = *ep++;
-        o << "    { real n = (real)1";
-        for (int q = 0; q < n; q++) o << " * " << valr(*ep++);
-        o << ";";
-        emit_denominator(o, ep, valr, "fl[" + std::to_string(e) + " * LW]");
-      }
-      o << "  } break;\n";
-    }
-    o << "  }\n}\n";
-    o << "__device__ __forceinline__ void dx_role(int role, const real* fl, real* Kc) {\n  switch (role) {\n";
-    for (int r = 0; r < R; r++) {
-      o << "  case " << r << ":\n";
-      for (int c = 0; c < P.C; c++) {
-        if (T.comp_role[c] != r) continue;
-        o << "    { real d = 0;";
-        for (int q = T.xg_off[c]; q < T.xg_off[c + 1]; q++) o << " d += fl[" << T.xg_src[q] << " * LW] * " << hexf(T.xg_coef[q]) << ";";
-        o << " Kc[" << c << " * LW] = d; }\n";
-      }
-      o << "    break;\n";
-    }
-    o << "  }\n}\n";
-    o << "template <int STRIDE> __device__ __forceinline__ void acc_role(int role, const real* col, real* out) {\n  switch (role) {\n";
-    for (int r = 0; r < R; r++) {
-      o << "  case " << r << ":\n";
-      for (int a = r; a < P.n_acc; a += R) {
-        o << "    out[" << a / R << "] = 0;";
-        for (int q = T.ag_off[a]; q < T.ag_off[a + 1]; q++) o << " out[" << a / R << "] += col[" << T.ag_src[q] << " * STRIDE] * " << hexf(T.ag_coef[q]) << ";";
-        o << "\n";
-      }
-      o << "    break;\n";
-    }
-    o << "  }\n}\n";
-  }
-
   // ---- streaming form for the env kernel's flow-slot regime: every flow is stored as soon as it is known and
   // scattered into dX on the fly (few live registers: y, d), instead of materialising all flows first
   if (P.LG > 32) {
@@ -1253,7 +1170,7 @@ std::string gen_spec(const epi_engine* h) {
   uint64_t k = 1469598103934665603ull;
   auto mix = [&](const void* p, size_t n) { for (size_t i = 0; i < n; i++) { k ^= ((const unsigned char*)p)[i]; k *= 1099511628211ull; } };
   mix(body.data(), body.size());
-  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 30 /* generator revision */};
+  size_t abi[4] = {sizeof(DevPlan), sizeof(DevState), sizeof(epi::StepArgs), 31 /* generator revision */};
   mix(abi, sizeof abi);
   char kb[32];
   snprintf(kb, sizeof kb, "%016llx", (unsigned long long)k);
@@ -1408,11 +1325,7 @@ void launch_cell(epi_engine* h, const DevState& S, const epi::StepArgs& a, cudaS
   if (h->spec_launch) {
     if (h->spec_launch(&h->plan, &S, &a, grid, h->cellW, (size_t)h->plan.cl.warp_bytes, nullptr) != 0)
       throw Invalid{"specialised cell kernel (host emulation)"};
-  } else if (h->plan.cl.roles > 1)
-    emu::run_warps(grid, h->cellW * h->plan.cl.roles, (size_t)h->plan.cl.warp_bytes, [&](char* smem, int tid, int group) {
-      epi::cteam::step_cta<real>(h->plan, S, a, smem, tid, group);
-    });
-  else
+  } else
     emu::run_warps(grid, h->cellW, (size_t)h->plan.cl.warp_bytes, [&](char* smem, int lane, int group) {
       epi::cell::step_warp<real>(h->plan, S, a, smem, lane, group);
     });
@@ -1420,11 +1333,6 @@ void launch_cell(epi_engine* h, const DevState& S, const epi::StepArgs& a, cudaS
   if (h->spec_launch) {
     int rc = h->spec_launch(&h->plan, &S, &a, grid, h->threads, h->smem_bytes, (void*)st);
     if (rc != 0) throw CudaFail{std::string("specialised cell kernel launch: ") + cudaGetErrorString((cudaError_t)rc)};
-  } else if (h->plan.cl.roles > 1) {
-    auto kern = epi::cteam::cell_team_kernel<real>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-    kern<<<grid, h->threads, h->smem_bytes, st>>>(h->plan, S, a);
-    CK(cudaGetLastError());
   } else {
     auto kern = epi::cell::cell_kernel<real>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));

@@ -9,9 +9,6 @@
 #if EPI_GRP_THREADS > 0
 #include "epi_grp.cuh"
 #endif
-#elif EPI_SPEC_ROLES > 1
-#include "epi_cellteam.cuh"
-#define EPI_SPEC_KERNEL epi::cteam::cell_team_kernel<epi::spec::real>
 #else
 #include "epi_cell.cuh"
 #define EPI_SPEC_KERNEL epi::cell::cell_kernel<epi::spec::real>
@@ -28,8 +25,6 @@ extern "C" int epi_spec_launch(const DevPlan* P, const DevState* S, const epi::S
     epi::env::Bx b = epi::env::bind(*P, *a, sm, tid, threads, cta);
     epi::env::step_cta<epi::spec::real>(*P, *S, *a, b, cta, grid);
   });
-#elif EPI_SPEC_ROLES > 1
-  return -1;
 #else
   emu::run_warps(grid, threads, smem, [&](char* sm, int lane, int group) {
     epi::cell::step_warp<epi::spec::real>(*P, *S, *a, sm, lane, group);
@@ -41,8 +36,16 @@ extern "C" int epi_spec_launch(const DevPlan* P, const DevState* S, const epi::S
 extern "C" int epi_spec_launch(const DevPlan* P, const DevState* S, const epi::StepArgs* a, int grid, int threads,
                                size_t smem, void* stream) {
   auto kern = EPI_SPEC_KERNEL;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
+  // the attribute is a property of the function, set when the size first appears (per device): a launch that is being
+  // captured into a CUDA graph makes no other API call than the launch itself
+  static size_t set_smem[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || set_smem[dev] != smem + 1) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    if (dev >= 0 && dev < 64) set_smem[dev] = smem + 1;
+  }
   kern<<<grid, threads, smem, (cudaStream_t)stream>>>(*P, *S, *a);
   return (int)cudaGetLastError();
 }

@@ -42,19 +42,23 @@ class ActorCritic(nn.Module):
         self.log_std = nn.Parameter(torch.full((act_dim,), init_log_std))
 
     def dist(self, obs):
-        return torch.distributions.Normal(torch.sigmoid(self.pi(obs)), self.log_std.exp())
+        # validate_args=False: the argument checks synchronise with the host (`.all()`), which is illegal inside the
+        # CUDA-graph capture of the rollout and wasted time everywhere else
+        return torch.distributions.Normal(torch.sigmoid(self.pi(obs)), self.log_std.exp(), validate_args=False)
+
+    def _logp(self, mean, a):
+        return (-0.5 * ((a - mean) / self.log_std.exp()) ** 2 - self.log_std - 0.5 * math.log(2 * math.pi)).sum(-1)
 
     @torch.no_grad()
     def act(self, obs, deterministic: bool = False, eps=None):
-        """eps: standard-normal noise [N, A] supplied by the caller (reproducible across rank layouts), else sampled"""
-        d = self.dist(obs)
+        """eps: standard-normal noise [N, A] supplied by the caller (reproducible across rank layouts), else sampled.
+        Plain tensor arithmetic (no torch.distributions object): capturable in a CUDA graph."""
+        mean = torch.sigmoid(self.pi(obs))
         if deterministic:
-            a = d.mean
-        elif eps is not None:
-            a = d.mean + d.stddev * eps
+            a = mean
         else:
-            a = d.sample()
-        return a, d.log_prob(a).sum(-1), self.v(obs).squeeze(-1)
+            a = mean + self.log_std.exp() * (eps if eps is not None else torch.randn_like(mean))
+        return a, self._logp(mean, a), self.v(obs).squeeze(-1)
 
     def evaluate(self, obs, act):
         d = self.dist(obs)

@@ -54,7 +54,7 @@ def _src_hash() -> str:
     if _SRC_HASH is None:
         import hashlib
         h = hashlib.sha1()
-        for f in ("epi_cell.cuh", "epi_cellteam.cuh", "epi_env.cuh", "epi_grp.cuh", "epi_rk.cuh", "epi_fdiv.cuh", "epi_kernels.cuh", "epi_plan.h", "epi_spec_main.cu"):
+        for f in ("epi_cell.cuh", "epi_env.cuh", "epi_grp.cuh", "epi_rk.cuh", "epi_fdiv.cuh", "epi_kernels.cuh", "epi_plan.h", "epi_spec_main.cu"):
             with open(os.path.join(CSRC, f), "rb") as fh:
                 h.update(fh.read())
         h.update(" ".join(NVCC_FLAGS + _extra_flags()).encode())

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 def build():
     out = os.path.join(HERE, "libepi_b200_emu.so")
     csrc = os.path.join(ROOT, "epipolicy_rl_b200", "csrc")
-    srcs = [os.path.join(csrc, f) for f in ("epi_engine.cu", "epi_kernels.cuh", "epi_cell.cuh", "epi_cellteam.cuh", "epi_env.cuh", "epi_grp.cuh", "epi_rk.cuh", "epi_fdiv.cuh", "epi_plan.h")] + [
+    srcs = [os.path.join(csrc, f) for f in ("epi_engine.cu", "epi_kernels.cuh", "epi_cell.cuh", "epi_env.cuh", "epi_grp.cuh", "epi_rk.cuh", "epi_fdiv.cuh", "epi_plan.h")] + [
         os.path.join(HERE, "cuda_runtime.h"), os.path.join(ROOT, "include", "epi_b200.h"), os.path.join(ROOT, "include", "epi_desc.h")]
     if (not os.path.exists(out)) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         subprocess.check_call(["g++", "-x", "c++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off",

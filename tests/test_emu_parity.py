@@ -93,12 +93,12 @@ def test_unsupported_programs_are_refused_not_approximated():
     assert ei.value.code == -2
 
 
-@pytest.mark.parametrize("knobs", [{"EPI_ROLES": "2"}, {"EPI_ROLES": "3"}, {"EPI_TEAM": "env", "EPI_ENV_FLOWSLOTS": "0"},
+@pytest.mark.parametrize("knobs", [{"EPI_TEAM": "env", "EPI_ENV_FLOWSLOTS": "0"},
                                    {"EPI_TEAM": "env", "EPI_ENV_FLOWSLOTS": "1"}, {"EPI_TEAM": "warp"}],
-                         ids=["roles2", "roles3", "env-flowsums", "env-flowslots", "warp-team"])
+                         ids=["env-flowsums", "env-flowslots", "warp-team"])
 def test_alternative_kernels_on_covid_c(knobs, monkeypatch):
     """The other kernels of the library on a shipped scenario whose episode includes rejected RK45 attempts:
-    the cell-team kernel (R cooperating warps), the env kernel in both flow regimes, the warp-team kernel."""
+    the env kernel in both flow regimes, the warp-team kernel."""
     for k, v in knobs.items():
         monkeypatch.setenv(k, v)
     d, z = load("COVID_C")

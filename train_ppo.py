@@ -33,7 +33,7 @@ def main():
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
     ap.add_argument("--updates", type=int, default=20)
     ap.add_argument("--n-steps", type=int, default=16)
-    ap.add_argument("--epochs", type=int, default=4)
+    ap.add_argument("--epochs", type=int, default=1, help="PPO epochs per update (configs/ppo_default.yaml: n_epochs 1)")
     ap.add_argument("--minibatches", type=int, default=4)
     ap.add_argument("--lr", type=float, default=3e-4)
     ap.add_argument("--precision", default="fp32")
