@@ -85,7 +85,8 @@ class BatchedPPO:
     def __init__(self, env, obs_dim: int, act_dim: int, obs_scale, n_steps: int = 16, n_epochs: int = 4,
                  minibatches: int = 4, gamma: float = 0.999, lam: float = 0.99, clip: float = 0.2,
                  lr: float = 3e-4, vf_coef: float = 0.974, ent_coef: float = 5.3e-8, max_grad_norm: float = 2.0,
-                 reward_scale: float = 1e-7, device="cuda", seed: int = 10, gather=None, use_graph: bool | None = None):
+                 reward_scale: float = 1e-7, device="cuda", seed: int = 10, gather=None, use_graph: bool | None = None,
+                 desync: int = 0):
         self.env, self.dev = env, torch.device(device)
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
@@ -105,6 +106,7 @@ class BatchedPPO:
         self._obs = None
         self.ep_return = None
         self._buf = None
+        self.desync = int(desync)  # episode length in gym steps: spread the envs' episode phases over it (0 = off)
         self._graph, self._graph_failed, self._warm = None, False, False
         self.use_graph = (self.dev.type == "cuda") if use_graph is None else use_graph
         # finished episodes of this rank's shard, kept on the device (no host sync inside the rollout)
@@ -169,6 +171,8 @@ class BatchedPPO:
             n = self._obs.shape[0]
             self.ep_return = torch.zeros(n, dtype=torch.float64, device=self.dev)
             self._alloc(n)
+            if self.desync > 1:
+                self._desynchronise(n)
         B, n = self._buf, self._obs.shape[0]
         # the fleet's noise for this rollout, this rank's slice of it (see the module docstring)
         eps = torch.randn((self.n_steps, self.world * n, self.act_dim), generator=self._noise, device=self.dev)
@@ -194,6 +198,21 @@ class BatchedPPO:
         last_v = allr[:, T * n * (D + A + 4):].reshape(-1)
         return (body[..., :D], body[..., D:D + A], body[..., D + A], body[..., D + A + 1], body[..., D + A + 2],
                 body[..., D + A + 3], last_v)
+
+    def _desynchronise(self, n):
+        """All envs of a fleet start on day 0, so a rollout of n_steps gym steps sees ONE phase of the epidemic (calm, peak,
+        tail) in every env and consecutive updates see different ones: the advantage baseline chases the phase instead
+        of the policy. Before the first rollout, env e (global index) is advanced (desync - 1 - e mod desync) gym steps
+        with uniform random actions: episode phases are then spread evenly and every rollout covers a whole episode's
+        worth of them. Runs once; the noise comes from the fleet generator (same on every rank layout)."""
+        L = self.desync
+        idx = torch.arange(self.rank * n, (self.rank + 1) * n, device=self.dev) % L
+        for t in range(L - 1):
+            u = torch.rand((self.world * n, self.act_dim), generator=self._noise, device=self.dev)[self.rank * n:(self.rank + 1) * n]
+            self.env.step(u.contiguous())
+            self.env.reset((idx > t).to(torch.uint8))  # envs whose offset is not reached yet start over
+        self._obs.copy_(self.env.epi.obs)
+        self.ep_return.zero_()
 
     def _capture(self):
         """capture the rollout into a CUDA graph (the first, eager rollout was the warm-up: allocator, cuBLAS handles,
@@ -229,7 +248,10 @@ class BatchedPPO:
                     loss = pg + self.vf_coef * vl - self.ent_coef * ent.mean()
                     self.opt.zero_grad(set_to_none=True)
                     loss.backward()
-                    nn.utils.clip_grad_norm_(self.ac.parameters(), self.max_grad_norm)
+                    # policy and value networks are separate: each is clipped on its own norm (one joint norm lets the
+                    # value loss, large while the critic is still fitting returns of O(10^2), throttle the policy step)
+                    nn.utils.clip_grad_norm_(list(self.ac.pi.parameters()) + [self.ac.log_std], self.max_grad_norm)
+                    nn.utils.clip_grad_norm_(self.ac.v.parameters(), self.max_grad_norm)
                     self.opt.step()
             stats = {"pg_loss": float(pg.detach()), "v_loss": float(vl.detach()), "entropy": float(ent.mean().detach())}
         if self.world > 1:  # the learner's weights go back to every shard's replica

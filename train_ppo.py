@@ -33,7 +33,7 @@ def main():
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
     ap.add_argument("--updates", type=int, default=20)
     ap.add_argument("--n-steps", type=int, default=16)
-    ap.add_argument("--epochs", type=int, default=1, help="PPO epochs per update (configs/ppo_default.yaml: n_epochs 1)")
+    ap.add_argument("--epochs", type=int, default=2, help="PPO epochs per update (configs/ppo_default.yaml has n_epochs 1 for batches of 128 samples)")
     ap.add_argument("--minibatches", type=int, default=4)
     ap.add_argument("--lr", type=float, default=3e-4)
     ap.add_argument("--precision", default="fp32")
@@ -120,7 +120,8 @@ def main():
     log = lambda s: emit({**s, "n_gpus": world})  # noqa: E731
     if args.algo == "ppo":
         ppo = BatchedPPO(env, env.epi.obs_dim, desc.A, obs_scale=pop, n_steps=args.n_steps, n_epochs=args.epochs,
-                         minibatches=args.minibatches, lr=args.lr, device=dev, use_graph=not args.no_graph)
+                         minibatches=args.minibatches, lr=args.lr, device=dev, use_graph=not args.no_graph,
+                         desync=(desc.horizon + 6) // 7)
         hist = ppo.train(2, log=log)  # untimed: eager warm-up rollout, graph capture, cuBLAS / Adam state start-up
         torch.cuda.synchronize()
         t0 = time.perf_counter()
