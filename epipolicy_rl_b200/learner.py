@@ -86,7 +86,7 @@ class BatchedPPO:
                  minibatches: int = 4, gamma: float = 0.999, lam: float = 0.99, clip: float = 0.2,
                  lr: float = 3e-4, vf_coef: float = 0.974, ent_coef: float = 5.3e-8, max_grad_norm: float = 2.0,
                  reward_scale: float = 1e-7, device="cuda", seed: int = 10, gather=None, use_graph: bool | None = None,
-                 desync: int = 0):
+                 desync: int = 0, update_mode: str = "learner"):
         self.env, self.dev = env, torch.device(device)
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
@@ -106,6 +106,8 @@ class BatchedPPO:
         self._obs = None
         self.ep_return = None
         self._buf = None
+        assert update_mode in ("learner", "sharded")
+        self.update_mode = update_mode
         self.desync = int(desync)  # episode length in gym steps: spread the envs' episode phases over it (0 = off)
         self._graph, self._graph_failed, self._warm = None, False, False
         self.use_graph = (self.dev.type == "cuda") if use_graph is None else use_graph
@@ -187,7 +189,7 @@ class BatchedPPO:
         else:
             self._rollout_body()  # the first rollout runs eagerly: it is also the warm-up a graph capture needs
             self._warm = True
-        if self.world == 1:
+        if self.world == 1 or self.update_mode == "sharded":
             return tuple(B[k] for k in ("O", "A", "LP", "V", "R", "D", "last_v"))
         # ONE exchange per update: the packed rollout record of every shard (rank-major = global env order)
         T, D, A = self.n_steps, self.obs_dim, self.act_dim
@@ -231,13 +233,27 @@ class BatchedPPO:
             torch.cuda.synchronize(self.dev)
 
     def update(self, batch):
+        """`learner` mode (the north_star's wording): the gathered rollout of the whole fleet is optimised on rank 0 and
+        the weights are broadcast. `sharded` mode: every rank optimises on ITS OWN shard's rollout (no rollout exchange
+        at all), the flattened gradients of every minibatch step are averaged with one all-reduce, and the advantage
+        normalisation uses fleet-wide moments - the update then costs what it costs on one GPU however many GPUs step
+        envs, and the replicas stay bit-identical without a broadcast (same averaged gradients, same optimiser state)."""
         O, A, LP, V, R, D, last_v = batch
         adv, ret = gae(R, V, D, last_v, self.gamma, self.lam)
         O, A, LP, adv, ret = (x.reshape(-1, *x.shape[2:]) for x in (O, A, LP, adv, ret))
-        adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+        sharded = self.world > 1 and self.update_mode == "sharded"
+        if sharded:
+            m = torch.stack([adv.sum(dtype=torch.float64), (adv.double() ** 2).sum(), torch.tensor(float(adv.numel()), dtype=torch.float64, device=adv.device)])
+            dist.all_reduce(m)
+            mean = m[0] / m[2]
+            std = ((m[1] - m[2] * mean ** 2) / (m[2] - 1)).clamp_min(0).sqrt()
+            adv = ((adv - mean.float()) / (std.float() + 1e-8))
+        else:
+            adv = (adv - adv.mean()) / (adv.std() + 1e-8)
         n = O.shape[0]
         stats = {}
-        if self.rank == 0:
+        if self.rank == 0 or sharded:
+            params = list(self.ac.parameters())
             for _ in range(self.n_epochs):
                 perm = torch.randperm(n, device=self.dev, generator=self._perm)
                 for idx in perm.chunk(self.minibatches):
@@ -248,13 +264,21 @@ class BatchedPPO:
                     loss = pg + self.vf_coef * vl - self.ent_coef * ent.mean()
                     self.opt.zero_grad(set_to_none=True)
                     loss.backward()
+                    if sharded:
+                        flat = torch.cat([p.grad.reshape(-1) for p in params])
+                        dist.all_reduce(flat)
+                        flat /= self.world
+                        off = 0
+                        for p in params:
+                            p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+                            off += p.numel()
                     # policy and value networks are separate: each is clipped on its own norm (one joint norm lets the
                     # value loss, large while the critic is still fitting returns of O(10^2), throttle the policy step)
                     nn.utils.clip_grad_norm_(list(self.ac.pi.parameters()) + [self.ac.log_std], self.max_grad_norm)
                     nn.utils.clip_grad_norm_(self.ac.v.parameters(), self.max_grad_norm)
                     self.opt.step()
             stats = {"pg_loss": float(pg.detach()), "v_loss": float(vl.detach()), "entropy": float(ent.mean().detach())}
-        if self.world > 1:  # the learner's weights go back to every shard's replica
+        if self.world > 1 and not sharded:  # the learner's weights go back to every shard's replica
             flat = torch.cat([p.data.reshape(-1) for p in self.ac.parameters()])
             dist.broadcast(flat, 0)
             off = 0
@@ -268,7 +292,12 @@ class BatchedPPO:
         for u in range(n_updates):
             batch = self.collect()
             st = self.update(batch)
-            mean_r = float(batch[4].sum(0).mean()) / self.reward_scale / self.n_steps
+            mr = batch[4].sum(0).mean()
+            if self.world > 1 and self.update_mode == "sharded":
+                mr = mr.clone()
+                dist.all_reduce(mr)
+                mr = mr / self.world
+            mean_r = float(mr) / self.reward_scale / self.n_steps
             n_ep, mean_ep = self.finished_episodes
             st.update(update=u, mean_step_reward=mean_r, episodes=n_ep, mean_episode_return=mean_ep)
             hist.append(st)

@@ -123,6 +123,32 @@ def test_two_rank_rollout_equals_one_rank_rollout(tmp_path):
         ppo.update(batch)
 
 
+def _sharded_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 16
+    env = DetEnv(n, rank * n, world * n)
+    ppo = BatchedPPO(env, 3, 2, obs_scale=np.ones(3), n_steps=5, n_epochs=2, lr=3e-3, reward_scale=1.0, device="cpu", seed=5,
+                     update_mode="sharded")
+    w0 = torch.cat([p.data.reshape(-1) for p in ppo.ac.parameters()]).clone()
+    hist = ppo.train(6)
+    flat = torch.cat([p.data.reshape(-1) for p in ppo.ac.parameters()])
+    assert not torch.equal(flat, w0)
+    torch.save((flat, [h["mean_step_reward"] for h in hist]), os.path.join(out, f"s{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_sharded_update_keeps_replicas_identical(tmp_path):
+    """`sharded` update mode: no rollout exchange; gradients are averaged per minibatch step, so every rank applies the
+    same optimiser steps and the replicas stay bit-identical without a weight broadcast; the logged reward is the
+    fleet's."""
+    port = 29350 + os.getpid() % 100
+    mp.spawn(_sharded_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    (w0, r0), (w1, r1) = torch.load(tmp_path / "s0.pt"), torch.load(tmp_path / "s1.pt")
+    assert torch.equal(w0, w1)
+    assert r0 == r1
+
+
 def test_gae_matches_naive_fp64_loop_with_episode_ends():
     T, N = 16, 7
     g = torch.Generator().manual_seed(4)

@@ -38,6 +38,8 @@ def main():
     ap.add_argument("--lr", type=float, default=3e-4)
     ap.add_argument("--precision", default="fp32")
     ap.add_argument("--algo", default="ppo", choices=["ppo", "sac"], help="runner.py --algo")
+    ap.add_argument("--update", default="learner", choices=["learner", "sharded"],
+                    help="learner: all-gather the rollouts, optimise on rank 0, broadcast; sharded: every rank optimises on its shard, gradients all-reduced")
     ap.add_argument("--no-graph", action="store_true", help="eager rollout instead of the captured CUDA graph")
     ap.add_argument("--jsonl", default="", help="append the per-update JSON lines and the summary to this file")
     args = ap.parse_args()
@@ -121,7 +123,7 @@ def main():
     if args.algo == "ppo":
         ppo = BatchedPPO(env, env.epi.obs_dim, desc.A, obs_scale=pop, n_steps=args.n_steps, n_epochs=args.epochs,
                          minibatches=args.minibatches, lr=args.lr, device=dev, use_graph=not args.no_graph,
-                         desync=(desc.horizon + 6) // 7)
+                         desync=(desc.horizon + 6) // 7, update_mode=args.update)
         hist = ppo.train(2, log=log)  # untimed: eager warm-up rollout, graph capture, cuBLAS / Adam state start-up
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -150,6 +152,7 @@ def main():
           "fraction_of_env_only": rate / env_only, "train_seconds": dt,
           "mean_step_reward": {"trained": trained, **base},
           "beats_lax": trained > base["lax"], "beats_random": trained > base["random"],
+          "update_mode": args.update if args.algo == "ppo" else None, "epochs": args.epochs, "minibatches": args.minibatches,
           "first_update_reward": hist[0]["mean_step_reward"], "last_update_reward": hist[-1]["mean_step_reward"], **extra})
     env.close()
     if world > 1:
