@@ -92,7 +92,10 @@ class BatchedPPO:
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         torch.manual_seed(seed)  # identical replicas on every rank (same init, weights broadcast after every update)
         self.ac = ActorCritic(obs_dim, act_dim).to(self.dev)
-        self.opt = torch.optim.Adam(self.ac.parameters(), lr=lr)
+        self.use_graph = (self.dev.type == "cuda") if use_graph is None else use_graph
+        # capturable: the step counters live on the device, so the optimiser steps can sit inside the update graph (set
+        # with and without graphs: both paths then run the same kernels and produce the same weights)
+        self.opt = torch.optim.Adam(self.ac.parameters(), lr=lr, capturable=self.dev.type == "cuda")
         self.obs_scale = torch.as_tensor(obs_scale, dtype=torch.float32, device=self.dev)
         self.n_steps, self.n_epochs, self.minibatches = n_steps, n_epochs, minibatches
         self.gamma, self.lam, self.clip = gamma, lam, clip
@@ -110,7 +113,7 @@ class BatchedPPO:
         self.update_mode = update_mode
         self.desync = int(desync)  # episode length in gym steps: spread the envs' episode phases over it (0 = off)
         self._graph, self._graph_failed, self._warm = None, False, False
-        self.use_graph = (self.dev.type == "cuda") if use_graph is None else use_graph
+        self._ugraph, self._ugraph_failed, self._uwarm, self._ubuf = None, False, False, None
         # finished episodes of this rank's shard, kept on the device (no host sync inside the rollout)
         self._fin_sum = torch.zeros((), dtype=torch.float64, device=self.dev)
         self._fin_cnt = torch.zeros((), dtype=torch.int64, device=self.dev)
@@ -237,47 +240,29 @@ class BatchedPPO:
         the weights are broadcast. `sharded` mode: every rank optimises on ITS OWN shard's rollout (no rollout exchange
         at all), the flattened gradients of every minibatch step are averaged with one all-reduce, and the advantage
         normalisation uses fleet-wide moments - the update then costs what it costs on one GPU however many GPUs step
-        envs, and the replicas stay bit-identical without a broadcast (same averaged gradients, same optimiser state)."""
-        O, A, LP, V, R, D, last_v = batch
-        adv, ret = gae(R, V, D, last_v, self.gamma, self.lam)
-        O, A, LP, adv, ret = (x.reshape(-1, *x.shape[2:]) for x in (O, A, LP, adv, ret))
+        envs, and the replicas stay bit-identical without a broadcast (same averaged gradients, same optimiser state).
+
+        On a CUDA device the whole update (GAE, advantage normalisation, n_epochs x minibatches optimiser steps with
+        their gradient all-reduces) is ONE CUDA graph over static buffers, captured after the first (eager) update and
+        replayed afterwards; only the minibatch permutations are drawn outside it."""
         sharded = self.world > 1 and self.update_mode == "sharded"
-        if sharded:
-            m = torch.stack([adv.sum(dtype=torch.float64), (adv.double() ** 2).sum(), torch.tensor(float(adv.numel()), dtype=torch.float64, device=adv.device)])
-            dist.all_reduce(m)
-            mean = m[0] / m[2]
-            std = ((m[1] - m[2] * mean ** 2) / (m[2] - 1)).clamp_min(0).sqrt()
-            adv = ((adv - mean.float()) / (std.float() + 1e-8))
-        else:
-            adv = (adv - adv.mean()) / (adv.std() + 1e-8)
-        n = O.shape[0]
         stats = {}
         if self.rank == 0 or sharded:
-            params = list(self.ac.parameters())
-            for _ in range(self.n_epochs):
-                perm = torch.randperm(n, device=self.dev, generator=self._perm)
-                for idx in perm.chunk(self.minibatches):
-                    lp, ent, v = self.ac.evaluate(O[idx], A[idx])
-                    ratio = (lp - LP[idx]).exp()
-                    pg = -torch.min(ratio * adv[idx], ratio.clamp(1 - self.clip, 1 + self.clip) * adv[idx]).mean()
-                    vl = ((v - ret[idx]) ** 2).mean()
-                    loss = pg + self.vf_coef * vl - self.ent_coef * ent.mean()
-                    self.opt.zero_grad(set_to_none=True)
-                    loss.backward()
-                    if sharded:
-                        flat = torch.cat([p.grad.reshape(-1) for p in params])
-                        dist.all_reduce(flat)
-                        flat /= self.world
-                        off = 0
-                        for p in params:
-                            p.grad.copy_(flat[off:off + p.numel()].view_as(p))
-                            off += p.numel()
-                    # policy and value networks are separate: each is clipped on its own norm (one joint norm lets the
-                    # value loss, large while the critic is still fitting returns of O(10^2), throttle the policy step)
-                    nn.utils.clip_grad_norm_(list(self.ac.pi.parameters()) + [self.ac.log_std], self.max_grad_norm)
-                    nn.utils.clip_grad_norm_(self.ac.v.parameters(), self.max_grad_norm)
-                    self.opt.step()
-            stats = {"pg_loss": float(pg.detach()), "v_loss": float(vl.detach()), "entropy": float(ent.mean().detach())}
+            U = self._update_buffers(batch)
+            for e in range(self.n_epochs):
+                U["perm"][e].copy_(torch.randperm(U["perm"].shape[1], device=self.dev, generator=self._perm))
+            if self.use_graph and not self._ugraph_failed and self._uwarm:
+                if self._ugraph is None:
+                    self._capture_update(U)
+                if self._ugraph is not None:
+                    self._ugraph.replay()
+                else:
+                    self._update_body(U)
+            else:
+                self._update_body(U)  # the first update runs eagerly: warm-up of cuBLAS, Adam state, NCCL
+                self._uwarm = True
+            pg, vl, ent = U["stats"].tolist()  # the update's one host synchronisation
+            stats = {"pg_loss": pg, "v_loss": vl, "entropy": ent}
         if self.world > 1 and not sharded:  # the learner's weights go back to every shard's replica
             flat = torch.cat([p.data.reshape(-1) for p in self.ac.parameters()])
             dist.broadcast(flat, 0)
@@ -286,6 +271,84 @@ class BatchedPPO:
                 p.data.copy_(flat[off:off + p.numel()].view_as(p))
                 off += p.numel()
         return stats
+
+    def _update_buffers(self, batch):
+        """static inputs of the update: the rollout tensors themselves when they already are this learner's static
+        rollout buffers (one rank, or `sharded`), else (the gathered fleet rollout on the learner rank) copies of them"""
+        names = ("O", "A", "LP", "V", "R", "D", "last_v")
+        if self._ubuf is None:
+            own = self._buf is not None and all(x is self._buf[k] for k, x in zip(names, batch))
+            U = {k: (x if own else torch.empty_like(x, memory_format=torch.contiguous_format)) for k, x in zip(names, batch)}
+            n = batch[4].numel()
+            U["perm"] = torch.zeros((self.n_epochs, n), dtype=torch.int64, device=self.dev)
+            U["stats"] = torch.zeros(3, dtype=torch.float32, device=self.dev)
+            U["own"] = own
+            self._ubuf = U
+        U = self._ubuf
+        if not U["own"]:
+            for k, x in zip(names, batch):
+                U[k].copy_(x)
+        return U
+
+    def _update_body(self, U):
+        """GAE, advantage normalisation and the optimiser steps over the static buffers; no host synchronisation (this is
+        the region the update graph captures)"""
+        sharded = self.world > 1 and self.update_mode == "sharded"
+        adv, ret = gae(U["R"], U["V"], U["D"], U["last_v"], self.gamma, self.lam)
+        O, A, LP, adv, ret = (x.reshape(-1, *x.shape[2:]) for x in (U["O"], U["A"], U["LP"], adv, ret))
+        if sharded:
+            m = torch.stack([adv.sum(dtype=torch.float64), (adv.double() ** 2).sum(),
+                             torch.full((), float(adv.numel()), dtype=torch.float64, device=adv.device)])
+            dist.all_reduce(m)
+            mean = m[0] / m[2]
+            std = ((m[1] - m[2] * mean ** 2) / (m[2] - 1)).clamp_min(0).sqrt()
+            adv = ((adv - mean.float()) / (std.float() + 1e-8))
+        else:
+            adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+        params = list(self.ac.parameters())
+        pi_params = list(self.ac.pi.parameters()) + [self.ac.log_std]
+        v_params = list(self.ac.v.parameters())
+        for e in range(self.n_epochs):
+            for idx in U["perm"][e].chunk(self.minibatches):
+                lp, ent, v = self.ac.evaluate(O[idx], A[idx])
+                ratio = (lp - LP[idx]).exp()
+                pg = -torch.min(ratio * adv[idx], ratio.clamp(1 - self.clip, 1 + self.clip) * adv[idx]).mean()
+                vl = ((v - ret[idx]) ** 2).mean()
+                ent = ent.mean()
+                loss = pg + self.vf_coef * vl - self.ent_coef * ent
+                self.opt.zero_grad(set_to_none=True)
+                loss.backward()
+                if sharded:
+                    flat = torch.cat([p.grad.reshape(-1) for p in params])
+                    dist.all_reduce(flat)
+                    flat /= self.world
+                    off = 0
+                    for p in params:
+                        p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+                        off += p.numel()
+                # policy and value networks are separate: each is clipped on its own norm (one joint norm lets the
+                # value loss, large while the critic is still fitting returns of O(10^2), throttle the policy step)
+                nn.utils.clip_grad_norm_(pi_params, self.max_grad_norm)
+                nn.utils.clip_grad_norm_(v_params, self.max_grad_norm)
+                self.opt.step()
+        U["stats"].copy_(torch.stack([pg.detach(), vl.detach(), ent.detach()]))
+
+    def _capture_update(self, U):
+        """capture the update into a CUDA graph (the first, eager update was the warm-up). Gradients are dropped first so
+        that the captured backward allocates them from the graph's pool. Any failure leaves the eager path in charge."""
+        try:
+            torch.cuda.synchronize(self.dev)
+            self.opt.zero_grad(set_to_none=True)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._update_body(U)
+            self._ugraph = g
+        except Exception as e:  # noqa: BLE001
+            import sys
+            print(f"[epi-b200] update graph capture failed ({type(e).__name__}: {e}); eager update", file=sys.stderr)
+            self._ugraph, self._ugraph_failed = None, True
+            torch.cuda.synchronize(self.dev)
+            self.opt.zero_grad(set_to_none=True)
 
     def train(self, n_updates: int, log=None):
         hist = []

@@ -286,8 +286,9 @@ def test_batched_ppo_runs_on_device():
 
 def test_ppo_graph_rollout_equals_eager_rollout_and_gae_on_device():
     """learner numerics on the GPU: (1) the rollout replayed from the captured CUDA graph is the rollout the eager loop
-    collects (same seeds, same envs: bit for bit), update after update; (2) GAE on the device against a naive fp64
-    loop on the host."""
+    collects (same seeds, same envs: bit for bit), update after update - which also pins the captured update graph,
+    since the rollout of update u is drawn with the weights the updates before it produced; (2) GAE on the device
+    against a naive fp64 loop on the host."""
     from epipolicy_rl_b200.env import BatchedEpiEnv
     from epipolicy_rl_b200.learner import BatchedPPO, gae
     d, _ = load("COVID_A")
@@ -303,11 +304,15 @@ def test_ppo_graph_rollout_equals_eager_rollout_and_gae_on_device():
             out.append([x.clone() for x in batch])
             ppo.update(batch)
         assert (ppo._graph is not None) == use_graph, "the rollout graph must be in use when asked for"
+        assert (ppo._ugraph is not None) == use_graph, "the update graph must be in use when asked for"
+        out.append([p.detach().clone() for p in ppo.ac.parameters()])
         runs.append(out)
         env.close()
     for u in range(3):
         for a, b in zip(runs[0][u], runs[1][u]):
             assert torch.equal(a, b), f"update {u}: graph and eager rollouts differ"
+    for a, b in zip(runs[0][3], runs[1][3]):  # (3) the weights after three updates (eager, captured, replayed)
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-7), "graph and eager updates differ"
     O, A, LP, V, R, D, last_v = runs[0][2]
     adv, ret = gae(R, V, D, last_v, 0.999, 0.99)
     r64, v64, d64, l64 = (x.double().cpu() for x in (R, V, D, last_v))

@@ -129,7 +129,7 @@ def main():
         t0 = time.perf_counter()
         hist += ppo.train(args.updates, log=log)
         policy = lambda o, i: ppo.ac.act(ppo._norm(o), deterministic=True)[0].clamp(0, 1).contiguous()  # noqa: E731
-        extra = {"rollout_graph": ppo._graph is not None}
+        extra = {"rollout_graph": ppo._graph is not None, "update_graph": ppo._ugraph is not None}
     else:
         # the same number of gym steps as the PPO run: `updates` x `n_steps` collect steps, gradient steps after each
         sac = BatchedSAC(env, env.epi.obs_dim, desc.A, obs_scale=pop, lr=args.lr, batch_size=4096, gamma=0.98, tau=0.08,
