@@ -203,7 +203,8 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
     if (it == cls_id.end()) { it = cls_id.emplace(ops, (int)cls_list.size()).first; cls_list.push_back(ops); }
     return it->second;
   };
-  int has_ft_ops = 0;
+  int has_ft_ops = 0, has_mob_ops = 0;
+  std::vector<int> mob_cls;
   {
     // per op masks
     struct OpM { int kind; std::vector<uint8_t> a, l, f, g, g2; };
@@ -214,7 +215,28 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
       if (om[o].kind == EPI_OP_PARAM_MUL) { om[o].a = mask(a[0], PP); om[o].l = mask(a[1], L); om[o].f = mask(a[2], F); om[o].g = mask(a[3], G); }
       else if (om[o].kind == EPI_OP_FI_MUL) { om[o].l = mask(a[0], L); om[o].f = mask(a[1], F); om[o].g = mask(a[2], G); om[o].g2 = mask(a[3], G); }
       else if (om[o].kind == EPI_OP_FT_MUL) { om[o].l = mask(a[0], L); om[o].f = mask(a[1], F); om[o].g = mask(a[2], G); has_ft_ops = 1; }
-      else if (om[o].kind == EPI_OP_MOB_MUL) throw Unsupported{"mobility multipliers (sim.apply with locale-from/locale-to) with a non-empty selection"};
+      else if (om[o].kind == EPI_OP_MOB_MUL) {
+        // sim.apply({'locale-from', 'locale-to'}, m): CooMatrix.pairwise_multiply on the mode's pattern
+        // (core/executor.py:121-127, matrix/coo.py:112-117): a = mode, g = groups, l = rows (from), f = columns (to)
+        if (a[0] < 0 || a[0] >= d.M) throw Unsupported{"mobility multiplier on an unknown mode"};
+        om[o].a = std::vector<uint8_t>(1, (uint8_t)a[0]); om[o].g = mask(a[1], G); om[o].l = mask(a[2], L); om[o].f = mask(a[3], L);
+        has_mob_ops = 1;
+      }
+    }
+    if (has_mob_ops) {
+      // multiplier class of every mobility cell (mode, group, pattern entry): the MOB_MUL ops covering it, in op order
+      mob_cls.assign((size_t)G * d.MODE_NNZ_TOTAL, 0);
+      for (int m = 0; m < d.M; m++) {
+        const int32_t* ip = d.mode_indptr + (size_t)m * (L + 1);
+        const int32_t* ix = d.mode_indices + d.mode_off[m];
+        const int nnz_m = d.mode_off[m + 1] - d.mode_off[m];
+        for (int g = 0; g < G; g++) for (int r = 0; r < L; r++) for (int k = ip[r]; k < ip[r + 1]; k++) {
+          std::vector<int> ops;
+          for (int o = 0; o < d.NOP; o++)
+            if (om[o].kind == EPI_OP_MOB_MUL && om[o].a[0] == m && om[o].g[g] && om[o].l[r] && om[o].f[ix[k]]) ops.push_back(o);
+          mob_cls[(size_t)G * d.mode_off[m] + (size_t)g * nnz_m + k] = get_cls(ops);
+        }
+      }
     }
     for (int lc = 0; lc < n_lc; lc++) {
       int l = rep[lc];
@@ -244,6 +266,8 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
     }
   }
   P.has_ft_ops = has_ft_ops;
+  P.mob_dyn = has_mob_ops;
+  P.M = d.M; P.nmob = G * d.MODE_NNZ_TOTAL;
   P.n_cls = (int)cls_list.size();
   std::vector<int> cls_off{0}, cls_op;
   for (auto& v : cls_list) { cls_op.insert(cls_op.end(), v.begin(), v.end()); cls_off.push_back((int)cls_op.size()); }
@@ -269,6 +293,7 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
   // ---- constant combined mobility (no mobility ops): get_normalized_matrix (matrix/coo.py:173-188)
   // with all multipliers 1, then compute_combined_mobility (core_optimize.py:69-92) in f32
   std::vector<float> mx_csr((size_t)G * d.nnz, 0.0f), mx_csc((size_t)G * d.nnz, 0.0f);
+  std::vector<int> comb_src, csc_of_csr;
   {
     std::vector<std::vector<float>> red(d.M);
     for (int m = 0; m < d.M; m++) {
@@ -287,17 +312,20 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
       }
     }
     std::vector<int> cptr(d.csc_indptr, d.csc_indptr + L + 1), mi(d.M);
+    comb_src.assign((size_t)d.M * d.nnz, -1); csc_of_csr.assign(d.nnz, 0);
     for (int r = 0; r < L; r++) {
       for (int m = 0; m < d.M; m++) mi[m] = d.mode_indptr[(size_t)m * (L + 1) + r];
       for (int k = d.csr_indptr[r]; k < d.csr_indptr[r + 1]; k++) {
         int c = d.csr_indices[k];
         int dest = cptr[c]++;
+        csc_of_csr[k] = dest;
         for (int m = 0; m < d.M; m++) {
           const int32_t* ip = d.mode_indptr + (size_t)m * (L + 1);
           const int32_t* ix = d.mode_indices + d.mode_off[m];
           int nnz_m = d.mode_off[m + 1] - d.mode_off[m];
           if (mi[m] < ip[r + 1] && c == ix[mi[m]]) {
             for (int g = 0; g < G; g++) mx_csr[(size_t)g * d.nnz + k] += d.mode_bias[m] * red[m][(size_t)g * nnz_m + mi[m]];
+            comb_src[(size_t)m * d.nnz + k] = mi[m];  // the union entry's position in mode m's pattern
             mi[m]++;
           }
         }
@@ -309,7 +337,7 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
   // dense column / row of every cell for tiny locale counts (specialised cell kernel); only when the pattern's
   // indices are ascending, so that the dense loop adds the non-zeros in the reference's order
   std::vector<float> dense_csc, dense_csr;
-  if (L <= 4) {
+  if (L <= 4 && !has_mob_ops) {  // (with mobility ops the values are per env and per day: the env's own tables)
     bool asc = true;
     for (int r = 0; r < L && asc; r++) {
       for (int k = d.csr_indptr[r] + 1; k < d.csr_indptr[r + 1]; k++) asc = asc && d.csr_indices[k - 1] < d.csr_indices[k];
@@ -548,6 +576,8 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
     P.o_Tnum = take(4 * (int64_t)n_lc * F * G * G); P.o_Tden = take(has_ft_ops ? rs * (int64_t)n_lc * F * G * G : 0);
     P.o_fi_y = take(4 * (int64_t)n_lc * F * G * G); P.o_fi_gap = take(4 * (int64_t)n_lc * F * G * G);
     P.o_ft_y = take(4 * (int64_t)n_lc * F * G); P.o_ft_gap = take(4 * (int64_t)n_lc * F * G);
+    P.o_mob_y = take(has_mob_ops ? 4 * (int64_t)P.nmob : 0); P.o_mob_g = take(has_mob_ops ? 4 * (int64_t)P.nmob : 0);
+    P.o_mxr = take(has_mob_ops ? 4 * (int64_t)G * d.nnz : 0); P.o_mxc = take(has_mob_ops ? 4 * (int64_t)G * d.nnz : 0);
     P.small_bytes = o;
     o = 0;
     const int64_t CLG = P.CLG, nA = (int64_t)P.n_acc * LG;
@@ -593,6 +623,10 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
   }
   P.mob_dense_csc = dense_csc.empty() ? nullptr : h->up(dense_csc);
   P.mob_dense_csr = dense_csr.empty() ? nullptr : h->up(dense_csr);
+  P.mob_org = h->up(vec(d.mode_origin, (size_t)G * d.MODE_NNZ_TOTAL)); P.mob_cls = h->up(has_mob_ops ? mob_cls : std::vector<int>(1, 0));
+  P.mode_indptr = h->up(vec(d.mode_indptr, (size_t)d.M * (L + 1))); P.mode_indices = h->up(vec(d.mode_indices, d.MODE_NNZ_TOTAL));
+  P.mode_off = h->up(vec(d.mode_off, d.M + 1)); P.mode_bias = h->up(vec(d.mode_bias, d.M));
+  P.comb_src = h->up(comb_src); P.csc_of_csr = h->up(csc_of_csr);
   P.csr_indptr = h->up(vec(d.csr_indptr, L + 1)); P.csr_indices = h->up(vec(d.csr_indices, d.nnz));
   P.csc_indptr = h->up(vec(d.csc_indptr, L + 1)); P.csc_indices = h->up(vec(d.csc_indices, d.nnz));
   P.cls_off = h->up(cls_off); P.cls_op = h->up(cls_op);
@@ -648,6 +682,8 @@ void build_cell_layout(epi_engine* h, int W) {
   Y.e_fi_y = take(4 * n_lc * F * G * G); Y.e_fi_gap = take(4 * n_lc * F * G * G);
   Y.e_ft_y = take(4 * n_lc * F * G); Y.e_ft_gap = take(4 * n_lc * F * G);
   Y.e_cost = take(8 * nC); Y.e_crY = take(8 * nC); Y.e_crD = take(8 * nC);
+  Y.e_mob_y = take(P.mob_dyn ? 4 * (int64_t)P.nmob : 0); Y.e_mob_g = take(P.mob_dyn ? 4 * (int64_t)P.nmob : 0);
+  Y.e_mxr = take(P.mob_dyn ? 4 * G * P.nnz : 0); Y.e_mxc = take(P.mob_dyn ? 4 * G * P.nnz : 0);
   Y.e_bytes = o;
   Y.warp_bytes = Y.e_base + Y.e_bytes * Y.epw;
 }
@@ -838,7 +874,7 @@ std::string gen_spec(const epi_engine* h) {
     << ", LG = " << P.LG << ", CLG = " << P.CLG << ", nnz = " << P.nnz << ", n_lc = " << P.n_lc << ", E = " << P.E
     << ", NG = " << P.NG << ", NSRC = " << P.NSRC << ", n_acc = " << P.n_acc << ", n_slot = " << P.n_slot
     << ", has_ft_ops = " << P.has_ft_ops << ", has_src64 = " << P.has_src64
-    << ", dense_mob = " << (P.mob_dense_csc ? 1 : 0) << ", flow_slots = " << (P.LG > 32 ? P.el.flow_slots : 0) << ", R = " << (P.cl.roles > 0 ? P.cl.roles : 1) << ";\n";
+    << ", dense_mob = " << (P.mob_dense_csc ? 1 : 0) << ", mob_dyn = " << P.mob_dyn << ", flow_slots = " << (P.LG > 32 ? P.el.flow_slots : 0) << ", R = " << (P.cl.roles > 0 ? P.cl.roles : 1) << ";\n";
   o << "constexpr int big = " << (P.LG > 32 ? 1 : 0) << ";  // 1: env kernel (epi_env.cuh), 0: cell kernel (epi_cell.cuh)\n";
   if (P.LG <= 32) {
     const CellLayout& Y = P.cl;  // built for 32-lane warps
@@ -850,7 +886,8 @@ std::string gen_spec(const epi_engine* h) {
       << ", e_mpg = " << Y.e_mpg << ", e_mpt0 = " << Y.e_mpt0 << ", e_mpFy = " << Y.e_mpFy << ", e_mpFg = " << Y.e_mpFg
       << ", e_coefS = " << Y.e_coefS << ", e_Tnum = " << Y.e_Tnum << ", e_Tden = " << Y.e_Tden << ", e_fi_y = " << Y.e_fi_y
       << ", e_fi_gap = " << Y.e_fi_gap << ", e_ft_y = " << Y.e_ft_y << ", e_ft_gap = " << Y.e_ft_gap << ", e_cost = " << Y.e_cost
-      << ", e_crY = " << Y.e_crY << ", e_crD = " << Y.e_crD << ", warp_bytes = " << Y.warp_bytes << ";\n";
+      << ", e_crY = " << Y.e_crY << ", e_crD = " << Y.e_crD << ", e_mob_y = " << Y.e_mob_y << ", e_mob_g = " << Y.e_mob_g
+      << ", e_mxr = " << Y.e_mxr << ", e_mxc = " << Y.e_mxc << ", warp_bytes = " << Y.warp_bytes << ";\n";
   }
   auto arr = [&](const char* name, const std::vector<int>& v) {
     o << "__device__ constexpr int " << name << "[" << (v.empty() ? 1 : v.size()) << "] = {";
@@ -1225,7 +1262,9 @@ void choose_launch(epi_engine* h) {
     }
   }
   P.el.enabled = 0;
-  if ((P.LG > 32 || (force && !strcmp(force, "env"))) && !(force && (!strcmp(force, "warp") || !strcmp(force, "cta")))) {
+  // (mobility multipliers, MOB_MUL: per-env mobility tables exist in the cell kernel and the team kernels only)
+  if (P.mob_dyn && force && !strcmp(force, "env")) throw Unsupported{"mobility multipliers in the env kernel"};
+  if (!P.mob_dyn && (P.LG > 32 || (force && !strcmp(force, "env"))) && !(force && (!strcmp(force, "warp") || !strcmp(force, "cta")))) {
     // ENV kernel: one CTA per env, threads strided over the cells
 #ifdef EPI_HOST_EMU
     int threads = P.LG < 24 ? P.LG : 24;  // host threads per emulated CTA

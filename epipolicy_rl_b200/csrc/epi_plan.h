@@ -29,6 +29,7 @@ struct CellLayout {
   int64_t e_base, e_bytes;
   int64_t e_mult_y, e_mult_d, e_cpv, e_act, e_live, e_elive, e_expr, e_sel, e_mpy, e_mpg, e_mpt0, e_mpFy, e_mpFg, e_coefS, e_Tnum,
       e_Tden, e_fi_y, e_fi_gap, e_ft_y, e_ft_gap, e_cost, e_crY, e_crD;
+  int64_t e_mob_y, e_mob_g, e_mxr, e_mxc;  // mobility multipliers present: the env's mode matrices (y, gap) and combined mobility at time t
   int64_t warp_bytes;
 };
 
@@ -97,6 +98,15 @@ struct DevPlan {
   const float *mob_dense_csc, *mob_dense_csr; // [LG,L] dense column / row of every cell when L <= 4 (else null)
   const float *mx_csrT, *mx_cscT;             // [nnz,G] the same values, groups fastest (env-group kernel: a locale's lanes read one line)
   const int *csr_indptr, *csr_indices, *csc_indptr, *csc_indices;
+  // ---- mobility multipliers (MOB_MUL ops, core/executor.py:121-127): the combined mobility then depends on the env
+  // and the day; the mode matrices are rebuilt in the day prologue (matrix/coo.py:173-188) and combined per evaluation
+  int mob_dyn, M, nmob;      // MOB_MUL ops present; modes; G * (sum of the modes' nnz)
+  const float* mob_org;      // [nmob] static.mode_group_coo values, block m at G*mode_off[m], shape [G,nnz_m]
+  const int* mob_cls;        // [nmob] multiplier class of every cell (0 = identity)
+  const int *mode_indptr, *mode_indices, *mode_off;  // [M,L+1] [sum nnz_m] [M+1] the modes' CSR patterns
+  const float* mode_bias;    // [M]
+  const int* comb_src;       // [M,nnz] position of a union-pattern entry (CSR order) in mode m's pattern, or -1
+  const int* csc_of_csr;     // [nnz] CSC position of a CSR entry
   // ---- multiplier classes
   const int* cls_off;        // [n_cls+1]
   const int* cls_op;         // op ids in execution order
@@ -149,7 +159,7 @@ struct DevPlan {
   int small_in_smem, big_in_smem;
   int64_t small_bytes, big_bytes;
   int64_t o_mult_y, o_mult_d, o_cpv, o_act, o_expr, o_sel, o_mpt0, o_coefS, o_Tnum, o_Tden, o_fi_y, o_fi_gap,
-      o_ft_y, o_ft_gap;                                  // small region (bytes)
+      o_ft_y, o_ft_gap, o_mob_y, o_mob_g, o_mxr, o_mxc;  // small region (bytes)
   int64_t o_X, o_ys, o_K, o_accY, o_accB, o_accE, o_accF, o_accF2, o_flows, o_alive, o_Xw, o_Ag, o_Wg, o_s, o_r,
       o_mvY, o_mvD, o_cost, o_crY, o_crD, o_ysS, o_KS;   // big region (bytes)
   CellLayout cl;

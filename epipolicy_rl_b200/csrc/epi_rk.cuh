@@ -100,6 +100,10 @@ __device__ __forceinline__ double rkCO(double, int ph, int j) { return RK_CO64[p
 #define T_cost double
 #define T_crY double
 #define T_crD double
+#define T_mob_y float
+#define T_mob_g float
+#define T_mxr float
+#define T_mxc float
 
 
 template <class T> struct Pair { T x, y; };

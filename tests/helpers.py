@@ -8,8 +8,11 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def load(name):
+    """(descriptor, golden trajectories); test-only scenario variants keep their descriptor next to the trajectories"""
     from epipolicy_rl_b200 import scenarios
-    return scenarios.load(name), np.load(os.path.join(GOLDEN, f"traj_{name}.npz"))
+    local = os.path.join(GOLDEN, f"desc_{name}.npz")
+    d = EpiDesc.load(local) if os.path.exists(local) else scenarios.load(name)
+    return d, np.load(os.path.join(GOLDEN, f"traj_{name}.npz"))
 
 
 def x_err(x, ref, desc):

@@ -81,3 +81,30 @@ def test_sirv_b_batch_subset():
     total, fin = rollout(d, acts)
     assert x_err(fin, z["batch_X"][:, -1], d) <= 1e-11
     assert abs(total - z["batch_rewards"].sum()) <= 1e-11 * abs(total)
+
+
+def test_schedule_plan_border_closure_mobility_multipliers():
+    """Mobility multipliers with a NON-EMPTY locale selection (core/executor.py:121-134, matrix/coo.py:112-117,173-188):
+    COVID_C with its Border_Closures schedule pointed at one real locale and a change of degree on day 59, run through
+    the unmodified reference (tools/gen_border_golden.py). The mode matrices of the first ten days bit-exact, the
+    90-day trajectory and costs, the RK45 step sequence."""
+    d, z = load("COVID_C_border")
+    assert list(d.op_kind).count(4) == 2  # the two sim.apply({'locale-from', 'locale-to'}) of the effect code
+    o = Oracle(d)
+    p = o.params(1)
+    for k in ("mp", "ft", "fi", "mob"):
+        assert np.array_equal(p[k], z[f"init_{k}"].reshape(p[k].shape)), k
+    X, C = z["sched_X"], z["sched_cost"]
+    nfev = []
+    for day in range(len(X)):
+        o.day_step(z["sched_plan_cpv"][day], z["sched_plan_active"][day], init_programs=True)
+        assert x_err(o.X, X[day], d) <= 1e-11
+        assert cost_err(o.cost, C[day]) <= 1e-11
+        if day < 10:
+            p = o.params(0)
+            assert np.array_equal(p["mob"], z["sched_p_mob"][day].reshape(p["mob"].shape)), day
+        nfev.append(o.trace["nfev"])
+    assert np.array_equal(np.array(nfev), z["sched_nfev"])
+    # the closure changes the dynamics: the same schedule without it (all other rows equal) ends somewhere else
+    zc = load("COVID_C")[1]
+    assert x_err(X[59], zc["sched_X"][59], d) > 1e-4
