@@ -196,6 +196,15 @@ __device__ __forceinline__ void fill_tables(const DevPlan& P, const Cx& c, float
     }
     EV(coefS, i) = cf;
   }
+  if (DIM(mob_dyn)) {
+    const int nnz = DIM(nnz);
+    for (int i = c.cell; i < G * nnz; i += LG) {
+      const int g = i / nnz, k = i - g * nnz;
+      const float v = mob_comb(P, &EV(mob_y, 0), &EV(mob_g, 0), g, k, tf);
+      EV(mxr, i) = v;
+      EV(mxc, g * nnz + __ldg(P.csc_of_csr + k)) = v;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -260,7 +269,7 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Cx& c, bool on, bool
 #endif
     for (int q = __ldg(P.csc_indptr + c.j); q < __ldg(P.csc_indptr + c.j + 1); q++) {
       int src = c.l0 + __ldg(P.csc_indices + q) * G + c.u;
-      real val = (real)__ldg(P.mx_csc + c.u * nnz + q);
+      real val = (real)(DIM(mob_dyn) ? EV(mxc, c.u * nnz + q) : __ldg(P.mx_csc + c.u * nnz + q));
       a += LO(cmA, 0, src) * val;
 #pragma unroll
       for (int k = 0; k < EPI_MAX_NG; k++)
@@ -322,7 +331,7 @@ __device__ __forceinline__ void rhs(const DevPlan& P, const Cx& c, bool on, bool
 #endif
       for (int q = __ldg(P.csr_indptr + c.j); q < __ldg(P.csr_indptr + c.j + 1); q++) {
         int dst = c.l0 + __ldg(P.csr_indices + q) * G + c.u;
-        real val = (real)__ldg(P.mx_csr + c.u * nnz + q);
+        real val = (real)(DIM(mob_dyn) ? EV(mxr, c.u * nnz + q) : __ldg(P.mx_csr + c.u * nnz + q));
 #pragma unroll
         for (int k = 0; k < EPI_MAX_NG; k++)
           if (k < NG) rs[k] += LO(cmA, 1 + k, dst) * val;
@@ -605,6 +614,9 @@ __device__ __forceinline__ int prologue(const DevPlan& P, const Cx& c, bool on, 
       EV(mpFy, i) = y;
       EV(mpFg, i) = __fsub_rn(d, y);
     }
+    if (DIM(mob_dyn))  // the mode matrices of yesterday and today -> (y, gap)  (matrix/coo.py:173-188)
+      for (int it = c.cell; it < P.M * G * L; it += LG)
+        mob_row(P, &EV(mult_y, 0), &EV(mult_d, 0), it / (G * L), (it / L) % G, it % L, &EV(mob_y, 0), &EV(mob_g, 0));
   }
   if (on) {
     // 5. move table of today (nb_move, executor.py:166-234; different compartment, same locale)

@@ -81,6 +81,7 @@ struct Ws {
   float* Tnum;   // [n_lc,F,G,G]
   real* Tden;    // [n_lc,F,G,G] (only when has_ft_ops)
   float *fi_y, *fi_gap, *ft_y, *ft_gap;
+  float *mob_y, *mob_g, *mxr, *mxc;  // mobility multipliers present (P.mob_dyn): mode matrices (y, gap), combined at time t
   // big region
   double* X;  // state is integrated in double in BOTH modes (see rk45_day); stages are `real`
   real *ys, *K, *accY, *accB, *accE, *accF, *accF2, *flows, *alive, *Xw, *Ag, *Wg, *s, *r;
@@ -101,6 +102,8 @@ __device__ __forceinline__ void bind_ws(const DevPlan& P, char* small, char* big
   w.Tnum = (float*)(small + P.o_Tnum); w.Tden = (real*)(small + P.o_Tden);
   w.fi_y = (float*)(small + P.o_fi_y); w.fi_gap = (float*)(small + P.o_fi_gap);
   w.ft_y = (float*)(small + P.o_ft_y); w.ft_gap = (float*)(small + P.o_ft_gap);
+  w.mob_y = (float*)(small + P.o_mob_y); w.mob_g = (float*)(small + P.o_mob_g);
+  w.mxr = (float*)(small + P.o_mxr); w.mxc = (float*)(small + P.o_mxc);
   w.X = (double*)(big + P.o_X); w.ys = (real*)(big + P.o_ys); w.K = (real*)(big + P.o_K);
   w.accY = (real*)(big + P.o_accY); w.accB = (real*)(big + P.o_accB); w.accE = (real*)(big + P.o_accE);
   w.accF = (real*)(big + P.o_accF); w.accF2 = (real*)(big + P.o_accF2); w.flows = (real*)(big + P.o_flows);
@@ -121,6 +124,47 @@ __device__ __forceinline__ float mp_at(const DevPlan& P, const float* mult_y, co
   if (cls == 0) return m0;
   float y = __fmul_rn(m0, mult_y[cls]), d = __fmul_rn(m0, mult_d[cls]);
   return lerp_rn(y, __fsub_rn(d, y), tf);
+}
+
+// ---- mobility multipliers (MOB_MUL ops; core/executor.py:121-127 -> CooMatrix.pairwise_multiply, coo.py:112-117)
+// One row (mode m, group g, origin row r) of the env's mode matrix for yesterday's and today's class multipliers:
+// origin (*) delta, the row rescaled to the ORIGIN's row sum; a row multiplied to nothing becomes the identity row
+// scaled by that sum (get_normalized_matrix, matrix/coo.py:173-188: sums in double, cells float). Writes y and the
+// float gap = today - yesterday (get_gap_parameter, obj/parameter.py:68-78).
+__device__ inline void mob_row(const DevPlan& P, const float* mult_y, const float* mult_d, int m, int g, int r, float* oy,
+                               float* og) {
+  const int off = P.mode_off[m], nnz_m = P.mode_off[m + 1] - off, base = P.G * off + g * nnz_m;
+  const int k0 = P.mode_indptr[m * (P.L + 1) + r], k1 = P.mode_indptr[m * (P.L + 1) + r + 1];
+  double osum = 0, sy = 0, sd = 0;
+  for (int k = k0; k < k1; k++) {
+    const float org = P.mob_org[base + k];
+    const int cls = P.mob_cls[base + k];
+    osum += (double)org;
+    sy += (double)__fmul_rn(org, mult_y[cls]);
+    sd += (double)__fmul_rn(org, mult_d[cls]);
+  }
+  for (int k = k0; k < k1; k++) {
+    const float org = P.mob_org[base + k];
+    const int cls = P.mob_cls[base + k];
+    const bool diag = P.mode_indices[off + k] == r;
+    const float a = sy > 1e-15 ? (float)__dmul_rn(__ddiv_rn((double)__fmul_rn(org, mult_y[cls]), sy), osum) : (diag ? (float)osum : 0.0f);
+    const float b = sd > 1e-15 ? (float)__dmul_rn(__ddiv_rn((double)__fmul_rn(org, mult_d[cls]), sd), osum) : (diag ? (float)osum : 0.0f);
+    oy[base + k] = a;
+    og[base + k] = __fsub_rn(b, a);
+  }
+}
+
+// combined mobility of union-pattern entry k (CSR order) and group g at interpolation weight tf: every mode matrix
+// interpolated in float (parameter.py:85), then the f32 sum over the modes of bias * value (core_optimize.py:69-92)
+__device__ __forceinline__ float mob_comb(const DevPlan& P, const float* mob_y, const float* mob_g, int g, int k, float tf) {
+  float v = 0.0f;
+  for (int m = 0; m < P.M; m++) {
+    const int km = P.comb_src[m * P.nnz + k];
+    if (km < 0) continue;
+    const int off = P.mode_off[m], i = P.G * off + g * (P.mode_off[m + 1] - off) + km;
+    v = __fadd_rn(v, __fmul_rn(P.mode_bias[m], lerp_rn(mob_y[i], mob_g[i], tf)));
+  }
+  return v;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -160,6 +204,13 @@ __device__ void rhs(const DevPlan& P, const Ws<real>& w, const Team<CTA>& tm, do
     }
     w.coefS[i] = c;
   }
+  if (P.mob_dyn)
+    for (int i = tm.lane; i < G * nnz; i += tm.T) {
+      const int g = i / nnz, k = i - g * nnz;
+      const float v = mob_comb(P, w.mob_y, w.mob_g, g, k, tf);
+      w.mxr[i] = v;
+      w.mxc[g * nnz + __ldg(P.csc_of_csr + k)] = v;
+    }
   // phase A: alive matrix (N excludes death and hospitalized, :28-41,:168) and weighted infectious fields
   for (int i = tm.lane; i < LG; i += tm.T) {
     real a = 0;
@@ -180,7 +231,7 @@ __device__ void rhs(const DevPlan& P, const Ws<real>& w, const Team<CTA>& tm, do
     for (int k = 0; k < EPI_MAX_NG; k++) xs[k] = 0;
     for (int q = __ldg(P.csc_indptr + j); q < __ldg(P.csc_indptr + j + 1); q++) {
       int src = __ldg(P.csc_indices + q) * G + u;
-      real val = (real)__ldg(P.mx_csc + u * nnz + q);
+      real val = (real)(P.mob_dyn ? w.mxc[u * nnz + q] : __ldg(P.mx_csc + u * nnz + q));
       a += w.alive[src] * val;
 #pragma unroll
       for (int k = 0; k < EPI_MAX_NG; k++)
@@ -232,7 +283,7 @@ __device__ void rhs(const DevPlan& P, const Ws<real>& w, const Team<CTA>& tm, do
     for (int k = 0; k < EPI_MAX_NG; k++) rs[k] = 0;
     for (int q = __ldg(P.csr_indptr + i0); q < __ldg(P.csr_indptr + i0 + 1); q++) {
       int dst = __ldg(P.csr_indices + q) * G + u0;
-      real val = (real)__ldg(P.mx_csr + u0 * nnz + q);
+      real val = (real)(P.mob_dyn ? w.mxr[u0 * nnz + q] : __ldg(P.mx_csr + u0 * nnz + q));
 #pragma unroll
       for (int k = 0; k < EPI_MAX_NG; k++)
         if (k < NG) rs[k] += w.s[k * LG + dst] * val;
@@ -451,6 +502,8 @@ __device__ int prologue(const DevPlan& P, const Ws<real>& w, const Team<CTA>& tm
       }
     }
   }
+  if (P.mob_dyn)  // the mode matrices of yesterday and today -> (y, gap)
+    for (int it = tm.lane; it < P.M * G * L; it += tm.T) mob_row(P, w.mult_y, w.mult_d, it / (G * L), (it / L) % G, it % L, w.mob_y, w.mob_g);
   // 5. move table of today (nb_move, executor.py:166-234; different compartment, same locale)
   for (int it = tm.lane; it < P.n_slot * LG; it += tm.T) w.mvD[it] = 0.0f;
   int ex_d = 0;

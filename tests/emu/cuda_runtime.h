@@ -39,6 +39,7 @@ inline float __fdiv_rn(float a, float b) { return a / b; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dsub_rn(double a, double b) { return a - b; }
 inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __ddiv_rn(double a, double b) { return a / b; }
 inline long long __double_as_longlong(double d) { long long r; memcpy(&r, &d, 8); return r; }
 inline double __longlong_as_double(long long l) { double r; memcpy(&r, &l, 8); return r; }
 namespace emu {

@@ -80,17 +80,38 @@ def test_known_answer_and_fused_week():
 
 
 def test_unsupported_programs_are_refused_not_approximated():
-    """A mobility multiplier with a non-empty selection is outside the compiled op algebra of the
-    CUDA path: epi_create must fail with EPI_E_UNSUPPORTED."""
+    """A move whose target locales differ from its source locales (nb_move's cross-locale branches,
+    core/executor.py:185-200,213-233) is outside the compiled op algebra of the CUDA path: epi_create must fail with
+    EPI_E_UNSUPPORTED rather than run something else."""
     from epipolicy_rl_b200 import lib
-    from epipolicy_rl_b200.desc import OP_MOB_MUL
-    d, _ = load("COVID_C")
-    k = d.arrays["op_kind"].copy()
-    k[np.where(k == 1)[0][0]] = OP_MOB_MUL
-    d.arrays["op_kind"] = k
+    from epipolicy_rl_b200.desc import OP_MOB_MUL, OP_MOVE
+    d, _ = load("COVID_C_border")
+    kind, arg = d.arrays["op_kind"], d.arrays["op_arg"].copy().reshape(-1, 8)
+    mv, mob = int(np.where(kind == OP_MOVE)[0][0]), int(np.where(kind == OP_MOB_MUL)[0][0])
+    arg[mv, 4] = arg[mob, 2]  # target locales := the closure's single 'locale-from' locale; sources stay all locales
+    d.arrays["op_arg"] = arg.reshape(-1)
     with pytest.raises(lib.EpiError) as ei:
         EmuEngine(d, 1, "fp64")
     assert ei.value.code == -2
+
+
+@pytest.mark.parametrize("knobs", [{}, {"EPI_TEAM": "warp"}, {"EPI_TEAM": "cta"}], ids=["cell", "warp-team", "cta-team"])
+def test_border_closure_mobility_multipliers_vs_reference(knobs, monkeypatch):
+    """Mobility multipliers with a non-empty locale selection (sim.apply({'locale-from', 'locale-to'}, m),
+    core/executor.py:121-134; row renormalisation matrix/coo.py:173-188; per-evaluation combination
+    core_optimize.py:69-92): COVID_C with Border_Closures on one real locale and a change of degree on day 59, against
+    the unmodified reference's trajectory (tools/gen_border_golden.py), with the identical RK45 step sequence."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    d, z = load("COVID_C_border")
+    eng = EmuEngine(d, 1, "fp64")
+    X, C = z["sched_X"], z["sched_cost"]
+    for day in range(len(X)):
+        eng.step_plan(z["sched_plan_cpv"][day][None], z["sched_plan_active"][day][None].astype(np.uint8), True, 1)
+        assert x_err(eng.get_state("X"), X[day], d) <= 1e-9, day
+        assert cost_err(eng.get_state("cost"), C[day]) <= 1e-9, day
+        assert int(eng.get_state("trace")[0, 0]) == int(z["sched_nfev"][day])
+    eng.close()
 
 
 @pytest.mark.parametrize("knobs", [{"EPI_TEAM": "env", "EPI_ENV_FLOWSLOTS": "0"},

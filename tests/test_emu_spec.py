@@ -66,3 +66,21 @@ def test_forced_kernel_kind_without_a_specialised_build_is_refused(monkeypatch):
         eng.attach_spec()
     assert ei.value.code == -2
     eng.close()
+
+
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+def test_specialised_cell_kernel_with_mobility_multipliers(prec):
+    """the specialised build of a scenario with MOB_MUL ops (per-env mobility tables instead of the dense registers)
+    against the unmodified reference's border-closure trajectory"""
+    d, z = load("COVID_C_border")
+    eng = EmuEngine(d, 1, prec)
+    eng.attach_spec()
+    assert eng.info.specialized == 1
+    X, C = z["sched_X"], z["sched_cost"]
+    for day in range(len(X)):
+        eng.step_plan(z["sched_plan_cpv"][day][None], z["sched_plan_active"][day][None].astype(np.uint8), True, 1)
+        assert x_err(eng.get_state("X"), X[day], d) <= TOL[prec], day
+        assert cost_err(eng.get_state("cost"), C[day]) <= TOL[prec], day
+        if prec == "fp64":
+            assert int(eng.get_state("trace")[0, 0]) == int(z["sched_nfev"][day])
+    eng.close()

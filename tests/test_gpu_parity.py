@@ -73,6 +73,29 @@ def test_schedule_plan_vs_reference(name):
     eng.close()
 
 
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+def test_border_closure_mobility_multipliers_vs_reference(prec):
+    """Mobility multipliers with a non-empty locale selection (core/executor.py:121-134, matrix/coo.py:173-188,
+    core_optimize.py:69-92): COVID_C with Border_Closures on one real locale and a change of degree on day 59, a batch of
+    3 envs (one warp) following the same schedule, against the unmodified reference (tools/gen_border_golden.py)."""
+    d, z = load("COVID_C_border")
+    eng = _engine(d, 3, prec)
+    assert eng.info.specialized == 1
+    X, C = z["sched_X"], z["sched_cost"]
+    tol = 1e-9 if prec == "fp64" else 1e-4
+    for day in range(len(X)):
+        cpv = torch.from_numpy(np.repeat(z["sched_plan_cpv"][day][None], 3, 0)).cuda()
+        act = torch.from_numpy(np.repeat(z["sched_plan_active"][day][None].astype(np.uint8), 3, 0)).cuda()
+        eng.step_plan(cpv, act, True, 1)
+        x = eng.get_state("X")
+        for e in range(3):
+            assert x_err(x[e], X[day], d) <= tol, (day, e)
+            assert cost_err(eng.get_state("cost")[e], C[day]) <= tol, (day, e)
+        if prec == "fp64":
+            assert (eng.get_state("trace")[:, 0] == int(z["sched_nfev"][day])).all()
+    eng.close()
+
+
 def test_run_batch_of_schedules():
     """BatchedEpidemic.run (Epidemic.run for a batch): env 0 follows SIR_A's own schedule, env 1 the same schedule
     with both degrees raised; env 0 reproduces the golden trajectory, env 1 differs."""
