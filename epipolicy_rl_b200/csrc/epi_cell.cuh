@@ -1107,6 +1107,22 @@ __device__ __forceinline__ void step_warp(const DevPlan& P, const DevState& S, c
   const int n_days = a.init_only ? 1 : a.n_days;
   for (int day = 0; day < n_days; day++) {
     if (!__any_sync(EPI_FULL, on)) break;
+    if (day > 0 && a.cpv_days) {  // schedule mode: today's row of control parameters / Act flags, and what is live with them
+      if (on0) {
+        const size_t row = (size_t)day * a.N + e;
+        for (int k = c.cell; k < P.NCP; k += LG) EV(cpv, k) = a.cpv_days[row * P.NCP + k];
+        for (int i = c.cell; i < P.I; i += LG) EV(act, i) = a.active_days ? a.active_days[row * P.I + i] : 1;
+      }
+      __syncwarp();
+      if (on0) {
+        for (int o = c.cell; o < P.n_op; o += LG) EV(live, o) = (uint8_t)op_live(P, &EV(act, 0), a.variant, o);
+        for (int x = c.cell; x < P.n_expr; x += LG) {
+          int itv = P.expr_itv[x];
+          EV(elive, x) = (uint8_t)(EV(act, itv) && P.expr_prog[x] == (a.variant ? P.prog_init[itv] : P.prog_step[itv]));
+        }
+      }
+      __syncwarp();
+    }
     bool dyn = true;
     int ex_bits = prologue<real>(P, c, on, a.variant, gXprev, ex_y, dyn, tabs_current);
     if (!a.init_only) {
@@ -1121,7 +1137,12 @@ __device__ __forceinline__ void step_warp(const DevPlan& P, const DevState& S, c
       // reward = -sum(cumulative_cost_next - cumulative_cost_current)  (epidemic.py:115)
       double dr;
       TEAM_SUM(dr, c1 - c0, on);
-      if (on) { reward -= dr; t_day++; }
+      if (on) {
+        reward -= dr; t_day++;
+        if (a.reward_days && c.cell == 0) a.reward_days[(size_t)day * a.N + env] = -dr;
+        if (a.obs_days)
+          for (int k = 0; k < C; k++) ((real*)a.obs_days)[((size_t)day * a.N + e) * CLG + k * LG + c.cell] = (real)LA(X, k);
+      }
     }
     // today's parameters become yesterday's (State(t+1, next_obs, dest_parameter), epidemic.py:89)
     if (on) {

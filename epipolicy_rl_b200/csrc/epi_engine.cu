@@ -1646,6 +1646,24 @@ int epi_step_plan(epi_t* h, const float* cpv_dev, const uint8_t* active_dev, int
   });
 }
 
+int epi_run_plan(epi_t* h, const float* cpv_days_dev, const uint8_t* active_days_dev, int schedule_programs, int n_days,
+                 void* obs_days_out_dev, double* reward_days_out_dev, void* obs_out_dev, double* reward_out_dev,
+                 uint8_t* done_out_dev, void* cuda_stream) {
+  if (!h) return EPI_E_INVALID;
+  return guarded(h, [&] {
+    if (!cpv_days_dev) throw Invalid{"cpv_days_dev is NULL"};
+    if (n_days < 1) throw Invalid{"n_days < 1"};
+    CK(cudaSetDevice(h->device));
+    epi::StepArgs a{};
+    a.cpv = cpv_days_dev; a.active = active_days_dev;  // row 0; the kernels move on to row d on day d
+    a.cpv_days = cpv_days_dev; a.active_days = active_days_dev;
+    a.obs_days = obs_days_out_dev; a.reward_days = reward_days_out_dev;
+    a.variant = schedule_programs ? 1 : 0; a.n_days = n_days; a.N = h->N;
+    a.obs_out = obs_out_dev; a.reward_out = reward_out_dev; a.done_out = done_out_dev;
+    launch(h, h->S, a, (cudaStream_t)cuda_stream);
+  });
+}
+
 int epi_step_host(epi_t* h, const float* actions_host, int n_days, void* obs_out_host, double* reward_out_host,
                   uint8_t* done_out_host) {
   if (!h) return EPI_E_INVALID;

@@ -972,6 +972,12 @@ __device__ __forceinline__ void step_cta(const DevPlan& P, const DevState& S, co
     int rot = 0;
     const int n_days = a.init_only ? 1 : a.n_days;
     for (int day = 0; day < n_days; day++) {
+      if (day > 0 && a.cpv_days) {  // schedule mode: today's row
+        const size_t row = (size_t)day * a.N + e;
+        for (int k = b.tid; k < P.NCP; k += b.nt) ET(cpv, k) = a.cpv_days[row * P.NCP + k];
+        for (int i = b.tid; i < P.I; i += b.nt) ET(act, i) = a.active_days ? a.active_days[row * P.I + i] : 1;
+        __syncthreads();
+      }
       bool dyn = true;
       int ex_bits = prologue<real>(P, b, a.variant, gXprev, ex_y, dyn, tabs_current);
       if (!a.init_only) {
@@ -981,8 +987,13 @@ __device__ __forceinline__ void step_cta(const DevPlan& P, const DevState& S, co
         fsal_ok = rk45_day<real>(P, b, dyn, ex_bits, meta, S.last_err + e,
                                  a.dbg_attempts ? a.dbg_attempts + e * 128 : nullptr, skip0, rot);
         for (int i = b.tid; i < nC; i += b.nt) c1 += b.cost[i];
-        reward -= block_sum(b, c1 - c0);  // -sum(cumulative_cost_next - cumulative_cost_current), epidemic.py:115
+        const double dr = block_sum(b, c1 - c0);
+        reward -= dr;  // -sum(cumulative_cost_next - cumulative_cost_current), epidemic.py:115
         t_day++;
+        if (a.reward_days && b.tid == 0) a.reward_days[(size_t)day * a.N + env] = -dr;
+        if (a.obs_days)
+          FOR_CELLS
+            for (int k = 0; k < C; k++) ((real*)a.obs_days)[((size_t)day * a.N + e) * CLG + (size_t)k * LG + cell] = (real)BA(X, k);
       }
       // today's parameters become yesterday's (State(t+1, next_obs, dest_parameter), epidemic.py:89)
       for (int i = b.tid; i < P.n_cls; i += b.nt) ET(mult_y, i) = ET(mult_d, i);

@@ -1137,6 +1137,12 @@ __device__ __forceinline__ void step_group(const DevPlan& P, const DevState& S, 
     const int n_days = a.init_only ? 1 : a.n_days;
     const int nCl = spec::I * b.nl;
     for (int day = 0; day < n_days; day++) {
+      if (day > 0 && a.cpv_days) {  // schedule mode: today's row (every CTA keeps its own copy of the env's tables)
+        const size_t row = (size_t)day * a.N + e;
+        for (int k = b.tid; k < P.NCP; k += b.T) GT(cpv, k) = a.cpv_days[row * P.NCP + k];
+        for (int i = b.tid; i < P.I; i += b.T) GT(act, i) = a.active_days ? a.active_days[row * P.I + i] : 1;
+        __syncthreads();
+      }
       bool dyn = true;
       TSEC(14);
       int ex_bits = prologue(P, b, a.variant, gXprev, ex_y, dyn, tabs_current);
@@ -1150,6 +1156,16 @@ __device__ __forceinline__ void step_group(const DevPlan& P, const DevState& S, 
         for (int q = b.tid; q < nCl; q += b.T) c1 += b.cost[(size_t)(q / b.nl) * L + b.l0 + q % b.nl];
         reward -= c1 - c0;  // -sum(cumulative_cost_next - cumulative_cost_current), epidemic.py:115
         t_day++;
+        if (a.reward_days) {  // schedule mode: the day's reward needs its own group sum
+          double dr[1] = {-(c1 - c0)};
+          grp_sum<1>(P, b, dr);
+          if (b.cta == 0 && b.tid == 0) a.reward_days[(size_t)day * a.N + env] = dr[0];
+        }
+        if (a.obs_days && b.valid) {
+#pragma unroll
+          for (int k = 0; k < C; k++)
+            ((real*)a.obs_days)[((size_t)day * a.N + e) * CLG + (size_t)k * LG + b.cell] = (real)b.gX[(size_t)k * LG + b.cell];
+        }
       }
       // today's parameters become yesterday's (State(t+1, next_obs, dest_parameter), epidemic.py:89)
       __syncthreads();

@@ -785,6 +785,13 @@ struct StepArgs {
   char* grp_scratch;
   char* grp_cta_scratch;
   unsigned* grp_bar;
+  // schedule mode (epi_run_plan; Epidemic.run, core/epidemic.py:118-134, for a batch of what-if schedules in ONE launch):
+  // day d of the launch takes its control parameters / Act flags from row d (`cpv` / `active` point at row 0) and
+  // emits the day's end state and reward
+  const float* cpv_days;       // [n_days,N,NCP] or null
+  const uint8_t* active_days;  // [n_days,N,I] or null (all interventions have an Act every day)
+  void* obs_days;              // real [n_days,N,CLG] or null
+  double* reward_days;         // [n_days,N] or null
 };
 
 // one team, one env at a time: load state, prologue + RK45 for each day, store
@@ -825,6 +832,12 @@ __device__ void step_team(const DevPlan& P, const DevState& S, const StepArgs& a
     double reward = 0;
     int done = t_day >= P.horizon;
     for (int day = 0; day < (a.init_only ? 1 : a.n_days); day++) {
+      if (day > 0 && a.cpv_days) {  // schedule mode: today's row
+        const size_t row = (size_t)day * a.N + env;
+        for (int k = tm.lane; k < P.NCP; k += tm.T) w.cpv[k] = a.cpv_days[row * P.NCP + k];
+        for (int i = tm.lane; i < P.I; i += tm.T) w.act[i] = a.active_days ? a.active_days[row * P.I + i] : 1;
+        tm.sync();
+      }
       int ex_bits = prologue<real, CTA>(P, w, tm, a.variant, gXprev, ex_y);
       double c0 = 0;
       if (!a.init_only) {
@@ -833,8 +846,12 @@ __device__ void step_team(const DevPlan& P, const DevState& S, const StepArgs& a
         double c1 = 0;
         for (int i = tm.lane; i < nC; i += tm.T) c1 += w.cost[i];
         // reward = -sum(cumulative_cost_next - cumulative_cost_current)  (epidemic.py:115)
-        reward -= tm.sum(c1 - c0);
+        const double dr = tm.sum(c1 - c0);
+        reward -= dr;
         t_day++;
+        if (a.reward_days && tm.lane == 0) a.reward_days[(size_t)day * a.N + env] = -dr;
+        if (a.obs_days)
+          for (int i = tm.lane; i < CLG; i += tm.T) ((real*)a.obs_days)[((size_t)day * a.N + env) * CLG + i] = (real)w.X[i];
       }
       // today's parameters become yesterday's (State(t+1, next_obs, dest_parameter), epidemic.py:89)
       for (int i = tm.lane; i < P.n_cls; i += tm.T) w.mult_y[i] = w.mult_d[i];

@@ -152,8 +152,8 @@ class BatchedEpidemic:
 
     def run(self, cpv: torch.Tensor, active: torch.Tensor | None = None, record_obs: bool = True,
             schedule_programs: bool = True, report: bool = False):
-        """Epidemic.run (core/epidemic.py:118-134) for a batch of what-if schedules: reset, then one day per launch
-        with day t's Acts taken from the schedule. cpv: [T, N, NCP] (or [T, NCP], broadcast to all envs) full
+        """Epidemic.run (core/epidemic.py:118-134) for a batch of what-if schedules: reset, then the whole schedule in
+        ONE launch (epi_run_plan) with day t's Acts taken from row t. cpv: [T, N, NCP] (or [T, NCP], broadcast to all envs) full
         control-parameter vectors; active: [T, N, I] / [T, I] flags of the interventions that have an Act on
         day t (None: all). Returns {"reward": [T, N] float64, "done": [N] uint8, "obs": [T, N, C*L*G]} on the device
         (obs only if record_obs). report=True adds "report": the reference Reporter's quantities for every env -
@@ -172,11 +172,25 @@ class BatchedEpidemic:
         if c.shape[1] != self.n_envs or (a is not None and a.shape[:2] != c.shape[:2]):
             raise ValueError("schedule must be [T, N, NCP] / [T, NCP] with matching active flags")
         self.reset()
-        rep = None
-        if report:
-            from .reporter_device import DeviceReporter
-            rep = DeviceReporter(self.desc, self.plan_tables(), self.device)
-            rep.record(self.state_dev("X"), self.state_dev("acc"), self.state_dev("mult"))
+        if not report:
+            # ONE launch for the whole schedule (epi_run_plan): day d of the launch reads row d of the schedule and emits
+            # the day's end state and reward; no per-day launch, no per-day copies
+            c = c.contiguous()
+            a = None if a is None else a.contiguous()
+            rew = torch.zeros((T, self.n_envs), dtype=torch.float64, device=self.device)
+            obs = torch.zeros((T, self.n_envs, self.obs_dim), dtype=self.dtype, device=self.device) if record_obs else None
+            self._ck(self.L.epi_run_plan(self._h, c.data_ptr(), None if a is None else a.data_ptr(), 1 if schedule_programs else 0,
+                                         int(T), None if obs is None else obs.data_ptr(), rew.data_ptr(), self.obs.data_ptr(),
+                                         self.reward.data_ptr(), self.done.data_ptr(), self._stream()))
+            out = {"reward": rew, "done": self.done}
+            if record_obs:
+                out["obs"] = obs
+            return out
+        # with the reporter: one launch per day, the reporter's inputs (state, live cumulative components, class
+        # multipliers) recorded by stream-ordered device copies between the launches
+        from .reporter_device import DeviceReporter
+        rep = DeviceReporter(self.desc, self.plan_tables(), self.device)
+        rep.record(self.state_dev("X"), self.state_dev("acc"), self.state_dev("mult"))
         rew = torch.empty((T, self.n_envs), dtype=torch.float64, device=self.device)
         obs = torch.empty((T, self.n_envs, self.obs_dim), dtype=self.dtype, device=self.device) if record_obs else None
         for t in range(T):
@@ -184,11 +198,8 @@ class BatchedEpidemic:
             rew[t].copy_(r)
             if record_obs:
                 obs[t].copy_(o)
-            if rep is not None:
-                rep.record(self.state_dev("X"), self.state_dev("acc"), self.state_dev("mult"))
-        out = {"reward": rew, "done": self.done}
-        if rep is not None:
-            out["report"] = rep.compute()
+            rep.record(self.state_dev("X"), self.state_dev("acc"), self.state_dev("mult"))
+        out = {"reward": rew, "done": self.done, "report": rep.compute()}
         if record_obs:
             out["obs"] = obs
         return out

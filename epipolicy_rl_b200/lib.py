@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libepi_b200.so")
 
 EPI_FP64, EPI_FP32 = 0, 1
-EXPORTS = ["epi_create", "epi_destroy", "epi_last_error", "epi_info", "epi_reset", "epi_step", "epi_step_plan",
+EXPORTS = ["epi_create", "epi_destroy", "epi_last_error", "epi_info", "epi_reset", "epi_step", "epi_step_plan", "epi_run_plan",
            "epi_step_host", "epi_get_state", "epi_set_state", "epi_launch_count", "epi_spec_source", "epi_spec_source_desc",
            "epi_spec_attach", "epi_host_buffers", "epi_bind_mirror", "epi_get_state_dev", "epi_get_plan"]
 
@@ -62,6 +62,8 @@ def bind(L):
     L.epi_step.argtypes = [P, P, I, P, P, P, P]
     L.epi_step_plan.restype = I
     L.epi_step_plan.argtypes = [P, P, P, I, I, P, P, P, P]
+    L.epi_run_plan.restype = I
+    L.epi_run_plan.argtypes = [P, P, P, I, I, P, P, P, P, P, P]
     L.epi_step_host.restype = I
     L.epi_step_host.argtypes = [P, P, I, P, P, P]
     L.epi_get_state.restype = I

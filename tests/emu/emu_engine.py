@@ -66,6 +66,18 @@ class EmuEngine:
                                       self.reward.ctypes.data, self.done.ctypes.data, None))
         return self.obs, self.reward, self.done
 
+    def run_plan(self, cpv_days, active_days, schedule_programs=True):
+        """epi_run_plan: [T, N, NCP] / [T, N, I] schedule rows, one launch; returns (obs_days [T, N, C*L*G], reward_days [T, N])"""
+        c = np.ascontiguousarray(cpv_days, np.float32)
+        a = None if active_days is None else np.ascontiguousarray(active_days, np.uint8)
+        T = c.shape[0]
+        obs_days = np.zeros((T,) + self.obs.shape, self.obs.dtype)
+        rew_days = np.zeros((T, self.n_envs), np.float64)
+        self._ck(self.L.epi_run_plan(self._h, c.ctypes.data, a.ctypes.data if a is not None else None,
+                                     1 if schedule_programs else 0, T, obs_days.ctypes.data, rew_days.ctypes.data,
+                                     self.obs.ctypes.data, self.reward.ctypes.data, self.done.ctypes.data, None))
+        return obs_days, rew_days
+
     def get_state(self, what):
         d, N = self.desc, self.n_envs
         spec = {"X": (0, (N, d.C, d.L, d.G), np.float64), "cost": (1, (N, d.I, d.L), np.float64),

@@ -84,3 +84,25 @@ def test_group_kernel_reset_and_horizon(monkeypatch):
     assert np.array_equal(o1, o2) and np.array_equal(r1, r2)   # deterministic, reset restores everything
     assert np.array_equal(o1[0], o1[1])                         # same action, same env: groups agree bit for bit
     grp.close()
+
+
+def test_group_kernel_run_plan_one_launch(monkeypatch):
+    """schedule mode (epi_run_plan) of the env-group kernel: 6 days of per-day control-parameter rows in ONE launch
+    against one epi_step_plan launch per day (fp32: the fused launch reuses a day's last stage as the next day's first
+    when the parameters did not move, so agreement is to float rounding, not bit for bit); the per-day reward needs its
+    own group sum."""
+    d, _ = load("syn_s")
+    T, n = 6, 2
+    rng = np.random.default_rng(5)
+    cpv = np.tile(d.cp_default.astype(np.float32), (T, n, 1))
+    free = d.cp_min != d.cp_max
+    cpv[:, :, free] = rng.uniform(d.cp_min[free], d.cp_max[free], (T, n, int(free.sum()))).astype(np.float32)
+    cpv[3] = cpv[2]  # a day whose parameters do not move
+    one, daily = _group_engine(d, n, 2, monkeypatch), _group_engine(d, n, 2, monkeypatch)
+    obs_days, rew_days = one.run_plan(cpv, None, False)
+    for t in range(T):
+        o, r, _ = daily.step_plan(cpv[t], None, False, 1)
+        assert x_err(obs_days[t], o, d) <= 1e-5, t
+        assert np.allclose(rew_days[t], r, rtol=1e-5), t
+    assert x_err(one.get_state("X"), daily.get_state("X"), d) <= 1e-5
+    one.close(); daily.close()

@@ -231,3 +231,30 @@ def test_stepping_past_the_horizon_keeps_simulating():
     assert done[0] and eng.get_state("day")[0] > 365 and r[0] < 0
     assert not np.array_equal(eng.get_state("X"), x)
     eng.close()
+
+
+@pytest.mark.parametrize("name,knobs", [("COVID_C", {}), ("SIR_A", {}), ("COVID_C_border", {}), ("COVID_C", {"EPI_TEAM": "warp"}),
+                                        ("COVID_C", {"EPI_TEAM": "env", "EPI_ENV_FLOWSLOTS": "1"})],
+                         ids=["COVID_C", "SIR_A", "border", "COVID_C-warp-team", "COVID_C-env"])
+def test_run_plan_one_launch_equals_daily_launches(name, knobs, monkeypatch):
+    """epi_run_plan (Epidemic.run for a batch, core/epidemic.py:118-134, ONE launch): env 0 follows the scenario's own
+    schedule (the reference's trajectory), env 1 the same schedule with its control parameters perturbed from day 20 on;
+    per-day states and rewards are bit-identical (fp64) with one epi_step_plan launch per day."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    d, z = load(name)
+    T = 45
+    cpv = np.repeat(z["sched_plan_cpv"][:T, None, :], 2, 1).astype(np.float32)
+    free = d.cp_min != d.cp_max
+    cpv[20:, 1, free] = np.clip(cpv[20:, 1, free] * 1.3 + 0.05, d.cp_min[free], d.cp_max[free])
+    act = np.repeat(z["sched_plan_active"][:T, None, :], 2, 1).astype(np.uint8)
+    one, daily = EmuEngine(d, 2, "fp64"), EmuEngine(d, 2, "fp64")
+    obs_days, rew_days = one.run_plan(cpv, act, True)
+    for t in range(T):
+        o, r, _ = daily.step_plan(cpv[t], act[t], True, 1)
+        assert np.array_equal(obs_days[t], o), t
+        assert np.array_equal(rew_days[t], r), t
+    assert x_err(obs_days[:, 0].reshape(T, d.C, d.L, d.G), z["sched_X"][:T], d) <= 1e-9
+    assert not np.array_equal(obs_days[-1, 0], obs_days[-1, 1])
+    assert np.array_equal(one.get_state("X"), daily.get_state("X")) and np.array_equal(one.get_state("cost"), daily.get_state("cost"))
+    one.close(); daily.close()
