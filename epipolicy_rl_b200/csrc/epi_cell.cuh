@@ -1140,8 +1140,15 @@ __device__ __forceinline__ void step_warp(const DevPlan& P, const DevState& S, c
       if (on) {
         reward -= dr; t_day++;
         if (a.reward_days && c.cell == 0) a.reward_days[(size_t)day * a.N + env] = -dr;
+        const size_t row = (size_t)day * a.N + e;
         if (a.obs_days)
-          for (int k = 0; k < C; k++) ((real*)a.obs_days)[((size_t)day * a.N + e) * CLG + k * LG + c.cell] = (real)LA(X, k);
+          for (int k = 0; k < C; k++) ((real*)a.obs_days)[row * CLG + k * LG + c.cell] = (real)LA(X, k);
+        if (a.x_days)
+          for (int k = 0; k < C; k++) a.x_days[row * CLG + k * LG + c.cell] = LA(X, k);
+        if (a.acc_days)
+          for (int a_ = 0; a_ < DIM(n_acc); a_++) ((real*)a.acc_days)[row * nA + a_ * LG + c.cell] = LA(accY, a_);
+        if (a.mult_days)
+          for (int i = c.cell; i < P.n_cls; i += LG) a.mult_days[row * P.n_cls + i] = EV(mult_d, i);
       }
     }
     // today's parameters become yesterday's (State(t+1, next_obs, dest_parameter), epidemic.py:89)

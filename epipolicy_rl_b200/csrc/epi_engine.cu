@@ -1647,8 +1647,8 @@ int epi_step_plan(epi_t* h, const float* cpv_dev, const uint8_t* active_dev, int
 }
 
 int epi_run_plan(epi_t* h, const float* cpv_days_dev, const uint8_t* active_days_dev, int schedule_programs, int n_days,
-                 void* obs_days_out_dev, double* reward_days_out_dev, void* obs_out_dev, double* reward_out_dev,
-                 uint8_t* done_out_dev, void* cuda_stream) {
+                 const EpiRunOut* days_out, void* obs_out_dev, double* reward_out_dev, uint8_t* done_out_dev,
+                 void* cuda_stream) {
   if (!h) return EPI_E_INVALID;
   return guarded(h, [&] {
     if (!cpv_days_dev) throw Invalid{"cpv_days_dev is NULL"};
@@ -1657,7 +1657,10 @@ int epi_run_plan(epi_t* h, const float* cpv_days_dev, const uint8_t* active_days
     epi::StepArgs a{};
     a.cpv = cpv_days_dev; a.active = active_days_dev;  // row 0; the kernels move on to row d on day d
     a.cpv_days = cpv_days_dev; a.active_days = active_days_dev;
-    a.obs_days = obs_days_out_dev; a.reward_days = reward_days_out_dev;
+    if (days_out) {
+      a.obs_days = days_out->obs_days; a.reward_days = days_out->reward_days; a.x_days = days_out->x_days;
+      a.acc_days = days_out->acc_days; a.mult_days = days_out->mult_days;
+    }
     a.variant = schedule_programs ? 1 : 0; a.n_days = n_days; a.N = h->N;
     a.obs_out = obs_out_dev; a.reward_out = reward_out_dev; a.done_out = done_out_dev;
     launch(h, h->S, a, (cudaStream_t)cuda_stream);

@@ -991,9 +991,18 @@ __device__ __forceinline__ void step_cta(const DevPlan& P, const DevState& S, co
         reward -= dr;  // -sum(cumulative_cost_next - cumulative_cost_current), epidemic.py:115
         t_day++;
         if (a.reward_days && b.tid == 0) a.reward_days[(size_t)day * a.N + env] = -dr;
+        const size_t row = (size_t)day * a.N + e;
         if (a.obs_days)
           FOR_CELLS
-            for (int k = 0; k < C; k++) ((real*)a.obs_days)[((size_t)day * a.N + e) * CLG + (size_t)k * LG + cell] = (real)BA(X, k);
+            for (int k = 0; k < C; k++) ((real*)a.obs_days)[row * CLG + (size_t)k * LG + cell] = (real)BA(X, k);
+        if (a.x_days)
+          FOR_CELLS
+            for (int k = 0; k < C; k++) a.x_days[row * CLG + (size_t)k * LG + cell] = BA(X, k);
+        if (a.acc_days)
+          FOR_CELLS
+            for (int a_ = 0; a_ < EDIM(n_acc); a_++) ((real*)a.acc_days)[row * nA + (size_t)a_ * LG + cell] = ACCY(a_);
+        if (a.mult_days)
+          for (int i = b.tid; i < P.n_cls; i += b.nt) a.mult_days[row * P.n_cls + i] = ET(mult_d, i);
       }
       // today's parameters become yesterday's (State(t+1, next_obs, dest_parameter), epidemic.py:89)
       for (int i = b.tid; i < P.n_cls; i += b.nt) ET(mult_y, i) = ET(mult_d, i);

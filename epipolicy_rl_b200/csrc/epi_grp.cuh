@@ -1161,11 +1161,17 @@ __device__ __forceinline__ void step_group(const DevPlan& P, const DevState& S, 
           grp_sum<1>(P, b, dr);
           if (b.cta == 0 && b.tid == 0) a.reward_days[(size_t)day * a.N + env] = dr[0];
         }
-        if (a.obs_days && b.valid) {
-#pragma unroll
-          for (int k = 0; k < C; k++)
-            ((real*)a.obs_days)[((size_t)day * a.N + e) * CLG + (size_t)k * LG + b.cell] = (real)b.gX[(size_t)k * LG + b.cell];
+        const size_t row = (size_t)day * a.N + e;
+        if (b.valid) {
+          if (a.obs_days)
+            for (int k = 0; k < C; k++) ((real*)a.obs_days)[row * CLG + (size_t)k * LG + b.cell] = (real)b.gX[(size_t)k * LG + b.cell];
+          if (a.x_days)
+            for (int k = 0; k < C; k++) a.x_days[row * CLG + (size_t)k * LG + b.cell] = b.gX[(size_t)k * LG + b.cell];
+          if (a.acc_days)
+            for (int a_ = 0; a_ < spec::n_acc; a_++) ((real*)a.acc_days)[row * nA + (size_t)a_ * LG + b.cell] = b.acc[(size_t)a_ * LG + b.cell];
         }
+        if (a.mult_days && b.cta == 0)
+          for (int i = b.tid; i < P.n_cls; i += b.T) a.mult_days[row * P.n_cls + i] = GT(mult_d, i);
       }
       // today's parameters become yesterday's (State(t+1, next_obs, dest_parameter), epidemic.py:89)
       __syncthreads();

@@ -792,6 +792,9 @@ struct StepArgs {
   const uint8_t* active_days;  // [n_days,N,I] or null (all interventions have an Act every day)
   void* obs_days;              // real [n_days,N,CLG] or null
   double* reward_days;         // [n_days,N] or null
+  double* x_days;              // [n_days,N,CLG] the state in double (reporter input), or null
+  void* acc_days;              // real [n_days,N,n_acc*LG] live cumulative components at the end of the day, or null
+  float* mult_days;            // [n_days,N,n_cls] the day's class multipliers, or null
 };
 
 // one team, one env at a time: load state, prologue + RK45 for each day, store
@@ -850,8 +853,15 @@ __device__ void step_team(const DevPlan& P, const DevState& S, const StepArgs& a
         reward -= dr;
         t_day++;
         if (a.reward_days && tm.lane == 0) a.reward_days[(size_t)day * a.N + env] = -dr;
+        const size_t row = (size_t)day * a.N + env;
         if (a.obs_days)
-          for (int i = tm.lane; i < CLG; i += tm.T) ((real*)a.obs_days)[((size_t)day * a.N + env) * CLG + i] = (real)w.X[i];
+          for (int i = tm.lane; i < CLG; i += tm.T) ((real*)a.obs_days)[row * CLG + i] = (real)w.X[i];
+        if (a.x_days)
+          for (int i = tm.lane; i < CLG; i += tm.T) a.x_days[row * CLG + i] = w.X[i];
+        if (a.acc_days)
+          for (int i = tm.lane; i < nA; i += tm.T) ((real*)a.acc_days)[row * nA + i] = w.accY[i];
+        if (a.mult_days)
+          for (int i = tm.lane; i < P.n_cls; i += tm.T) a.mult_days[row * P.n_cls + i] = w.mult_d[i];
       }
       // today's parameters become yesterday's (State(t+1, next_obs, dest_parameter), epidemic.py:89)
       for (int i = tm.lane; i < P.n_cls; i += tm.T) w.mult_y[i] = w.mult_d[i];

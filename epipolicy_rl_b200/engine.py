@@ -172,34 +172,33 @@ class BatchedEpidemic:
         if c.shape[1] != self.n_envs or (a is not None and a.shape[:2] != c.shape[:2]):
             raise ValueError("schedule must be [T, N, NCP] / [T, NCP] with matching active flags")
         self.reset()
-        if not report:
-            # ONE launch for the whole schedule (epi_run_plan): day d of the launch reads row d of the schedule and emits
-            # the day's end state and reward; no per-day launch, no per-day copies
-            c = c.contiguous()
-            a = None if a is None else a.contiguous()
-            rew = torch.zeros((T, self.n_envs), dtype=torch.float64, device=self.device)
-            obs = torch.zeros((T, self.n_envs, self.obs_dim), dtype=self.dtype, device=self.device) if record_obs else None
-            self._ck(self.L.epi_run_plan(self._h, c.data_ptr(), None if a is None else a.data_ptr(), 1 if schedule_programs else 0,
-                                         int(T), None if obs is None else obs.data_ptr(), rew.data_ptr(), self.obs.data_ptr(),
-                                         self.reward.data_ptr(), self.done.data_ptr(), self._stream()))
-            out = {"reward": rew, "done": self.done}
-            if record_obs:
-                out["obs"] = obs
-            return out
-        # with the reporter: one launch per day, the reporter's inputs (state, live cumulative components, class
-        # multipliers) recorded by stream-ordered device copies between the launches
-        from .reporter_device import DeviceReporter
-        rep = DeviceReporter(self.desc, self.plan_tables(), self.device)
-        rep.record(self.state_dev("X"), self.state_dev("acc"), self.state_dev("mult"))
-        rew = torch.empty((T, self.n_envs), dtype=torch.float64, device=self.device)
-        obs = torch.empty((T, self.n_envs, self.obs_dim), dtype=self.dtype, device=self.device) if record_obs else None
-        for t in range(T):
-            o, r, _ = self.step_plan(c[t], None if a is None else a[t], schedule_programs, 1)
-            rew[t].copy_(r)
-            if record_obs:
-                obs[t].copy_(o)
-            rep.record(self.state_dev("X"), self.state_dev("acc"), self.state_dev("mult"))
-        out = {"reward": rew, "done": self.done, "report": rep.compute()}
+        # ONE launch for the whole schedule (epi_run_plan): day d of the launch reads row d of the schedule and emits the
+        # day's end state and reward - and, for the reporter, the state in double, the live cumulative components and
+        # the class multipliers; no per-day launch, no per-day copies
+        from .lib import EpiRunOut
+        c = c.contiguous()
+        a = None if a is None else a.contiguous()
+        N, d = self.n_envs, self.desc
+        rew = torch.zeros((T, N), dtype=torch.float64, device=self.device)
+        obs = torch.zeros((T, N, self.obs_dim), dtype=self.dtype, device=self.device) if record_obs else None
+        rep = x_days = acc_days = mult_days = None
+        if report:
+            from .reporter_device import DeviceReporter
+            rep = DeviceReporter(self.desc, self.plan_tables(), self.device)
+            rep.record(self.state_dev("X"), self.state_dev("acc"), self.state_dev("mult"))  # the state after reset
+            x_days = torch.zeros((T, N, self.obs_dim), dtype=torch.float64, device=self.device)
+            acc_days = torch.zeros((T, N, self.info.n_acc, d.L * d.G), dtype=self.dtype, device=self.device)
+            mult_days = torch.zeros((T, N, self.info.n_cls), dtype=torch.float32, device=self.device)
+        ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        days = EpiRunOut(ptr(obs), ptr(rew), ptr(x_days), ptr(acc_days), ptr(mult_days))
+        import ctypes
+        self._ck(self.L.epi_run_plan(self._h, c.data_ptr(), ptr(a), 1 if schedule_programs else 0, int(T), ctypes.byref(days),
+                                     self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(), self._stream()))
+        out = {"reward": rew, "done": self.done}
+        if rep is not None:
+            for t in range(T):
+                rep.record(x_days[t], acc_days[t], mult_days[t])
+            out["report"] = rep.compute()
         if record_obs:
             out["obs"] = obs
         return out

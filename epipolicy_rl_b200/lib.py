@@ -24,6 +24,11 @@ class EpiInfo(ctypes.Structure):
         (n, ctypes.c_int64) for n in ("smem_bytes", "small_bytes", "big_bytes", "scratch_bytes", "state_bytes_per_env")]
 
 
+class EpiRunOut(ctypes.Structure):
+    """include/epi_b200.h: per-day outputs of epi_run_plan (device pointers, 0 = not wanted)"""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("obs_days", "reward_days", "x_days", "acc_days", "mult_days")]
+
+
 class EpiError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libepi_b200 error {code}: {msg}")
@@ -63,7 +68,7 @@ def bind(L):
     L.epi_step_plan.restype = I
     L.epi_step_plan.argtypes = [P, P, P, I, I, P, P, P, P]
     L.epi_run_plan.restype = I
-    L.epi_run_plan.argtypes = [P, P, P, I, I, P, P, P, P, P, P]
+    L.epi_run_plan.argtypes = [P, P, P, I, I, ctypes.POINTER(EpiRunOut), P, P, P, P]
     L.epi_step_host.restype = I
     L.epi_step_host.argtypes = [P, P, I, P, P, P]
     L.epi_get_state.restype = I

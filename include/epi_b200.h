@@ -70,16 +70,25 @@ int epi_step(epi_t* h, const float* actions_dev, int n_days, void* obs_out_dev, 
 int epi_step_plan(epi_t* h, const float* cpv_dev, const uint8_t* active_dev, int schedule_programs, int n_days,
                   void* obs_out_dev, double* reward_out_dev, uint8_t* done_out_dev, void* cuda_stream);
 
+/* Per-day outputs of epi_run_plan, all device pointers, each may be NULL. Rows of days an env does not reach (horizon)
+ * are left untouched. */
+typedef struct EpiRunOut {
+  void* obs_days;      /* real   [n_days, n_envs, obs_dim]      the day's end state, as epi_step's obs_out */
+  double* reward_days; /* double [n_days, n_envs]               the day's reward (epidemic.py:115) */
+  double* x_days;      /* double [n_days, n_envs, obs_dim]      the state at full precision (reporter input) */
+  void* acc_days;      /* real   [n_days, n_envs, n_acc * L*G]  live cumulative components (epi_get_state_dev what = 10) */
+  float* mult_days;    /* float  [n_days, n_envs, n_cls]        the day's class multipliers (what = 7) */
+} EpiRunOut;
+
 /* Epidemic.run (core/epidemic.py:118-134) for a batch of what-if schedules in ONE launch: day d of the launch takes
  * its Acts from row d of `cpv_days_dev` float32 [n_days, n_envs, ncp] and `active_days_dev` uint8 [n_days, n_envs, n_itv]
- * (NULL: every intervention has an Act every day) and emits the day's end state into `obs_days_out_dev`
- * real [n_days, n_envs, obs_dim] and the day's reward into `reward_days_out_dev` double [n_days, n_envs] (either may be
- * NULL). Rows of days an env does not reach (horizon) are left untouched. The final outputs are those of epi_step_plan
- * with the same n_days. Equivalent to n_days calls of epi_step_plan(.., n_days = 1) (bit-identical in fp64; the fp32
- * mode reuses the last stage of a day as the first of the next when the parameters did not move, as epi_step does). */
+ * (NULL: every intervention has an Act every day) and emits the day's results into `days_out` (may be NULL). The final
+ * outputs are those of epi_step_plan with the same n_days. Equivalent to n_days calls of epi_step_plan(.., n_days = 1):
+ * bit-identical in fp64; the fp32 mode reuses the last stage of a day as the first of the next when the parameters
+ * did not move, as epi_step does. */
 int epi_run_plan(epi_t* h, const float* cpv_days_dev, const uint8_t* active_days_dev, int schedule_programs, int n_days,
-                 void* obs_days_out_dev, double* reward_days_out_dev, void* obs_out_dev, double* reward_out_dev,
-                 uint8_t* done_out_dev, void* cuda_stream);
+                 const EpiRunOut* days_out, void* obs_out_dev, double* reward_out_dev, uint8_t* done_out_dev,
+                 void* cuda_stream);
 
 /* The same step through HOST buffers (what a CPU-side caller such as SB3's DummyVecEnv sees):
  * pinned staging, H2D of the actions, the fused launch, D2H of obs/reward/done, then a stream sync. */

@@ -73,10 +73,24 @@ class EmuEngine:
         T = c.shape[0]
         obs_days = np.zeros((T,) + self.obs.shape, self.obs.dtype)
         rew_days = np.zeros((T, self.n_envs), np.float64)
+        from epipolicy_rl_b200.lib import EpiRunOut
+        d = self.desc
+        self.x_days = np.zeros((T, self.n_envs, d.C * d.L * d.G), np.float64)
+        self.acc_days = np.zeros((T, self.n_envs, self.info.n_acc, d.L * d.G), self.obs.dtype)
+        self.mult_days = np.zeros((T, self.n_envs, self.info.n_cls), np.float32)
+        out = EpiRunOut(obs_days.ctypes.data, rew_days.ctypes.data, self.x_days.ctypes.data, self.acc_days.ctypes.data,
+                        self.mult_days.ctypes.data)
         self._ck(self.L.epi_run_plan(self._h, c.ctypes.data, a.ctypes.data if a is not None else None,
-                                     1 if schedule_programs else 0, T, obs_days.ctypes.data, rew_days.ctypes.data,
+                                     1 if schedule_programs else 0, T, ctypes.byref(out),
                                      self.obs.ctypes.data, self.reward.ctypes.data, self.done.ctypes.data, None))
         return obs_days, rew_days
+
+    def acc(self):
+        """the live cumulative components [N, n_acc, L*G] (epi_get_state_dev what = 10; "device" memory is host memory here)"""
+        d = self.desc
+        out = np.empty((self.n_envs, self.info.n_acc, d.L * d.G), self.obs.dtype)
+        self._ck(self.L.epi_get_state_dev(self._h, 10, out.ctypes.data, out.nbytes, None))
+        return out
 
     def get_state(self, what):
         d, N = self.desc, self.n_envs

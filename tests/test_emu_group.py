@@ -104,5 +104,7 @@ def test_group_kernel_run_plan_one_launch(monkeypatch):
         o, r, _ = daily.step_plan(cpv[t], None, False, 1)
         assert x_err(obs_days[t], o, d) <= 1e-5, t
         assert np.allclose(rew_days[t], r, rtol=1e-5), t
+        assert x_err(one.x_days[t], daily.get_state("X"), d) <= 1e-5 and np.array_equal(one.mult_days[t], daily.get_state("mult"))
+        assert np.allclose(one.acc_days[t], daily.acc(), rtol=1e-4, atol=1e-3), t
     assert x_err(one.get_state("X"), daily.get_state("X"), d) <= 1e-5
     one.close(); daily.close()

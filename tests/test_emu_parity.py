@@ -254,6 +254,10 @@ def test_run_plan_one_launch_equals_daily_launches(name, knobs, monkeypatch):
         o, r, _ = daily.step_plan(cpv[t], act[t], True, 1)
         assert np.array_equal(obs_days[t], o), t
         assert np.array_equal(rew_days[t], r), t
+        # the reporter's inputs, emitted per day: state in double, live cumulative components, class multipliers
+        assert np.array_equal(one.x_days[t], daily.get_state("X").reshape(2, -1)), t
+        assert np.array_equal(one.acc_days[t], daily.acc()), t
+        assert np.array_equal(one.mult_days[t], daily.get_state("mult")), t
     assert x_err(obs_days[:, 0].reshape(T, d.C, d.L, d.G), z["sched_X"][:T], d) <= 1e-9
     assert not np.array_equal(obs_days[-1, 0], obs_days[-1, 1])
     assert np.array_equal(one.get_state("X"), daily.get_state("X")) and np.array_equal(one.get_state("cost"), daily.get_state("cost"))

@@ -154,9 +154,23 @@ def main():
           "beats_lax": trained > base["lax"], "beats_random": trained > base["random"],
           "update_mode": args.update if args.algo == "ppo" else None, "epochs": args.epochs, "minibatches": args.minibatches,
           "first_update_reward": hist[0]["mean_step_reward"], "last_update_reward": hist[-1]["mean_step_reward"], **extra})
-    env.close()
+    # teardown: the captured graphs hold NCCL work (sharded mode all-reduces inside the update graph) and must go before
+    # the process group does; a watchdog ends the process if the teardown still blocks (observed once at 8 GPUs: the
+    # results above are complete and flushed at this point)
+    import gc
+    import threading
+    sys.stdout.flush()
+    if logf:
+        logf.close()
+    threading.Thread(target=lambda: (time.sleep(30), os._exit(0)), daemon=True).start()
+    if args.algo == "ppo":
+        ppo._graph = ppo._ugraph = None
+    gc.collect()
+    torch.cuda.synchronize()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    env.close()
 
 
 if __name__ == "__main__":
