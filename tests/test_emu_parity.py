@@ -262,3 +262,32 @@ def test_run_plan_one_launch_equals_daily_launches(name, knobs, monkeypatch):
     assert not np.array_equal(obs_days[-1, 0], obs_days[-1, 1])
     assert np.array_equal(one.get_state("X"), daily.get_state("X")) and np.array_equal(one.get_state("cost"), daily.get_state("cost"))
     one.close(); daily.close()
+
+
+def test_product_host_class_run_on_the_emulation():
+    """engine.BatchedEpidemic.run as shipped (argument handling, EpiRunOut, the reporter fed from the per-day emission),
+    executed on the CPU against the emulated library: what-if schedules in one launch; env 0 = the reference's run."""
+    import torch
+    from host_engine import HostBatchedEpidemic
+    d, z = load("COVID_C")
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reporter_COVID_C.npz"))
+    T, n = int(g["T"]), 3
+    eng = HostBatchedEpidemic(d, n, "fp64")
+    cpv = torch.from_numpy(z["sched_plan_cpv"][:T]).float()[:, None, :].repeat(1, n, 1)
+    cpv[:, 1:, :] = cpv[:, 1:, :] * torch.tensor([0.5, 0.8])[None, :, None]
+    act = torch.from_numpy(z["sched_plan_active"][:T].astype(np.uint8))  # [T, I]: broadcast over the envs
+    n0 = eng.launches
+    out = eng.run(cpv, act, report=True)
+    assert eng.launches - n0 <= 2  # reset + ONE step launch
+    obs = out["obs"].numpy()
+    for day in range(T):
+        assert x_err(obs[day, 0], z["sched_X"][day], d) <= 1e-9, day
+    assert np.allclose(out["reward"][:, 0].numpy(), z["sched_rewards"][:T], rtol=1e-9)
+    assert x_err(obs[T - 1, 1], z["sched_X"][T - 1], d) > 1e-6
+    rel = lambda a, b, floor: float(np.max(np.abs(a - b) / (np.abs(b) + floor)))  # noqa: E731
+    for key, floor in (("location_instant_R", 1e-9), ("location_basic_R", 1e-9), ("location_case_R", 1e-9)):
+        assert rel(out["report"][key][:, 0].numpy(), g[key], floor) <= 1e-9, key
+    # the [T, NCP] form (one schedule for every env) and no recorded observations
+    out2 = eng.run(torch.from_numpy(z["sched_plan_cpv"][:T]), act, record_obs=False)
+    assert "obs" not in out2 and torch.equal(out2["reward"][:, 1], out["reward"][:, 0])
+    eng.close()
