@@ -41,3 +41,35 @@ def test_random_weekly_actions_vs_oracle(name, prec):
     print(f"{name} {prec}: X {worst:.2e} cost {worst_c:.2e} reward {worst_r:.2e}")
     assert worst <= TOL[prec] and worst_c <= TOL[prec] and worst_r <= TOL[prec]
     eng.close()
+
+
+@pytest.mark.parametrize("spec", [False, True], ids=["interpreted", "specialised"])
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+def test_random_border_closures_vs_oracle(prec, spec):
+    """mobility multipliers on fresh inputs: three envs of one warp follow different what-if schedules of the border
+    scenario (random closure degrees that change on some days and stay on others, so the envs' mobility tables and
+    their 'parameters moved today' flags differ inside the warp), day by day against the oracle"""
+    d, z = load("COVID_C_border")
+    n, T = 3, 24
+    rng = np.random.default_rng(17)
+    cpv = np.repeat(z["sched_plan_cpv"][:T, None, :], n, 1).astype(np.float32)
+    act = np.repeat(z["sched_plan_active"][:T, None, :], n, 1).astype(np.uint8)
+    free = np.where(d.cp_min != d.cp_max)[0]
+    for e in range(n):
+        for t in range(T):
+            if t == 0 or rng.uniform() < 0.4:  # redraw every free control parameter (the closure degree among them)
+                cpv[t:, e, free] = rng.uniform(d.cp_min[free], d.cp_max[free]).astype(np.float32)
+    eng = EmuEngine(d, n, prec)
+    if spec:
+        eng.attach_spec()
+    oracles = [Oracle(d) for _ in range(n)]
+    worst = worst_c = 0.0
+    for t in range(T):
+        eng.step_plan(cpv[t], act[t], True, 1)
+        for e, o in enumerate(oracles):
+            o.day_step(cpv[t, e], act[t, e], init_programs=True)
+            worst = max(worst, x_err(eng.get_state("X")[e], o.X, d))
+            worst_c = max(worst_c, cost_err(eng.get_state("cost")[e], o.cost))
+    print(f"border random {prec} spec={spec}: X {worst:.2e} cost {worst_c:.2e}")
+    assert worst <= TOL[prec] and worst_c <= TOL[prec]
+    eng.close()
