@@ -178,10 +178,17 @@ def run_reference(args):
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
         job = [(args.workload, per_core, 1, days, 100 + i) for i in range(cores)]
-        for _ in range(max(min(args.warmup, 2), 1)):
+        # bound the whole run (the contract: a default --steps K --warmup W run ends within a few minutes): on SYN the
+        # smallest possible step - one simulated day of one env per core - already takes ~25 s, so the number of timed
+        # steps is capped by --ref-total-seconds and reported as `steps` (the request as `steps_requested`)
+        step_est = 1.25 * (one / PERIOD) * days * per_core
+        n_warm = max(min(args.warmup, 2), 1) if step_est < 5.0 else 1
+        n_steps = min(args.steps, max(2, int((args.ref_total_seconds - n_warm * step_est) / step_est)))
+        for _ in range(n_warm):
             pool.map(_ref_worker, job)
         t0 = time.perf_counter()
         done = 0.0
+        steps_requested, args.steps, args.warmup = args.steps, n_steps, n_warm
         for k in range(args.steps):
             done += sum(pool.map(_ref_worker, [(args.workload, per_core, 1, days, 1000 + k * cores + i) for i in range(cores)]))
         dt = time.perf_counter() - t0
@@ -196,7 +203,7 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample,
                              "python_reference_survey": PY_REF},
             "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "steps_requested": steps_requested}
     print(json.dumps(line), flush=True)
 
 
@@ -408,6 +415,8 @@ def main():
     ap.add_argument("--cpu-sample-envs", type=int, default=64)
     ap.add_argument("--cpu-sample-steps", type=int, default=53)
     ap.add_argument("--ref-envs-per-core", type=int, default=64)
+    ap.add_argument("--ref-total-seconds", type=float, default=240.0,
+                    help="--impl reference: bound on the whole run; caps the number of timed steps when one step is slow")
     ap.add_argument("--ref-seconds-per-step", type=float, default=3.0,
                     help="--impl reference: CPU seconds per core and step the bounded sample aims at")
     args = ap.parse_args()
