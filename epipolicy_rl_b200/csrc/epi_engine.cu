@@ -368,16 +368,22 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
   P.n_chg = n_chg;
 
   // ---- MOVE ops -> slots
+  // Regular case (every shipped intervention): the move stays inside a locale ("different compartment, same locale",
+  // executor.py:201-212) and is a per-cell table. A move whose targets lie in other locales (executor.py:185-200,
+  // :213-233) switches the engine to GENERAL MOVE ENTRIES (xmove): a static list of (group, c1, c2, l1, l2) entries in
+  // the reference's insertion order, per-env amounts per entry, applied source cell by source cell with the
+  // reference's sequential clamp (core_optimize.py:196-208). Team kernels only.
   std::vector<int> mv_op, mv_c1_off{0}, mv_c1, mv_c2_off{0}, mv_c2, slot_of_pair((size_t)C * C, -1);
   std::vector<uint8_t> mv_g, mv_l1;
   std::vector<std::pair<int, int>> slots;
+  bool xmove = false;
   for (int o = 0; o < d.NOP; o++) {
     if (d.op_kind[o] != EPI_OP_MOVE) continue;
     const int32_t* a = d.op_arg + 8 * o;
     auto c1 = list(a[0]), c2 = list(a[3]);
     auto l1 = mask(a[1], L), g1 = mask(a[2], G), l2 = mask(a[4], L), g2 = mask(a[5], G);
-    for (int x : c1) for (int y : c2) if (x == y) throw Unsupported{"sim.move between locales within one compartment"};
-    for (int l = 0; l < L; l++) if (l1[l] && !l2[l]) throw Unsupported{"sim.move across locales"};
+    for (int x : c1) for (int y : c2) if (x == y) xmove = true;         // targets in the same compartment: other locales
+    for (int l = 0; l < L; l++) if (l1[l] && !l2[l]) xmove = true;     // a source locale that is not a target locale
     mv_op.push_back(o);
     for (int g = 0; g < G; g++) mv_g.push_back(g1[g] && g2[g]);
     mv_l1.insert(mv_l1.end(), l1.begin(), l1.end());
@@ -390,8 +396,75 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
   if (n_slot > EPI_MAX_SLOTS) throw Unsupported{"more than 8 distinct move (c1,c2) pairs"};
   for (int a = 0; a < n_slot; a++) for (int b = 0; b < n_slot; b++) {
     if (a != b && slots[a].first == slots[b].first) throw Unsupported{"two moves out of one compartment (order-dependent clamp)"};
-    if (slots[a].second == slots[b].first) throw Unsupported{"a move target that is another move's source (order-dependent clamp)"};
+    if ((a != b || !xmove) && slots[a].second == slots[b].first) throw Unsupported{"a move target that is another move's source (order-dependent clamp)"};
   }
+  // general move entries
+  std::vector<int> ent_g, ent_c1, ent_c2, ent_l1, ent_l2, ent_mo, ent_sl, src_off{0}, src_mo, src_idx, src_sl, mo_src_off{0},
+      tgt_off{0}, tgt_ent, tgt_idx, tgt_sl;
+  if (xmove) {
+    if (mv_op.size() > 16) throw Unsupported{"more than 16 move ops with cross-locale moves"};
+    for (size_t mo = 0; mo < mv_op.size(); mo++) {
+      const int32_t* a = d.op_arg + 8 * mv_op[mo];
+      auto c1s = list(a[0]), l1s = list(a[1]), g1s = list(a[2]), c2s = list(a[3]), l2s = list(a[4]);
+      auto c2m = mask(a[3], C), l2m = mask(a[4], L), g2m = mask(a[5], G);
+      for (int g : g1s) {
+        if (!g2m[g]) continue;
+        for (int c1 : c1s) for (int l1 : l1s) {
+          // one source cell (executor.py:178-183: it counts in the departing population whether or not it has targets)
+          src_mo.push_back((int)mo); src_idx.push_back(c1 * LG + l1 * G + g);
+          auto add = [&](int c2, int l2) {
+            ent_g.push_back(g); ent_c1.push_back(c1); ent_c2.push_back(c2); ent_l1.push_back(l1); ent_l2.push_back(l2);
+            ent_mo.push_back((int)mo); ent_sl.push_back(slot_of_pair[(size_t)c1 * C + c2]);
+          };
+          if (c2m[c1]) { if (!l2m[l1]) for (int l2 : l2s) add(c1, l2); }           // :185-200
+          else if (l2m[l1]) { for (int c2 : c2s) add(c2, l1); }                     // :201-212
+          else { for (int c2 : c2s) for (int l2 : l2s) add(c2, l2); }              // :213-233
+          src_off.push_back((int)ent_g.size());
+        }
+      }
+      mo_src_off.push_back((int)src_mo.size());
+    }
+    if (ent_g.size() > (size_t)1 << 22) throw Unsupported{"more than 4 M cross-locale move entries"};
+    // order independence between ops (the reference applies the entries in dict-insertion order, which depends on the
+    // history of live ops): among ops that can be live together (same program variant), every entry comes from one op,
+    // a source cell with entries belongs to one op, and no target cell is a source cell with entries
+    for (int variant = 0; variant < 2; variant++) {
+      auto in_set = [&](int mo) { int o = mv_op[mo], itv = d.op_itv[o]; return op_prog[o] == (variant ? d.prog_init[itv] : d.prog_step[itv]); };
+      std::map<std::vector<int>, int> owner;
+      std::map<int, int> src_owner;  // (compartment, cell) with outgoing entries -> op
+      for (size_t s_ = 0; s_ < src_mo.size(); s_++) {
+        if (!in_set(src_mo[s_]) || src_off[s_ + 1] == src_off[s_]) continue;
+        auto it = src_owner.find(src_idx[s_]);
+        if (it != src_owner.end() && it->second != src_mo[s_]) throw Unsupported{"two move ops out of one cell (order-dependent clamp)"};
+        src_owner[src_idx[s_]] = src_mo[s_];
+      }
+      for (size_t e = 0; e < ent_g.size(); e++) {
+        if (!in_set(ent_mo[e])) continue;
+        std::vector<int> key{ent_g[e], ent_c1[e], ent_c2[e], ent_l1[e], ent_l2[e]};
+        if (owner.count(key)) throw Unsupported{"two move ops feeding one (compartment, locale) pair (order-dependent sum)"};
+        owner[key] = ent_mo[e];
+        if (src_owner.count(ent_c2[e] * LG + ent_l2[e] * G + ent_g[e])) throw Unsupported{"a move target that is another move's source (order-dependent clamp)"};
+      }
+    }
+    for (size_t s_ = 0; s_ < src_mo.size(); s_++) {
+      int c1 = src_idx[s_] / LG, sl = -1;
+      for (int q = 0; q < n_slot; q++) if (slots[q].first == c1) sl = q;
+      src_sl.push_back(sl);
+    }
+    // target cells: their incoming entries in list order
+    std::map<int, std::vector<int>> by_tgt;
+    for (size_t e = 0; e < ent_g.size(); e++) by_tgt[ent_c2[e] * LG + ent_l2[e] * G + ent_g[e]].push_back((int)e);
+    for (auto& kv : by_tgt) {
+      tgt_idx.push_back(kv.first);
+      int c2 = kv.first / LG, sl = -1;
+      for (int q = 0; q < n_slot; q++) if (slots[q].first == c2) sl = q;  // the target's compartment is carried in double too
+      tgt_sl.push_back(sl);
+      tgt_ent.insert(tgt_ent.end(), kv.second.begin(), kv.second.end());
+      tgt_off.push_back((int)tgt_ent.size());
+    }
+  }
+  P.xmove = xmove ? 1 : 0; P.n_ent = (int)ent_g.size(); P.n_src = (int)src_mo.size(); P.n_tgt = (int)tgt_idx.size();
+  P.mv_len = xmove ? (P.n_ent > 0 ? P.n_ent : 1) : n_slot * LG;
   P.n_slot = n_slot; P.n_mv_op = (int)mv_op.size();
   std::vector<uint8_t> slot_cover((size_t)n_slot * LG, 0);
   for (size_t mo = 0; mo < mv_op.size(); mo++)
@@ -586,7 +659,7 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
     P.o_flows = take(rs * (int64_t)P.NSRC * LG);
     P.o_alive = take(rs * LG); P.o_Xw = take(rs * (int64_t)NG * LG); P.o_Ag = take(rs * LG); P.o_Wg = take(rs * (int64_t)NG * LG);
     P.o_s = take(rs * (int64_t)NG * LG); P.o_r = take(rs * (int64_t)NG * LG);
-    P.o_mvY = take(4 * (int64_t)n_slot * LG); P.o_mvD = take(4 * (int64_t)n_slot * LG);
+    P.o_mvY = take(4 * (int64_t)P.mv_len); P.o_mvD = take(4 * (int64_t)P.mv_len); P.o_xnv = take(xmove ? 8 * (int64_t)P.mv_len : 0);
     P.o_cost = take(8 * (int64_t)I * L); P.o_crY = take(8 * (int64_t)I * L); P.o_crD = take(8 * (int64_t)I * L);
     P.has_src64 = (rs == 4 && n_slot > 0) ? 1 : 0;
     P.o_ysS = take(P.has_src64 ? 8 * (int64_t)n_slot * LG : 0); P.o_KS = take(P.has_src64 ? 8 * 7 * (int64_t)n_slot * LG : 0);
@@ -638,6 +711,10 @@ void build_plan(epi_engine* h, const EpiDesc& d) {
   P.sel_c = h->up(sel_c); P.sel_l = h->up(sel_l); P.sel_g = h->up(sel_g); P.sel_mode = h->up(sel_mode); P.chg_slot_of_comp = h->up(chg_slot);
   P.mv_op = h->up(mv_op); P.mv_g = h->up(mv_g); P.mv_l1 = h->up(mv_l1); P.mv_c1_off = h->up(mv_c1_off); P.mv_c1 = h->up(mv_c1);
   P.mv_c2_off = h->up(mv_c2_off); P.mv_c2 = h->up(mv_c2); P.slot_of_pair = h->up(slot_of_pair); P.slot_cover = h->up(slot_cover);
+  P.ent_g = h->up(ent_g); P.ent_c1 = h->up(ent_c1); P.ent_c2 = h->up(ent_c2); P.ent_l1 = h->up(ent_l1); P.ent_l2 = h->up(ent_l2);
+  P.ent_mo = h->up(ent_mo); P.ent_sl = h->up(ent_sl); P.src_off = h->up(src_off); P.src_mo = h->up(src_mo); P.src_idx = h->up(src_idx);
+  P.src_sl = h->up(src_sl); P.mo_src_off = h->up(mo_src_off); P.tgt_off = h->up(tgt_off); P.tgt_ent = h->up(tgt_ent);
+  P.tgt_idx = h->up(tgt_idx); P.tgt_sl = h->up(tgt_sl);
   P.cr_off = h->up(cr_off); P.cr_ops = h->up(cr_ops); P.selc_off = h->up(selc_off); P.selc = h->up(selc);
   P.add_op = h->up(add_op); P.add_i = h->up(add_i); P.add_l = h->up(add_l); P.add_parts = h->up(add_parts);
   P.cp_src = h->up(cp_src); P.cp_fixed = h->up(cp_fixed); P.init_cpv = h->up(vec(d.init_cpv, d.NCP)); P.init_active = h->up(init_active);
@@ -1226,7 +1303,7 @@ void alloc_state(epi_engine* h, DevState& S, int N) {
   S.acc = h->dalloc<char>((size_t)N * P.n_acc * LG * rs);
   S.cost = h->dalloc<double>((size_t)N * P.I * P.L);
   S.crY = h->dalloc<double>((size_t)N * P.I * P.L);
-  S.mvY = h->dalloc<float>((size_t)N * P.n_slot * LG);
+  S.mvY = h->dalloc<float>((size_t)N * P.mv_len);
   S.Xprev = h->dalloc<double>((size_t)N * P.n_chg * LG);
   S.multY = h->dalloc<float>((size_t)N * P.n_cls);
   S.meta = h->dalloc<int>((size_t)N * 8);
@@ -1242,7 +1319,8 @@ void choose_launch(epi_engine* h) {
   int64_t per_env = P.small_bytes + P.big_bytes;
   const char* force = getenv("EPI_TEAM");  // debugging aid: "warp" / "cta" force the team kernels
   P.cl.enabled = 0;
-  if (P.LG <= 32 && !(force && (!strcmp(force, "warp") || !strcmp(force, "cta") || !strcmp(force, "env")))) {
+  // (cross-locale moves, xmove: general move entries exist in the team kernels only)
+  if (P.LG <= 32 && !P.xmove && !(force && (!strcmp(force, "warp") || !strcmp(force, "cta") || !strcmp(force, "env")))) {
 #ifdef EPI_HOST_EMU
     int W = P.LG * (h->N < 32 / P.LG ? h->N : 32 / P.LG);  // as many lanes as the test's envs need
 #else
@@ -1264,7 +1342,8 @@ void choose_launch(epi_engine* h) {
   P.el.enabled = 0;
   // (mobility multipliers, MOB_MUL: per-env mobility tables exist in the cell kernel and the team kernels only)
   if (P.mob_dyn && force && !strcmp(force, "env")) throw Unsupported{"mobility multipliers in the env kernel"};
-  if (!P.mob_dyn && (P.LG > 32 || (force && !strcmp(force, "env"))) && !(force && (!strcmp(force, "warp") || !strcmp(force, "cta")))) {
+  if (P.xmove && force && !strcmp(force, "env")) throw Unsupported{"cross-locale moves in the env kernel"};
+  if (!P.mob_dyn && !P.xmove && (P.LG > 32 || (force && !strcmp(force, "env"))) && !(force && (!strcmp(force, "warp") || !strcmp(force, "cta")))) {
     // ENV kernel: one CTA per env, threads strided over the cells
 #ifdef EPI_HOST_EMU
     int threads = P.LG < 24 ? P.LG : 24;  // host threads per emulated CTA
@@ -1587,7 +1666,7 @@ int epi_info(const epi_t* h, EpiInfo* o) {
   o->small_bytes = P.small_bytes; o->big_bytes = P.big_bytes; o->scratch_bytes = (int64_t)h->scratch_bytes;
   int64_t rs = (int64_t)h->real_size();
   o->state_bytes_per_env = 8 * (P.CLG + (int64_t)P.n_chg * P.LG) + rs * (int64_t)P.n_acc * P.LG + 16 * (int64_t)P.I * P.L +
-                           4 * ((int64_t)P.n_slot * P.LG + P.n_cls) + 32 + 8;
+                           4 * ((int64_t)P.mv_len + P.n_cls) + 32 + 8;
   return EPI_OK;
 }
 
@@ -1762,7 +1841,7 @@ int epi_get_state(epi_t* h, int what, void* out, size_t bytes) {
       case 5: need(N * 8); CK(cudaMemcpy(out, h->S.last_err, bytes, cudaMemcpyDeviceToHost)); break;
       case 6: need(N * nC * 8); CK(cudaMemcpy(out, h->S.crY, bytes, cudaMemcpyDeviceToHost)); break;
       case 7: need(N * P.n_cls * 4); CK(cudaMemcpy(out, h->S.multY, bytes, cudaMemcpyDeviceToHost)); break;
-      case 8: need(N * P.n_slot * LG * 4); if (bytes) CK(cudaMemcpy(out, h->S.mvY, bytes, cudaMemcpyDeviceToHost)); break;
+      case 8: need(N * (size_t)P.mv_len * 4); if (bytes) CK(cudaMemcpy(out, h->S.mvY, bytes, cudaMemcpyDeviceToHost)); break;
       case 9: {  // (h, error_norm) per attempted RK step of the last day; recording starts at the first query
         need(N * 128 * 8);
         if (!h->dbg_attempts) h->dbg_attempts = h->dalloc<double>(N * 128);
@@ -1793,7 +1872,7 @@ int epi_set_state(epi_t* h, int what, const void* in, size_t bytes) {
       } break;
       case 6: need(N * nC * 8); CK(cudaMemcpy(h->S.crY, in, bytes, cudaMemcpyHostToDevice)); break;
       case 7: need(N * P.n_cls * 4); CK(cudaMemcpy(h->S.multY, in, bytes, cudaMemcpyHostToDevice)); break;
-      case 8: need(N * P.n_slot * (size_t)P.LG * 4); if (bytes) CK(cudaMemcpy(h->S.mvY, in, bytes, cudaMemcpyHostToDevice)); break;
+      case 8: need(N * (size_t)P.mv_len * 4); if (bytes) CK(cudaMemcpy(h->S.mvY, in, bytes, cudaMemcpyHostToDevice)); break;
       default: throw Invalid{"state selector not settable"};
     }
   });
@@ -1861,6 +1940,9 @@ int epi_spec_source_desc(const EpiDesc* desc, int precision, char* buf, size_t c
   int rc = guarded(nullptr, [&] {
     h->d = *desc;
     build_plan(h, *desc);
+    // scenarios that run on the team kernels have no specialised build
+    if (h->plan.xmove) throw Unsupported{"cross-locale moves run on the team kernels: no specialised build"};
+    if (h->plan.mob_dyn && h->plan.LG > 32) throw Unsupported{"mobility multipliers with L*G > 32 run on the team kernels: no specialised build"};
     if (h->plan.LG <= 32) build_cell_layout(h, 32);
     else {
       build_env_layout(h, env_threads(h->plan.LG), 232448 - 1024);  // B200: 227 KB opt-in shared memory per CTA

@@ -91,6 +91,7 @@ struct Ws {
   // double. A clamped source decays like exp(-t) to 1e-46 and below while the reference still splits the
   // day's doses in proportion to those values (executor.py:181-183); float would freeze them at 0.
   double *ysS, *KS;
+  double* xnv;  // general move entries (P.xmove): the clamped amount of every entry in the current evaluation
 };
 
 template <class real>
@@ -111,7 +112,7 @@ __device__ __forceinline__ void bind_ws(const DevPlan& P, char* small, char* big
   w.Wg = (real*)(big + P.o_Wg); w.s = (real*)(big + P.o_s); w.r = (real*)(big + P.o_r);
   w.mvY = (float*)(big + P.o_mvY); w.mvD = (float*)(big + P.o_mvD);
   w.cost = (double*)(big + P.o_cost); w.crY = (double*)(big + P.o_crY); w.crD = (double*)(big + P.o_crD);
-  w.ysS = (double*)(big + P.o_ysS); w.KS = (double*)(big + P.o_KS);
+  w.ysS = (double*)(big + P.o_ysS); w.KS = (double*)(big + P.o_KS); w.xnv = (double*)(big + P.o_xnv);
 }
 
 // f32 linear interpolation with the reference's rounding points (obj/parameter.py:85-89)
@@ -338,6 +339,52 @@ __device__ void rhs(const DevPlan& P, const Ws<real>& w, const Team<CTA>& tm, do
       d += w.flows[__ldg(P.xg_src + q) * LG + cell] * (real)__ldg(P.xg_coef + q);
     Kout[it] = d;
   }
+  // ---- phase G with general move entries (a MOVE op with targets in other locales): source cell by source cell, the
+  // reference's sequential clamp over the cell's outgoing entries (next[c1,l1,g] shrinks entry by entry,
+  // core_optimize.py:196-208); then every target cell adds what arrived, in list order. The engine admits only
+  // entry lists whose result does not depend on the order between ops (build_plan).
+  if (P.xmove) {
+    tm.sync();
+    for (int it = tm.lane; it < P.n_slot * LG; it += tm.T) {
+      w.flows[(nE + NG) * LG + it] = 0;
+      if (P.has_src64) w.KS[(size_t)stage * P.n_slot * LG + it] = (double)Kout[P.slot_c1[it / LG] * LG + it % LG];
+    }
+    tm.sync();
+    for (int s_ = tm.lane; s_ < P.n_src; s_ += tm.T) {
+      const int e0 = P.src_off[s_], e1 = P.src_off[s_ + 1], mo = P.src_mo[s_];
+      if (e0 == e1 || !((ex_bits >> mo) & 0x10001)) continue;
+      const bool has_y = (ex_bits >> mo) & 1, has_d = (ex_bits >> (16 + mo)) & 1;
+      const int i1 = P.src_idx[s_], cell = i1 % LG, sl1 = P.src_sl[s_];
+      const double y1 = P.has_src64 ? w.ysS[sl1 * LG + cell] : (double)y[i1];
+      double n1 = y1 + (double)Kout[i1];
+      for (int e = e0; e < e1; e++) {
+        const float my = has_y ? w.mvY[e] : 0.0f, md = has_d ? w.mvD[e] : 0.0f;
+        const float v = __fadd_rn(__fmul_rn(__fsub_rn(md, my), qf), my);  // coo.py scale/add in f32
+        const double nv = (double)v < n1 ? (double)v : n1;
+        n1 -= nv;
+        w.xnv[e] = nv;
+        if (P.ent_l1[e] == P.ent_l2[e]) w.flows[(nE + NG + P.ent_sl[e]) * LG + cell] = (real)nv;  // cumulative_move: same locale only
+      }
+      const double k1 = n1 - y1;
+      Kout[i1] = (real)k1;
+      if (P.has_src64) w.KS[((size_t)stage * P.n_slot + sl1) * LG + cell] = k1;
+    }
+    tm.sync();
+    for (int t_ = tm.lane; t_ < P.n_tgt; t_ += tm.T) {
+      const int i2 = P.tgt_idx[t_], cell = i2 % LG, sl2 = P.tgt_sl[t_];
+      const double y2 = (P.has_src64 && sl2 >= 0) ? w.ysS[sl2 * LG + cell] : (double)y[i2];
+      double n2 = y2 + (double)Kout[i2];
+      bool any = false;
+      for (int q = P.tgt_off[t_]; q < P.tgt_off[t_ + 1]; q++) {
+        const int e = P.tgt_ent[q];
+        if ((ex_bits >> P.ent_mo[e]) & 0x10001) { n2 += w.xnv[e]; any = true; }
+      }
+      if (any) {
+        Kout[i2] = (real)(n2 - y2);
+        if (P.has_src64 && sl2 >= 0) w.KS[((size_t)stage * P.n_slot + sl2) * LG + cell] = n2 - y2;
+      }
+    }
+  } else
   // ---- phase G: clamped moves; each cell is owned by one thread, slots in op order
   if (P.n_slot > 0) {
     tm.sync();
@@ -504,10 +551,37 @@ __device__ int prologue(const DevPlan& P, const Ws<real>& w, const Team<CTA>& tm
   }
   if (P.mob_dyn)  // the mode matrices of yesterday and today -> (y, gap)
     for (int it = tm.lane; it < P.M * G * L; it += tm.T) mob_row(P, w.mult_y, w.mult_d, it / (G * L), (it / L) % G, it % L, w.mob_y, w.mob_g);
-  // 5. move table of today (nb_move, executor.py:166-234; different compartment, same locale)
-  for (int it = tm.lane; it < P.n_slot * LG; it += tm.T) w.mvD[it] = 0.0f;
+  // 5. move table of today (nb_move, executor.py:166-234)
+  for (int it = tm.lane; it < P.mv_len; it += tm.T) w.mvD[it] = 0.0f;
   int ex_d = 0;
   tm.sync();
+  if (P.xmove) {
+    // general move entries: all three branches of nb_move. Bit mo of the existence mask: the op added its entries today
+    for (int mo = 0; mo < P.n_mv_op; mo++) {
+      const int o = P.mv_op[mo];
+      if (!op_live(P, w.act, variant, o)) continue;  // uniform across the team
+      const double value = w.expr[P.op_expr[o]];
+      double part = 0;
+      for (int s_ = P.mo_src_off[mo] + tm.lane; s_ < P.mo_src_off[mo + 1]; s_ += tm.T) part += w.X[P.src_idx[s_]];
+      const double depart_sum = tm.sum(part);
+      if (depart_sum > 0) {
+        for (int s_ = P.mo_src_off[mo] + tm.lane; s_ < P.mo_src_off[mo + 1]; s_ += tm.T) {
+          const int e0 = P.src_off[s_], e1 = P.src_off[s_ + 1];
+          if (e0 == e1) continue;
+          const double depart = w.X[P.src_idx[s_]] / depart_sum * value;
+          double arrive = 0;
+          for (int e = e0; e < e1; e++) arrive += w.X[P.ent_c2[e] * LG + P.ent_l2[e] * G + P.ent_g[e]];
+          for (int e = e0; e < e1; e++) {
+            const double amt = arrive > 0 ? w.X[P.ent_c2[e] * LG + P.ent_l2[e] * G + P.ent_g[e]] / arrive * depart
+                                          : 1.0 / (e1 - e0) * depart;
+            w.mvD[e] = (float)(0.0 + amt);  // CooMatrix.element_add into a fresh f32 cell (coo.py:52-57)
+          }
+        }
+        ex_d |= 1 << mo;
+      }
+      tm.sync();
+    }
+  } else
   for (int mo = 0; mo < P.n_mv_op; mo++) {
     int o = P.mv_op[mo];
     if (!op_live(P, w.act, variant, o)) continue;  // uniform across the team
@@ -803,7 +877,7 @@ __device__ void step_team(const DevPlan& P, const DevState& S, const StepArgs& a
                           int n_teams, char* small, char* big) {
   Ws<real> w;
   bind_ws<real>(P, small, big, w);
-  const int CLG = P.CLG, LG = P.LG, nA = P.n_acc * LG, nC = P.I * P.L, nM = P.n_slot * LG;
+  const int CLG = P.CLG, LG = P.LG, nA = P.n_acc * LG, nC = P.I * P.L, nM = P.mv_len;
 
   for (int env = team; env < a.N; env += n_teams) {
     // ---- load the env's persistent state
@@ -933,7 +1007,7 @@ void step_emulated(const DevPlan& P, const DevState& S, const StepArgs& a) {
 template <class real>
 __global__ void reset_kernel(const DevPlan P, const DevState S, const DevState init, const uint8_t* mask, int N,
                              void* obs_out) {
-  const int CLG = P.CLG, LG = P.LG, nA = P.n_acc * LG, nC = P.I * P.L, nM = P.n_slot * LG, nP = P.n_chg * LG;
+  const int CLG = P.CLG, LG = P.LG, nA = P.n_acc * LG, nC = P.I * P.L, nM = P.mv_len, nP = P.n_chg * LG;
   for (int env = blockIdx.x; env < N; env += gridDim.x) {
     if (mask && !mask[env]) continue;
     for (int i = threadIdx.x; i < CLG; i += blockDim.x) {

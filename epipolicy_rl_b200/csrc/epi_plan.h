@@ -131,6 +131,13 @@ struct DevPlan {
   const int* slot_of_pair;              // [C*C] slot id or -1
   int slot_c1[EPI_MAX_SLOTS], slot_c2[EPI_MAX_SLOTS];
   const uint8_t* slot_cover;            // [n_slot,LG]
+  // general move entries (a MOVE op with targets in other locales, executor.py:185-200,:213-233; team kernels only)
+  int xmove, n_ent, n_src, n_tgt;
+  int mv_len;                           // floats of a move table per env: n_slot*LG, or n_ent with xmove
+  const int *ent_g, *ent_c1, *ent_c2, *ent_l1, *ent_l2, *ent_mo, *ent_sl;  // [n_ent] in the reference's insertion order
+  const int *src_off, *src_mo, *src_idx, *src_sl;  // source cells: entries [src_off[s], src_off[s+1]), op, c1*LG+cell, slot with that c1
+  const int* mo_src_off;                // [n_mv_op+1] the source cells of an op are contiguous
+  const int *tgt_off, *tgt_ent, *tgt_idx, *tgt_sl;  // target cells: incoming entries in list order, c2*LG+cell, slot whose c1 is c2 (or -1)
   // ADD ops
   int n_add_op;
   const int* add_op;                    // [n_add_op]
@@ -161,7 +168,7 @@ struct DevPlan {
   int64_t o_mult_y, o_mult_d, o_cpv, o_act, o_expr, o_sel, o_mpt0, o_coefS, o_Tnum, o_Tden, o_fi_y, o_fi_gap,
       o_ft_y, o_ft_gap, o_mob_y, o_mob_g, o_mxr, o_mxc;  // small region (bytes)
   int64_t o_X, o_ys, o_K, o_accY, o_accB, o_accE, o_accF, o_accF2, o_flows, o_alive, o_Xw, o_Ag, o_Wg, o_s, o_r,
-      o_mvY, o_mvD, o_cost, o_crY, o_crD, o_ysS, o_KS;   // big region (bytes)
+      o_mvY, o_mvD, o_cost, o_crY, o_crD, o_ysS, o_KS, o_xnv;   // big region (bytes)
   CellLayout cl;
   EnvLayout el;
   GrpLayout gl;

@@ -80,19 +80,45 @@ def test_known_answer_and_fused_week():
 
 
 def test_unsupported_programs_are_refused_not_approximated():
-    """A move whose target locales differ from its source locales (nb_move's cross-locale branches,
-    core/executor.py:185-200,213-233) is outside the compiled op algebra of the CUDA path: epi_create must fail with
-    EPI_E_UNSUPPORTED rather than run something else."""
+    """Moves whose result would depend on the order in which the reference's dictionaries are walked (two moves out of
+    one compartment: the clamp of the second sees what the first left, core_optimize.py:196-208) are outside the
+    compiled op algebra of the CUDA path: epi_create must fail with EPI_E_UNSUPPORTED rather than run something else."""
     from epipolicy_rl_b200 import lib
-    from epipolicy_rl_b200.desc import OP_MOB_MUL, OP_MOVE
-    d, _ = load("COVID_C_border")
+    from epipolicy_rl_b200.desc import OP_MOVE
+    d, _ = load("COVID_C_xmove")
     kind, arg = d.arrays["op_kind"], d.arrays["op_arg"].copy().reshape(-1, 8)
-    mv, mob = int(np.where(kind == OP_MOVE)[0][0]), int(np.where(kind == OP_MOB_MUL)[0][0])
-    arg[mv, 4] = arg[mob, 2]  # target locales := the closure's single 'locale-from' locale; sources stay all locales
+    mv = np.where(kind == OP_MOVE)[0]
+    arg[mv[-1], 0] = arg[mv[-2], 0]  # the hospital transfer now leaves from E as well: (E -> E) and (E -> Hmild)
     d.arrays["op_arg"] = arg.reshape(-1)
     with pytest.raises(lib.EpiError) as ei:
         EmuEngine(d, 1, "fp64")
-    assert ei.value.code == -2
+    assert ei.value.code == -2 and "order-dependent" in str(ei.value)
+
+
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+@pytest.mark.parametrize("knobs", [{}, {"EPI_TEAM": "cta"}], ids=["warp-team", "cta-team"])
+def test_cross_locale_moves_vs_reference(knobs, prec, monkeypatch):
+    """Cross-locale moves (nb_move's other-locale branches, core/executor.py:185-200,:213-233): exposed people leaving the
+    closed locale for the others (clamped on the first days) and mild cases transferred to the other locales' hospitals,
+    against the unmodified reference (tools/gen_xmove_golden.py). Such scenarios run on the team kernels (general move
+    entries: the reference's sequential clamp per source cell)."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    d, z = load("COVID_C_xmove")
+    eng = EmuEngine(d, 2, prec)
+    assert eng.info.team_kind in (0, 1)
+    X, C = z["sched_X"], z["sched_cost"]
+    tol = 1e-9 if prec == "fp64" else 1e-4
+    for day in range(len(X)):
+        cpv = np.repeat(z["sched_plan_cpv"][day][None], 2, 0)
+        act = np.repeat(z["sched_plan_active"][day][None].astype(np.uint8), 2, 0)
+        eng.step_plan(cpv, act, True, 1)
+        for e in range(2):
+            assert x_err(eng.get_state("X")[e], X[day], d) <= tol, (day, e)
+            assert cost_err(eng.get_state("cost")[e], C[day]) <= tol, (day, e)
+        if prec == "fp64":
+            assert int(eng.get_state("trace")[0, 0]) == int(z["sched_nfev"][day])
+    eng.close()
 
 
 @pytest.mark.parametrize("knobs", [{}, {"EPI_TEAM": "warp"}, {"EPI_TEAM": "cta"}], ids=["cell", "warp-team", "cta-team"])

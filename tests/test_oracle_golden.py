@@ -108,3 +108,32 @@ def test_schedule_plan_border_closure_mobility_multipliers():
     # the closure changes the dynamics: the same schedule without it (all other rows equal) ends somewhere else
     zc = load("COVID_C")[1]
     assert x_err(X[59], zc["sched_X"][59], d) > 1e-4
+
+
+def test_schedule_plan_cross_locale_moves():
+    """Cross-locale moves (nb_move's other-locale branches, core/executor.py:185-200,:213-233; sequential clamp per source
+    cell, core_optimize.py:196-208), which no shipped intervention uses: COVID_C with two such moves appended to the
+    Border_Closures effect and the schedule on one locale, through the unmodified reference (tools/gen_xmove_golden.py).
+    The move tables of the first ten days (same entries and float32 amounts; the reference lists them group by group,
+    the oracle in insertion order), the 60-day trajectory and costs, the RK45 step sequence."""
+    d, z = load("COVID_C_xmove")
+    o = Oracle(d)
+    X, C = z["sched_X"], z["sched_cost"]
+    nfev, clamped = [], 0
+    for day in range(len(X)):
+        o.day_step(z["sched_plan_cpv"][day], z["sched_plan_active"][day], init_programs=True)
+        assert x_err(o.X, X[day], d) <= 1e-11
+        assert cost_err(o.cost, C[day]) <= 1e-11
+        if day < 10:
+            mine, ref = o.params(0)["moves"], z[f"sched_p_moves{day}"].reshape(-1, 6)
+            key = lambda m: m[np.lexsort(m[:, :5].T[::-1])]  # noqa: E731
+            assert np.array_equal(key(mine), key(ref)), day
+            if len(ref):
+                cross = ref[ref[:, 3] != ref[:, 4]]
+                assert len(cross) > 0
+                E0 = X[day - 1].reshape(d.C, d.L, d.G)[1, 0] if day else None  # exposed in the closed locale, yesterday
+                if E0 is not None:
+                    clamped += int(np.any(cross[cross[:, 1] == 1][:, 5].reshape(d.G, -1).sum(1) > E0))
+        nfev.append(o.trace["nfev"])
+    assert np.array_equal(np.array(nfev), z["sched_nfev"])
+    assert clamped > 0  # on the first days more exposed people are asked to leave than there are: the clamp binds

@@ -1,0 +1,33 @@
+"""Cross-locale moves on the device (sorted last: this path was finished after the round's GPU budget was spent and has
+been run on the host emulation only - tests/test_emu_parity.py::test_cross_locale_moves_vs_reference)."""
+import numpy as np
+import pytest
+
+from helpers import cost_err, load, x_err
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+def test_cross_locale_moves_vs_reference_on_device(prec):
+    """nb_move's other-locale branches (core/executor.py:185-200,:213-233) through the C-ABI on the GPU (team kernel,
+    general move entries) against the unmodified reference's trajectory (tools/gen_xmove_golden.py)."""
+    from epipolicy_rl_b200.engine import BatchedEpidemic
+    d, z = load("COVID_C_xmove")
+    n = 5
+    eng = BatchedEpidemic(d, n, device=0, precision=prec)
+    assert eng.info.team_kind in (0, 1)
+    X, C = z["sched_X"], z["sched_cost"]
+    tol = 1e-9 if prec == "fp64" else 1e-4
+    for day in range(len(X)):
+        cpv = torch.from_numpy(np.repeat(z["sched_plan_cpv"][day][None], n, 0)).cuda()
+        act = torch.from_numpy(np.repeat(z["sched_plan_active"][day][None].astype(np.uint8), n, 0)).cuda()
+        eng.step_plan(cpv, act, True, 1)
+        x, c = eng.get_state("X"), eng.get_state("cost")
+        for e in range(n):
+            assert x_err(x[e], X[day], d) <= tol, (day, e)
+            assert cost_err(c[e], C[day]) <= tol, (day, e)
+        if prec == "fp64":
+            assert (eng.get_state("trace")[:, 0] == int(z["sched_nfev"][day])).all()
+    eng.close()
