@@ -73,3 +73,33 @@ def test_random_border_closures_vs_oracle(prec, spec):
     print(f"border random {prec} spec={spec}: X {worst:.2e} cost {worst_c:.2e}")
     assert worst <= TOL[prec] and worst_c <= TOL[prec]
     eng.close()
+
+
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+def test_random_cross_locale_moves_vs_oracle(prec):
+    """cross-locale moves on fresh inputs: four envs follow different what-if schedules of the xmove scenario (random
+    closure degrees, i.e. random amounts asked to leave / to be transferred, redrawn on some days), day by day against
+    the oracle; vaccination switched on from day 5 so that same-locale and cross-locale entries are live together"""
+    d, z = load("COVID_C_xmove")
+    n, T = 4, 20
+    rng = np.random.default_rng(23)
+    cpv = np.repeat(z["sched_plan_cpv"][:T, None, :], n, 1).astype(np.float32)
+    act = np.repeat(z["sched_plan_active"][:T, None, :], n, 1).astype(np.uint8)
+    act[5:, :, 0] = 1  # Vaccination has an Act
+    free = np.where(d.cp_min != d.cp_max)[0]
+    for e in range(n):
+        for t in range(T):
+            if t == 0 or rng.uniform() < 0.4:
+                cpv[t:, e, free] = rng.uniform(d.cp_min[free], d.cp_max[free]).astype(np.float32)
+    eng = EmuEngine(d, n, prec)
+    oracles = [Oracle(d) for _ in range(n)]
+    worst = worst_c = 0.0
+    for t in range(T):
+        eng.step_plan(cpv[t], act[t], True, 1)
+        for e, o in enumerate(oracles):
+            o.day_step(cpv[t, e], act[t, e], init_programs=True)
+            worst = max(worst, x_err(eng.get_state("X")[e], o.X, d))
+            worst_c = max(worst_c, cost_err(eng.get_state("cost")[e], o.cost))
+    print(f"xmove random {prec}: X {worst:.2e} cost {worst_c:.2e}")
+    assert worst <= TOL[prec] and worst_c <= TOL[prec]
+    eng.close()
