@@ -1665,6 +1665,7 @@ int epi_info(const epi_t* h, EpiInfo* o) {
   o->specialized = h->spec_launch ? 1 : 0; o->reserved = h->cta_mode == 4 ? P.gl.S : 0;  // CTAs per env group
   o->small_bytes = P.small_bytes; o->big_bytes = P.big_bytes; o->scratch_bytes = (int64_t)h->scratch_bytes;
   int64_t rs = (int64_t)h->real_size();
+  o->mv_len = P.mv_len;
   o->state_bytes_per_env = 8 * (P.CLG + (int64_t)P.n_chg * P.LG) + rs * (int64_t)P.n_acc * P.LG + 16 * (int64_t)P.I * P.L +
                            4 * ((int64_t)P.mv_len + P.n_cls) + 32 + 8;
   return EPI_OK;

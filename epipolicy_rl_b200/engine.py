@@ -234,7 +234,8 @@ class BatchedEpidemic:
             "X": (0, (N, d.C, d.L, d.G), np.float64), "cost": (1, (N, d.I, d.L), np.float64),
             "day": (2, (N,), np.int32), "flat": (3, (N, d.n_flat), np.float64), "trace": (4, (N, 4), np.int32),
             "last_err": (5, (N,), np.float64), "cost_rate": (6, (N, d.I, d.L), np.float64),
-            "mult": (7, (N, self.info.n_cls), np.float32), "moves": (8, (N, self.info.n_slot, d.L, d.G), np.float32),
+            "mult": (7, (N, self.info.n_cls), np.float32), "moves": (8, (N, self.info.n_slot, d.L, d.G) if self.info.mv_len == self.info.n_slot * d.L * d.G
+                                                                          else (N, self.info.mv_len), np.float32),
             "attempts": (9, (N, 64, 2), np.float64),
         }[what]
         out = np.empty(spec[1], spec[2])

@@ -21,7 +21,7 @@ class EpiInfo(ctypes.Structure):
         "n_envs", "precision", "device", "obs_dim", "action_dim", "ncp", "n_itv", "horizon", "n_flat", "n_acc",
         "n_slot", "n_lc", "n_groups_inf", "n_cls", "team_kind", "threads", "grid", "envs_per_cta", "specialized",
         "reserved")] + [
-        (n, ctypes.c_int64) for n in ("smem_bytes", "small_bytes", "big_bytes", "scratch_bytes", "state_bytes_per_env")]
+        (n, ctypes.c_int64) for n in ("smem_bytes", "small_bytes", "big_bytes", "scratch_bytes", "state_bytes_per_env", "mv_len")]
 
 
 class EpiRunOut(ctypes.Structure):

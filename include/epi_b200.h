@@ -41,6 +41,8 @@ typedef struct EpiInfo {
   int32_t specialized; /* 1 once a scenario-specialised build of the cell kernel is attached */
   int32_t reserved;
   int64_t smem_bytes, small_bytes, big_bytes, scratch_bytes, state_bytes_per_env;
+  int64_t mv_len;      /* floats of a move table per env (state selector 8): n_slot*L*G, or the number of general move
+                          entries when the scenario has cross-locale moves */
 } EpiInfo;
 
 /* Epidemic.__init__ + make_setting (core/epidemic.py:36-80) for n_envs independent instances of one
@@ -114,7 +116,7 @@ int epi_host_buffers(epi_t* h, float** actions, void** obs, double** reward, uin
  *   2 day counter [n_envs] int32        3 reference-layout flat observable [n_envs, n_flat] double (get only)
  *   4 trace [n_envs, 4] int32: nfev, accepted steps, rejected steps, status of the last simulated day
  *   5 last error norm [n_envs] double   6 yesterday's cost rate [n_envs, I*L] double
- *   7 yesterday's class multipliers [n_envs, n_cls] float    8 yesterday's move table [n_envs, n_slot*L*G] float
+ *   7 yesterday's class multipliers [n_envs, n_cls] float    8 yesterday's move table [n_envs, mv_len] float
  *   9 (h, error_norm) of each attempted RK45 step of the last day [n_envs, 64, 2] double (get only; recording
  *     starts with the first query)
  * Host buffers; sizes are checked. */
