@@ -103,3 +103,48 @@ def test_random_cross_locale_moves_vs_oracle(prec):
     print(f"xmove random {prec}: X {worst:.2e} cost {worst_c:.2e}")
     assert worst <= TOL[prec] and worst_c <= TOL[prec]
     eng.close()
+
+
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+def test_mobility_multipliers_on_a_large_scenario_vs_oracle(prec):
+    """L*G > 32 with mobility multipliers: such scenarios are routed to the CTA-team kernel (the env / env-group kernels
+    keep static mobility tables). syn_s (20 locales x 4 groups) with one of its parameter multipliers re-targeted at
+    the border-mode mobility from locales 0-4 to locales 5-19 (a partial selection, so the row renormalisation does
+    not cancel it), random weekly actions against the oracle (which is pinned on mobility multipliers by the border
+    golden)."""
+    from epipolicy_rl_b200.desc import OP_MOB_MUL, OP_PARAM_MUL
+    d, _ = load("syn_s")
+    a = d.arrays
+    off, data = list(a["list_off"]), list(a["list_data"])
+    ids = []
+    for lst in (list(range(0, 5)), list(range(5, d.L))):
+        data += lst
+        off.append(len(data))
+        ids.append(len(off) - 2)
+    a["list_off"], a["list_data"] = np.array(off, np.int32), np.array(data, np.int32)
+    kind, arg = a["op_kind"].copy(), a["op_arg"].copy().reshape(-1, 8)
+    o = int(np.where(kind == OP_PARAM_MUL)[0][-1])
+    g_list = int(arg[o, 3])
+    kind[o] = OP_MOB_MUL
+    arg[o] = [1, g_list, ids[0], ids[1], -1, -1, -1, -1]  # mode 1 = border (utility/singleton.py:10)
+    a["op_kind"], a["op_arg"] = kind, arg.reshape(-1)
+    d.finalize()  # the list pool grew: refresh the descriptor's sizes
+    n, weeks = 2, 2
+    rng = np.random.default_rng(31)
+    acts = rng.uniform(0, 1, (weeks, n, d.A)).astype(np.float32)
+    eng = EmuEngine(d, n, prec)
+    assert eng.info.team_kind in (0, 1)
+    oracles = [Oracle(d) for _ in range(n)]
+    plain = Oracle(load("syn_s")[0])
+    worst = worst_c = 0.0
+    for w in range(weeks):
+        obs, rew, _ = eng.step(acts[w], 7)
+        p_obs, _, _ = plain.step(acts[w, 0], 7)
+        for e, o_ in enumerate(oracles):
+            o_obs, o_rew, _ = o_.step(acts[w, e], 7)
+            worst = max(worst, x_err(obs[e], o_obs, d))
+            worst_c = max(worst_c, cost_err(eng.get_state("cost")[e], o_.cost))
+    assert x_err(obs[0], p_obs, d) > 1e-6  # the closure changes the trajectory
+    print(f"syn_s + mobility multiplier {prec}: X {worst:.2e} cost {worst_c:.2e}")
+    assert worst <= TOL[prec] and worst_c <= TOL[prec]
+    eng.close()
