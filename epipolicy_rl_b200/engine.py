@@ -151,7 +151,7 @@ class BatchedEpidemic:
         return t
 
     def run(self, cpv: torch.Tensor, active: torch.Tensor | None = None, record_obs: bool = True,
-            schedule_programs: bool = True, report: bool = False):
+            schedule_programs: bool = True, report: bool = False, one_launch: bool = True):
         """Epidemic.run (core/epidemic.py:118-134) for a batch of what-if schedules: reset, then the whole schedule in
         ONE launch (epi_run_plan) with day t's Acts taken from row t. cpv: [T, N, NCP] (or [T, NCP], broadcast to all envs) full
         control-parameter vectors; active: [T, N, I] / [T, I] flags of the interventions that have an Act on
@@ -172,6 +172,8 @@ class BatchedEpidemic:
         if c.shape[1] != self.n_envs or (a is not None and a.shape[:2] != c.shape[:2]):
             raise ValueError("schedule must be [T, N, NCP] / [T, NCP] with matching active flags")
         self.reset()
+        if not one_launch:
+            return self._run_daily(c, a, T, record_obs, schedule_programs, report)
         # ONE launch for the whole schedule (epi_run_plan): day d of the launch reads row d of the schedule and emits the
         # day's end state and reward - and, for the reporter, the state in double, the live cumulative components and
         # the class multipliers; no per-day launch, no per-day copies
@@ -198,6 +200,30 @@ class BatchedEpidemic:
         if rep is not None:
             for t in range(T):
                 rep.record(x_days[t], acc_days[t], mult_days[t])
+            out["report"] = rep.compute()
+        if record_obs:
+            out["obs"] = obs
+        return out
+
+    def _run_daily(self, c, a, T, record_obs, schedule_programs, report):
+        """run(one_launch=False): one epi_step_plan launch per simulated day, results and the reporter's inputs copied
+        between the launches (stream-ordered device copies) - the round-1 path, kept as the A/B of epi_run_plan"""
+        rep = None
+        if report:
+            from .reporter_device import DeviceReporter
+            rep = DeviceReporter(self.desc, self.plan_tables(), self.device)
+            rep.record(self.state_dev("X"), self.state_dev("acc"), self.state_dev("mult"))
+        rew = torch.empty((T, self.n_envs), dtype=torch.float64, device=self.device)
+        obs = torch.empty((T, self.n_envs, self.obs_dim), dtype=self.dtype, device=self.device) if record_obs else None
+        for t in range(T):
+            o, r, _ = self.step_plan(c[t], None if a is None else a[t], schedule_programs, 1)
+            rew[t].copy_(r)
+            if record_obs:
+                obs[t].copy_(o)
+            if rep is not None:
+                rep.record(self.state_dev("X"), self.state_dev("acc"), self.state_dev("mult"))
+        out = {"reward": rew, "done": self.done}
+        if rep is not None:
             out["report"] = rep.compute()
         if record_obs:
             out["obs"] = obs

@@ -313,6 +313,11 @@ def test_product_host_class_run_on_the_emulation():
     rel = lambda a, b, floor: float(np.max(np.abs(a - b) / (np.abs(b) + floor)))  # noqa: E731
     for key, floor in (("location_instant_R", 1e-9), ("location_basic_R", 1e-9), ("location_case_R", 1e-9)):
         assert rel(out["report"][key][:, 0].numpy(), g[key], floor) <= 1e-9, key
+    # the day-by-day path (one epi_step_plan launch per day) gives the same, bit for bit
+    daily = eng.run(cpv, act, report=True, one_launch=False)
+    assert torch.equal(daily["obs"], out["obs"]) and torch.equal(daily["reward"], out["reward"])
+    for key in ("location_instant_R", "location_basic_R", "location_case_R", "incidences"):
+        assert torch.equal(daily["report"][key], out["report"][key]), key
     # the [T, NCP] form (one schedule for every env) and no recorded observations
     out2 = eng.run(torch.from_numpy(z["sched_plan_cpv"][:T]), act, record_obs=False)
     assert "obs" not in out2 and torch.equal(out2["reward"][:, 1], out["reward"][:, 0])

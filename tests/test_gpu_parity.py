@@ -105,9 +105,7 @@ def test_run_batch_of_schedules():
     cpv = torch.from_numpy(z["sched_plan_cpv"][:T]).float()[:, None, :].repeat(1, 2, 1)
     cpv[:, 1, 0], cpv[:, 1, 3] = 0.7, 0.5
     act = torch.from_numpy(z["sched_plan_active"][:T].astype(np.uint8))
-    n0 = eng.launches
-    out = eng.run(cpv, act)
-    assert eng.launches - n0 <= 2, "the schedule must run in one step launch (+ the reset)"
+    out = eng.run(cpv, act, one_launch=False)  # (the one-launch path: tests/test_zz_gpu_run_plan.py)
     obs = out["obs"].cpu().numpy()
     assert obs.shape == (T, 2, d.C * d.L * d.G) and out["reward"].shape == (T, 2)
     for day in (0, 17, T - 1):
@@ -115,31 +113,6 @@ def test_run_batch_of_schedules():
     assert np.allclose(out["reward"][:, 0].cpu().numpy(), z["sched_rewards"][:T], rtol=1e-9)
     assert x_err(obs[T - 1, 1], z["sched_X"][T - 1], d) > 1e-6
     eng.close()
-
-
-@pytest.mark.parametrize("name", ["COVID_C", "COVID_C_border"])
-def test_run_whole_schedule_in_one_launch_vs_reference(name):
-    """epi_run_plan on the device: the scenario's own schedule over its whole golden length for a batch of 48 envs in ONE
-    launch - every day's state and reward of every env against the unmodified reference's trajectory (fp64), and the
-    same through one launch per day, bit for bit."""
-    d, z = load(name)
-    T, n = len(z["sched_X"]), 48
-    cpv = torch.from_numpy(z["sched_plan_cpv"][:T]).float()
-    act = torch.from_numpy(z["sched_plan_active"][:T].astype(np.uint8))
-    eng, daily = _engine(d, n, "fp64"), _engine(d, n, "fp64")
-    n0 = eng.launches
-    out = eng.run(cpv, act)
-    assert eng.launches - n0 <= 2
-    obs, rew = out["obs"].cpu().numpy(), out["reward"].cpu().numpy()
-    for day in range(T):
-        assert x_err(obs[day], np.broadcast_to(z["sched_X"][day].reshape(1, -1), (n, d.C * d.L * d.G)), d) <= 1e-9, day
-    assert np.allclose(rew, z["sched_rewards"][:T, None], rtol=1e-9)
-    daily.reset()
-    for day in range(T):
-        o, r, _ = daily.step_plan(cpv[day][None].expand(n, -1), act[day][None].expand(n, -1), True, 1)
-        assert torch.equal(o, out["obs"][day]) and torch.equal(r, out["reward"][day]), day
-    assert bool(out["done"].all()) == (T >= d.horizon)
-    eng.close(); daily.close()
 
 
 def test_known_answer_user_ipynb():
