@@ -148,3 +148,59 @@ def test_mobility_multipliers_on_a_large_scenario_vs_oracle(prec):
     print(f"syn_s + mobility multiplier {prec}: X {worst:.2e} cost {worst_c:.2e}")
     assert worst <= TOL[prec] and worst_c <= TOL[prec]
     eng.close()
+
+
+def _restrict_ops_to_locales(d):
+    """interventions restricted to SOME locales (the `locales` regex of a schedule entry, core/executor.py:111-114):
+    the first parameter multiplier acts on locale 0 only, the second on locales {1, 2}, the first facility-interaction
+    multiplier on {1, 2}, the second on locale 0 - the locales then fall into several LOCALE CLASSES (epi_plan.h), which
+    no shipped scenario does"""
+    from epipolicy_rl_b200.desc import OP_FI_MUL, OP_PARAM_MUL
+    a = d.arrays
+    off, data = list(a["list_off"]), list(a["list_data"])
+    ids = []
+    for lst in ([0], [1, 2]):
+        data += lst
+        off.append(len(data))
+        ids.append(len(off) - 2)
+    kind, arg = a["op_kind"], a["op_arg"].copy().reshape(-1, 8)
+    pm, fi = np.where(kind == OP_PARAM_MUL)[0], np.where(kind == OP_FI_MUL)[0]
+    arg[pm[0], 1] = ids[0]
+    if len(pm) > 1:
+        arg[pm[1], 1] = ids[1]
+    if len(fi) > 0:
+        arg[fi[0], 0] = ids[1]
+    if len(fi) > 1:
+        arg[fi[1], 0] = ids[0]
+    a["list_off"], a["list_data"], a["op_arg"] = np.array(off, np.int32), np.array(data, np.int32), arg.reshape(-1)
+    return d.finalize()
+
+
+@pytest.mark.parametrize("name,prec,spec,knobs", [
+    ("COVID_C", "fp64", False, {}), ("COVID_C", "fp64", True, {}), ("COVID_C", "fp32", True, {}),
+    ("COVID_C", "fp64", False, {"EPI_TEAM": "warp"}), ("syn_s", "fp64", True, {"EPI_GRP": "0"}),
+    ("syn_s", "fp32", True, {"EPI_GRP": "2", "EPI_GRP_S": "2"})],
+    ids=["cell-interpreted", "cell-specialised", "cell-specialised-fp32", "warp-team", "env-specialised", "env-group-fp32"])
+def test_locale_restricted_interventions_vs_oracle(name, prec, spec, knobs, monkeypatch):
+    """several locale classes (interventions that act on some locales only) through every kernel family, random weekly
+    actions against the oracle"""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    d = _restrict_ops_to_locales(load(name)[0])
+    n, weeks = 3, 3
+    acts = np.random.default_rng(5).uniform(0, 1, (weeks, n, d.A)).astype(np.float32)
+    eng = EmuEngine(d, n, prec)
+    if spec:
+        eng.attach_spec()
+    assert eng.info.n_lc > 1
+    oracles = [Oracle(d) for _ in range(n)]
+    worst = worst_c = 0.0
+    for w in range(weeks):
+        obs, _, _ = eng.step(acts[w], 7)
+        for e, o in enumerate(oracles):
+            o_obs, _, _ = o.step(acts[w, e], 7)
+            worst = max(worst, x_err(obs[e], o_obs, d))
+            worst_c = max(worst_c, cost_err(eng.get_state("cost")[e], o.cost))
+    print(f"{name} {prec} n_lc={eng.info.n_lc} kind={eng.info.team_kind}: X {worst:.2e} cost {worst_c:.2e}")
+    assert worst <= TOL[prec] and worst_c <= TOL[prec]
+    eng.close()
