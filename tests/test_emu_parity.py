@@ -322,3 +322,29 @@ def test_product_host_class_run_on_the_emulation():
     out2 = eng.run(torch.from_numpy(z["sched_plan_cpv"][:T]), act, record_obs=False)
     assert "obs" not in out2 and torch.equal(out2["reward"][:, 1], out["reward"][:, 0])
     eng.close()
+
+
+@pytest.mark.parametrize("prec,spec,knobs", [("fp64", False, {}), ("fp64", True, {}), ("fp32", True, {}),
+                                             ("fp64", False, {"EPI_TEAM": "warp"}), ("fp64", False, {"EPI_TEAM": "env"})],
+                         ids=["cell-interpreted", "cell-specialised", "cell-specialised-fp32", "warp-team", "env"])
+def test_facility_timespent_multiplier_vs_reference(prec, spec, knobs, monkeypatch):
+    """sim.apply({'facility', 'locale'}, m) (facility-timespent multiplier: the force-of-infection denominator tables
+    then depend on the env, `has_ft_ops`) and a value-mode 'default' select, against the unmodified reference
+    (tools/gen_ft_golden.py): 16 weekly random actions, day by day"""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    d, z = load("COVID_C_ft")
+    eng = EmuEngine(d, 1, prec)
+    if spec:
+        eng.attach_spec()
+    tol = 1e-9 if prec == "fp64" else 1e-4
+    day = 0
+    for a in z["rnd_actions"]:
+        for _ in range(7):
+            eng.step(a[None], 1)
+            assert x_err(eng.get_state("X"), z["rnd_X"][day], d) <= tol, day
+            assert cost_err(eng.get_state("cost"), z["rnd_cost"][day]) <= tol, day
+            if prec == "fp64":
+                assert int(eng.get_state("trace")[0, 0]) == int(z["rnd_nfev"][day])
+            day += 1
+    eng.close()

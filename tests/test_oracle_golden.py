@@ -137,3 +137,34 @@ def test_schedule_plan_cross_locale_moves():
         nfev.append(o.trace["nfev"])
     assert np.array_equal(np.array(nfev), z["sched_nfev"])
     assert clamped > 0  # on the first days more exposed people are asked to leave than there are: the clamp binds
+
+
+def test_facility_timespent_multiplier_and_default_mode_select():
+    """Two intervention-code shapes no shipped JSON uses: sim.apply({'facility', 'locale'}, m) - the facility-timespent
+    multiplier of nb_apply's last branch (core/executor.py:156-162), renormalised over the facilities
+    (matrix/dense.py:6-19) - and a select with value-mode 'default' (core/executor.py:300-303). COVID_C with School
+    closure rewritten in that form, through the unmodified reference (tools/gen_ft_golden.py): weekly random actions
+    through EpiEnv.step and the schedule through Epidemic.step; float32 tables of the first ten days bit-exact."""
+    d, z = load("COVID_C_ft")
+    assert list(d.op_kind).count(3) == 1 and 1 in set(np.asarray(d.arrays["sel_arg"]).reshape(-1, 4)[:, 3])
+    o = Oracle(d)
+    p = o.params(1)
+    for k in ("mp", "ft", "fi", "mob"):
+        assert np.array_equal(p[k], z[f"init_{k}"].reshape(p[k].shape)), k
+    X, C = z["rnd_X"], z["rnd_cost"]
+    day, nfev = 0, []
+    for a in z["rnd_actions"]:
+        for _ in range(7):
+            o.step(a, 1)
+            assert x_err(o.X, X[day], d) <= 1e-11 and cost_err(o.cost, C[day]) <= 1e-11, day
+            if day < 10:
+                p = o.params(0)
+                for k in ("mp", "ft", "fi"):
+                    assert np.array_equal(p[k], z[f"rnd_p_{k}"][day].reshape(p[k].shape)), (day, k)
+            nfev.append(o.trace["nfev"])
+            day += 1
+    assert np.array_equal(np.array(nfev), z["rnd_nfev"])
+    o = Oracle(d)
+    for day in range(len(z["sched_X"])):
+        o.day_step(z["sched_plan_cpv"][day], z["sched_plan_active"][day], init_programs=True)
+        assert x_err(o.X, z["sched_X"][day], d) <= 1e-11 and cost_err(o.cost, z["sched_cost"][day]) <= 1e-11, day

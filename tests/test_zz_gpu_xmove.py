@@ -1,4 +1,4 @@
-"""Cross-locale moves on the device (sorted last: this path was finished after the round's GPU budget was spent and has
+"""Cross-locale moves and facility-timespent multipliers on the device (sorted last: this path was finished after the round's GPU budget was spent and has
 been run on the host emulation only - tests/test_emu_parity.py::test_cross_locale_moves_vs_reference)."""
 import numpy as np
 import pytest
@@ -30,4 +30,22 @@ def test_cross_locale_moves_vs_reference_on_device(prec):
             assert cost_err(c[e], C[day]) <= tol, (day, e)
         if prec == "fp64":
             assert (eng.get_state("trace")[:, 0] == int(z["sched_nfev"][day])).all()
+    eng.close()
+
+
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+def test_facility_timespent_multiplier_vs_reference_on_device(prec):
+    """sim.apply({'facility', 'locale'}, m) and a value-mode 'default' select (tools/gen_ft_golden.py) on the GPU: the
+    fused week of 3 envs of one warp against the unmodified reference's weekly observations and rewards"""
+    from epipolicy_rl_b200.engine import BatchedEpidemic
+    d, z = load("COVID_C_ft")
+    n = 3
+    eng = BatchedEpidemic(d, n, device=0, precision=prec)
+    tol = 1e-9 if prec == "fp64" else 1e-4
+    for w, a in enumerate(z["rnd_actions"]):
+        obs, rew, _ = eng.step(torch.from_numpy(np.repeat(a[None], n, 0)).cuda(), 7)
+        o = obs.double().cpu().numpy()
+        for e in range(n):
+            assert x_err(o[e], z["rnd_obs_weekly"][w], d) <= tol, (w, e)
+            assert abs(float(rew[e]) - z["rnd_rewards"][w]) <= tol * abs(z["rnd_rewards"][w]), (w, e)
     eng.close()
