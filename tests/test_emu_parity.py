@@ -348,3 +348,30 @@ def test_facility_timespent_multiplier_vs_reference(prec, spec, knobs, monkeypat
                 assert int(eng.get_state("trace")[0, 0]) == int(z["rnd_nfev"][day])
             day += 1
     eng.close()
+
+
+@pytest.mark.parametrize("prec,spec,knobs", [("fp64", False, {}), ("fp64", True, {}), ("fp32", True, {}),
+                                             ("fp64", False, {"EPI_TEAM": "warp"}), ("fp64", False, {"EPI_TEAM": "env"})],
+                         ids=["cell-interpreted", "cell-specialised", "cell-specialised-fp32", "warp-team", "env"])
+def test_non_conserving_model_vs_reference(prec, spec, knobs, monkeypatch):
+    """births and deaths (gain / lost maps, obj/edge.py:76-111; cumulative_gain / cumulative_lost in the flat state and in
+    the error norm) against the unmodified reference (tools/gen_vital_golden.py), incl. the flat observable at the end"""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    d, z = load("SIRV_B_vital")
+    eng = EmuEngine(d, 2, prec)
+    if spec:
+        eng.attach_spec()
+    tol = 1e-9 if prec == "fp64" else 1e-4
+    day = 0
+    for a in z["rnd_actions"]:
+        for _ in range(7):
+            eng.step(np.repeat(a[None], 2, 0), 1)
+            assert x_err(eng.get_state("X")[1], z["rnd_X"][day], d) <= tol, day
+            assert cost_err(eng.get_state("cost")[1], z["rnd_cost"][day]) <= tol, day
+            if prec == "fp64":
+                assert int(eng.get_state("trace")[0, 0]) == int(z["rnd_nfev"][day])
+            day += 1
+    ref = z["rnd_flat_last"]
+    assert np.max(np.abs(eng.get_state("flat")[0] - ref) / (np.abs(ref) + 1e-3)) <= tol
+    eng.close()

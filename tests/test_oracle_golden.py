@@ -168,3 +168,24 @@ def test_facility_timespent_multiplier_and_default_mode_select():
     for day in range(len(z["sched_X"])):
         o.day_step(z["sched_plan_cpv"][day], z["sched_plan_active"][day], init_programs=True)
         assert x_err(o.X, z["sched_X"][day], d) <= 1e-11 and cost_err(o.cost, z["sched_cost"][day]) <= 1e-11, day
+
+
+def test_non_conserving_model_gain_and_lost_maps():
+    """Equation terms without a counterpart (births into S, deaths out of R) become gain / lost entries of their edges
+    (obj/edge.py:76-111) and feed cumulative_gain / cumulative_lost (core_optimize.py:171-195), which sit in the flat
+    ODE state and in the RK45 error norm; every shipped model conserves mass. SIRV_B with vital dynamics through the
+    unmodified reference (tools/gen_vital_golden.py): 140 days of weekly random actions, the flat observable at the end."""
+    d, z = load("SIRV_B_vital")
+    assert {1, 2} <= set(int(k) for k in d.arrays["sc_kind"])  # EPI_SC_GAIN, EPI_SC_LOST
+    o = Oracle(d)
+    day, nfev = 0, []
+    for a in z["rnd_actions"]:
+        for _ in range(7):
+            o.step(a, 1)
+            assert x_err(o.X, z["rnd_X"][day], d) <= 1e-11 and cost_err(o.cost, z["rnd_cost"][day]) <= 1e-11, day
+            nfev.append(o.trace["nfev"])
+            day += 1
+    assert np.array_equal(np.array(nfev), z["rnd_nfev"])
+    ref = z["rnd_flat_last"]
+    assert np.max(np.abs(o.flat() - ref) / (np.abs(ref) + 1e-3)) <= 1e-11
+    assert z["rnd_X"][-1].sum() > 1.5 * z["rnd_X"][0].sum()  # the population grows: mass is not conserved

@@ -49,3 +49,23 @@ def test_facility_timespent_multiplier_vs_reference_on_device(prec):
             assert x_err(o[e], z["rnd_obs_weekly"][w], d) <= tol, (w, e)
             assert abs(float(rew[e]) - z["rnd_rewards"][w]) <= tol * abs(z["rnd_rewards"][w]), (w, e)
     eng.close()
+
+
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+def test_non_conserving_model_vs_reference_on_device(prec):
+    """births and deaths (gain / lost maps; tools/gen_vital_golden.py) on the GPU: fused weeks of a full warp of envs
+    against the unmodified reference's weekly observations, rewards and the flat observable at the end"""
+    from epipolicy_rl_b200.engine import BatchedEpidemic
+    d, z = load("SIRV_B_vital")
+    n = 10
+    eng = BatchedEpidemic(d, n, device=0, precision=prec)
+    tol = 1e-9 if prec == "fp64" else 1e-4
+    for w, a in enumerate(z["rnd_actions"]):
+        obs, rew, _ = eng.step(torch.from_numpy(np.repeat(a[None], n, 0)).cuda(), 7)
+        o = obs.double().cpu().numpy()
+        for e in (0, n - 1):
+            assert x_err(o[e], z["rnd_obs_weekly"][w], d) <= tol, (w, e)
+            assert abs(float(rew[e]) - z["rnd_rewards"][w]) <= tol * abs(z["rnd_rewards"][w]), (w, e)
+    ref = z["rnd_flat_last"]
+    assert np.max(np.abs(eng.get_state("flat")[n - 1] - ref) / (np.abs(ref) + 1e-3)) <= tol
+    eng.close()
