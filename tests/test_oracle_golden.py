@@ -187,5 +187,5 @@ def test_non_conserving_model_gain_and_lost_maps():
             day += 1
     assert np.array_equal(np.array(nfev), z["rnd_nfev"])
     ref = z["rnd_flat_last"]
-    assert np.max(np.abs(o.flat() - ref) / (np.abs(ref) + 1e-3)) <= 1e-11
+    assert np.max(np.abs(o.flat - ref) / (np.abs(ref) + 1e-3)) <= 1e-11
     assert z["rnd_X"][-1].sum() > 1.5 * z["rnd_X"][0].sum()  # the population grows: mass is not conserved
