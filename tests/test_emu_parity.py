@@ -375,3 +375,22 @@ def test_non_conserving_model_vs_reference(prec, spec, knobs, monkeypatch):
     ref = z["rnd_flat_last"]
     assert np.max(np.abs(eng.get_state("flat")[0] - ref) / (np.abs(ref) + 1e-3)) <= tol
     eng.close()
+
+
+@pytest.mark.parametrize("prec,spec", [("fp64", False), ("fp64", True), ("fp32", True)],
+                         ids=["cell-interpreted", "cell-specialised", "cell-specialised-fp32"])
+def test_facility_interaction_multipliers_above_one_vs_reference(prec, spec):
+    """facility-interaction rows pushed above a sum of one by their multipliers are rescaled (matrix/dense.py:21-32):
+    against the unmodified reference (tools/gen_finorm_golden.py)"""
+    d, z = load("COVID_C_finorm")
+    eng = EmuEngine(d, 1, prec)
+    if spec:
+        eng.attach_spec()
+    tol = 1e-9 if prec == "fp64" else 1e-4
+    for day in range(len(z["sched_X"])):
+        eng.step_plan(z["sched_plan_cpv"][day][None], z["sched_plan_active"][day][None].astype(np.uint8), True, 1)
+        assert x_err(eng.get_state("X"), z["sched_X"][day], d) <= tol, day
+        assert cost_err(eng.get_state("cost"), z["sched_cost"][day]) <= tol, day
+        if prec == "fp64":
+            assert int(eng.get_state("trace")[0, 0]) == int(z["sched_nfev"][day])
+    eng.close()

@@ -189,3 +189,23 @@ def test_non_conserving_model_gain_and_lost_maps():
     ref = z["rnd_flat_last"]
     assert np.max(np.abs(o.flat - ref) / (np.abs(ref) + 1e-3)) <= 1e-11
     assert z["rnd_X"][-1].sum() > 1.5 * z["rnd_X"][0].sum()  # the population grows: mass is not conserved
+
+
+def test_facility_interaction_rows_renormalised_under_multipliers_above_one():
+    """get_normalized_facility_interaction (matrix/dense.py:21-32) rescales a row only when its sum is > 1 or < 0; with the
+    shipped schedules (multipliers <= 1) only the default rows reach that branch. COVID_C with negative closure
+    percentages (multipliers 1.6 / 1.3, other values from day 20) through the unmodified reference
+    (tools/gen_finorm_golden.py): the float32 tables of the first ten days bit-exact, 45 days of trajectory and costs."""
+    d, z = load("COVID_C_finorm")
+    o = Oracle(d)
+    nfev = []
+    for day in range(len(z["sched_X"])):
+        o.day_step(z["sched_plan_cpv"][day], z["sched_plan_active"][day], init_programs=True)
+        assert x_err(o.X, z["sched_X"][day], d) <= 1e-11 and cost_err(o.cost, z["sched_cost"][day]) <= 1e-11, day
+        if day < 10:
+            p = o.params(0)
+            for k in ("mp", "ft", "fi", "mob"):
+                assert np.array_equal(p[k], z[f"sched_p_{k}"][day].reshape(p[k].shape)), (day, k)
+        nfev.append(o.trace["nfev"])
+    assert np.array_equal(np.array(nfev), z["sched_nfev"])
+    assert float(z["sched_plan_cpv"][0].min()) < 0  # the multipliers 1 - percentage are above one
