@@ -394,3 +394,27 @@ def test_facility_interaction_multipliers_above_one_vs_reference(prec, spec):
         if prec == "fp64":
             assert int(eng.get_state("trace")[0, 0]) == int(z["sched_nfev"][day])
     eng.close()
+
+
+@pytest.mark.parametrize("prec,spec,knobs", [("fp64", False, {}), ("fp64", True, {}), ("fp32", True, {}), ("fp64", False, {"EPI_TEAM": "warp"})],
+                         ids=["cell-interpreted", "cell-specialised", "cell-specialised-fp32", "warp-team"])
+def test_intervention_code_arithmetic_vs_reference(prec, spec, knobs, monkeypatch):
+    """expression programs with ADD / DIV / NEG tokens and mixed literals (interpreted on the device, generated as
+    straight-line code in the specialised build) against the unmodified reference (tools/gen_expr_golden.py)"""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    d, z = load("COVID_C_expr")
+    eng = EmuEngine(d, 1, prec)
+    if spec:
+        eng.attach_spec()
+    tol = 1e-9 if prec == "fp64" else 1e-4
+    day = 0
+    for a in z["rnd_actions"]:
+        for _ in range(7):
+            eng.step(a[None], 1)
+            assert x_err(eng.get_state("X"), z["rnd_X"][day], d) <= tol, day
+            assert cost_err(eng.get_state("cost"), z["rnd_cost"][day]) <= tol, day
+            if prec == "fp64":
+                assert int(eng.get_state("trace")[0, 0]) == int(z["rnd_nfev"][day])
+            day += 1
+    eng.close()

@@ -209,3 +209,31 @@ def test_facility_interaction_rows_renormalised_under_multipliers_above_one():
         nfev.append(o.trace["nfev"])
     assert np.array_equal(np.array(nfev), z["sched_nfev"])
     assert float(z["sched_plan_cpv"][0].min()) < 0  # the multipliers 1 - percentage are above one
+
+
+def test_intervention_code_arithmetic_beyond_the_shipped_shapes():
+    """Addition, division, unary minus, integer / float literals and a select total inside longer expressions (the shipped
+    JSONs only multiply and subtract): the recorder's numpy-scalar promotion and rounding points (export.py) and the
+    expression VM against the unmodified reference executing the Python code (tools/gen_expr_golden.py): float32
+    parameter tables and move tables of the first ten days bit-exact, cost rates to 1e-12, 84 days of trajectory."""
+    d, z = load("COVID_C_expr")
+    assert {3, 6, 7} <= set(int(x) for x in d.arrays["tok_op"])  # ADD, DIV, NEG
+    o = Oracle(d)
+    day, nfev = 0, []
+    for a in z["rnd_actions"]:
+        for _ in range(7):
+            o.step(a, 1)
+            assert x_err(o.X, z["rnd_X"][day], d) <= 1e-11 and cost_err(o.cost, z["rnd_cost"][day]) <= 1e-11, day
+            if day < 10:
+                p = o.params(0)
+                for k in ("mp", "ft", "fi", "mob"):
+                    assert np.array_equal(p[k], z[f"rnd_p_{k}"][day].reshape(p[k].shape)), (day, k)
+                assert np.array_equal(p["moves"], z[f"rnd_p_moves{day}"].reshape(p["moves"].shape)), day
+                assert np.allclose(p["cost"], z["rnd_p_cost"][day], rtol=1e-12, atol=0), day
+            nfev.append(o.trace["nfev"])
+            day += 1
+    assert np.array_equal(np.array(nfev), z["rnd_nfev"])
+    o = Oracle(d)
+    for day in range(len(z["sched_X"])):
+        o.day_step(z["sched_plan_cpv"][day], z["sched_plan_active"][day], init_programs=True)
+        assert x_err(o.X, z["sched_X"][day], d) <= 1e-11 and cost_err(o.cost, z["sched_cost"][day]) <= 1e-11, day
