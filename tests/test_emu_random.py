@@ -204,3 +204,47 @@ def test_locale_restricted_interventions_vs_oracle(name, prec, spec, knobs, monk
     print(f"{name} {prec} n_lc={eng.info.n_lc} kind={eng.info.team_kind}: X {worst:.2e} cost {worst_c:.2e}")
     assert worst <= TOL[prec] and worst_c <= TOL[prec]
     eng.close()
+
+
+@pytest.mark.parametrize("name,prec,spec,knobs", [
+    ("COVID_C", "fp64", False, {}), ("COVID_C", "fp64", True, {}), ("COVID_C", "fp32", True, {}),
+    ("COVID_C", "fp64", False, {"EPI_TEAM": "warp"}), ("syn_s", "fp32", True, {"EPI_GRP": "2", "EPI_GRP_S": "2"})],
+    ids=["cell-interpreted", "cell-specialised", "cell-specialised-fp32", "warp-team", "env-group-fp32"])
+def test_move_from_several_compartments_and_some_groups_vs_oracle(name, prec, spec, knobs, monkeypatch):
+    """a move whose source selector names several compartments (S and Qs -> V: two move slots fed by one op, the
+    departing population summed over both, executor.py:176-183) and only some groups; strong vaccination so that the
+    clamp binds when the sources run out"""
+    from epipolicy_rl_b200.desc import OP_MOVE
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    d = load(name)[0]
+    a = d.arrays
+    off, data = list(a["list_off"]), list(a["list_data"])
+    ids = []
+    for lst in ([0, 9], [0, 2]):  # compartments S, Qs; groups 0 and 2
+        data += lst
+        off.append(len(data))
+        ids.append(len(off) - 2)
+    arg = a["op_arg"].copy().reshape(-1, 8)
+    mv = int(np.where(a["op_kind"] == OP_MOVE)[0][0])
+    arg[mv, 0], arg[mv, 2], arg[mv, 5] = ids[0], ids[1], ids[1]
+    a["list_off"], a["list_data"], a["op_arg"] = np.array(off, np.int32), np.array(data, np.int32), arg.reshape(-1)
+    d.finalize()
+    n, weeks = 3, 5
+    acts = np.random.default_rng(9).uniform(0, 1, (weeks, n, d.A)).astype(np.float32)
+    acts[:, :, 0] = np.maximum(acts[:, :, 0], 0.5)
+    eng = EmuEngine(d, n, prec)
+    if spec:
+        eng.attach_spec()
+    assert eng.info.n_slot == 2
+    oracles = [Oracle(d) for _ in range(n)]
+    worst = worst_c = 0.0
+    for w in range(weeks):
+        obs, _, _ = eng.step(acts[w], 7)
+        for e, o in enumerate(oracles):
+            o_obs, _, _ = o.step(acts[w, e], 7)
+            worst = max(worst, x_err(obs[e], o_obs, d))
+            worst_c = max(worst_c, cost_err(eng.get_state("cost")[e], o.cost))
+    print(f"{name} {prec} kind={eng.info.team_kind}: X {worst:.2e} cost {worst_c:.2e}")
+    assert worst <= TOL[prec] and worst_c <= TOL[prec]
+    eng.close()
