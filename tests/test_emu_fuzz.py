@@ -1,0 +1,111 @@
+"""Randomised intervention selectors: every op of a scenario gets random locale / facility / group subsets (so that the
+plan compiler produces several locale classes and multiplier classes), facility-interaction multipliers randomly become
+facility-timespent multipliers, selects get random masks and value modes, moves random groups and locales - then the
+emulated kernels run random weekly actions against the oracle (which is pinned against the reference for every op kind
+in test_oracle_golden.py). Deterministic seeds."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+from emu_engine import EmuEngine  # noqa: E402
+from helpers import cost_err, load, x_err  # noqa: E402
+
+from epipolicy_rl_b200.desc import OP_ADD, OP_FI_MUL, OP_FT_MUL, OP_MOVE, OP_PARAM_MUL  # noqa: E402
+from oracle.oracle import Oracle  # noqa: E402
+
+TOL = {"fp64": 1e-9, "fp32": 1e-4}
+
+
+def variant(name, seed):
+    rng = np.random.default_rng(seed)
+    d, _ = load(name)
+    a = d.arrays
+    off, data = list(a["list_off"]), list(a["list_data"])
+
+    def newlist(lst):
+        data.extend(int(x) for x in lst)
+        off.append(len(data))
+        return len(off) - 2
+
+    def subset(n):
+        return sorted(rng.choice(n, size=rng.integers(1, n + 1), replace=False))
+
+    kind, arg = a["op_kind"].copy(), a["op_arg"].copy().reshape(-1, 8)
+    sel = np.asarray(a["sel_arg"]).copy().reshape(-1, 4)
+    for o in range(len(kind)):
+        if kind[o] == OP_PARAM_MUL:
+            if rng.uniform() < 0.7:
+                arg[o, 1] = newlist(subset(d.L))
+            if rng.uniform() < 0.5:
+                arg[o, 2] = newlist(subset(d.F))
+            if rng.uniform() < 0.5:
+                arg[o, 3] = newlist(subset(d.G))
+        elif kind[o] == OP_FI_MUL:
+            if rng.uniform() < 0.3:
+                kind[o] = OP_FT_MUL
+                arg[o, 3] = -1
+                if rng.uniform() < 0.5:
+                    arg[o, 2] = newlist(subset(d.G))
+            else:
+                if rng.uniform() < 0.5:
+                    arg[o, 2] = newlist(subset(d.G))
+                if rng.uniform() < 0.5:
+                    arg[o, 3] = newlist(subset(d.G))
+            if rng.uniform() < 0.6:
+                arg[o, 0] = newlist(subset(d.L))
+            if rng.uniform() < 0.4:
+                arg[o, 1] = newlist(subset(d.F))
+        elif kind[o] == OP_MOVE:
+            if rng.uniform() < 0.5:
+                g = newlist(subset(d.G))
+                arg[o, 2] = arg[o, 5] = g
+            if rng.uniform() < 0.4:
+                lo = newlist(subset(d.L))
+                arg[o, 1] = arg[o, 4] = lo
+        elif kind[o] == OP_ADD:
+            if rng.uniform() < 0.4:
+                arg[o, 1] = newlist(subset(d.L))
+    for s in range(len(sel)):
+        if rng.uniform() < 0.5:
+            sel[s, 1] = newlist(subset(d.L))
+        if rng.uniform() < 0.5:
+            sel[s, 2] = newlist(subset(d.G))
+        # ('change' is left where the scenario has it: over all compartments it is zero up to rounding noise)
+        if rng.uniform() < 0.3 and sel[s, 3] == 0:
+            sel[s, 3] = 1
+    a["list_off"], a["list_data"] = np.array(off, np.int32), np.array(data, np.int32)
+    a["op_kind"], a["op_arg"], a["sel_arg"] = kind, arg.reshape(-1), sel.reshape(-1)
+    return d.finalize()
+
+
+CASES = ([("COVID_C", s, "fp64", False, {}) for s in range(6)] + [("COVID_C", s, "fp32", True, {}) for s in range(6)] +
+         [("SIRV_B", s, "fp64", True, {}) for s in range(3)] + [("COVID_C", s, "fp64", False, {"EPI_TEAM": "warp"}) for s in range(2)] +
+         [("syn_s", s, "fp64", True, {"EPI_GRP": "0"}) for s in range(2)] +
+         [("syn_s", s, "fp32", True, {"EPI_GRP": "2", "EPI_GRP_S": "2"}) for s in range(3)])
+
+
+@pytest.mark.parametrize("name,seed,prec,spec,knobs", CASES,
+                         ids=[f"{n}-{s}-{p}-{'spec' if sp else 'interp'}{''.join('-' + v for v in k.values())}" for n, s, p, sp, k in CASES])
+def test_random_selectors_vs_oracle(name, seed, prec, spec, knobs, monkeypatch):
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    d = variant(name, seed)
+    n, weeks = 3, 2
+    acts = np.random.default_rng(1000 + seed).uniform(0, 1, (weeks, n, d.A)).astype(np.float32)
+    eng = EmuEngine(d, n, prec)
+    if spec:
+        eng.attach_spec()
+    oracles = [Oracle(d) for _ in range(n)]
+    worst = worst_c = 0.0
+    for w in range(weeks):
+        obs, _, _ = eng.step(acts[w], 7)
+        for e, o in enumerate(oracles):
+            o_obs, _, _ = o.step(acts[w, e], 7)
+            worst = max(worst, x_err(obs[e], o_obs, d))
+            worst_c = max(worst_c, cost_err(eng.get_state("cost")[e], o.cost))
+    print(f"{name} seed {seed} {prec}: kind {eng.info.team_kind} n_lc {eng.info.n_lc} n_cls {eng.info.n_cls} X {worst:.1e} cost {worst_c:.1e}")
+    assert worst <= TOL[prec] and worst_c <= TOL[prec]
+    eng.close()
