@@ -109,3 +109,47 @@ def test_random_selectors_vs_oracle(name, seed, prec, spec, knobs, monkeypatch):
     print(f"{name} seed {seed} {prec}: kind {eng.info.team_kind} n_lc {eng.info.n_lc} n_cls {eng.info.n_cls} X {worst:.1e} cost {worst_c:.1e}")
     assert worst <= TOL[prec] and worst_c <= TOL[prec]
     eng.close()
+
+
+@pytest.mark.parametrize("seed", range(5))
+@pytest.mark.parametrize("prec,spec", [("fp64", False), ("fp32", True)], ids=["fp64-interp", "fp32-spec"])
+def test_random_mobility_multiplier_selections_vs_oracle(seed, prec, spec):
+    """the border scenario's mobility multipliers with random modes, groups and from / to locale subsets, stepped through
+    the schedule's programs with randomly redrawn control parameters, day by day against the oracle"""
+    from epipolicy_rl_b200.desc import OP_MOB_MUL
+    rng = np.random.default_rng(500 + seed)
+    d, z = load("COVID_C_border")
+    a = d.arrays
+    off, data = list(a["list_off"]), list(a["list_data"])
+
+    def newlist(n):
+        data.extend(int(x) for x in sorted(rng.choice(n, size=rng.integers(1, n + 1), replace=False)))
+        off.append(len(data))
+        return len(off) - 2
+
+    arg = a["op_arg"].copy().reshape(-1, 8)
+    for o in np.where(a["op_kind"] == OP_MOB_MUL)[0]:
+        arg[o, :4] = [rng.integers(0, d.M), newlist(d.G), newlist(d.L), newlist(d.L)]
+    a["list_off"], a["list_data"], a["op_arg"] = np.array(off, np.int32), np.array(data, np.int32), arg.reshape(-1)
+    d.finalize()
+    n, T = 3, 12
+    cpv = np.repeat(z["sched_plan_cpv"][:T, None, :], n, 1).astype(np.float32)
+    act = np.repeat(z["sched_plan_active"][:T, None, :], n, 1).astype(np.uint8)
+    free = np.where(d.cp_min != d.cp_max)[0]
+    for e in range(n):
+        for t in range(T):
+            if t == 0 or rng.uniform() < 0.4:
+                cpv[t:, e, free] = rng.uniform(d.cp_min[free], d.cp_max[free]).astype(np.float32)
+    eng = EmuEngine(d, n, prec)
+    if spec:
+        eng.attach_spec()
+    oracles = [Oracle(d) for _ in range(n)]
+    worst = worst_c = 0.0
+    for t in range(T):
+        eng.step_plan(cpv[t], act[t], True, 1)
+        for e, o in enumerate(oracles):
+            o.day_step(cpv[t, e], act[t, e], init_programs=True)
+            worst = max(worst, x_err(eng.get_state("X")[e], o.X, d))
+            worst_c = max(worst_c, cost_err(eng.get_state("cost")[e], o.cost))
+    assert worst <= TOL[prec] and worst_c <= TOL[prec], (worst, worst_c)
+    eng.close()
