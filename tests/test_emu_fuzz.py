@@ -153,3 +153,46 @@ def test_random_mobility_multiplier_selections_vs_oracle(seed, prec, spec):
             worst_c = max(worst_c, cost_err(eng.get_state("cost")[e], o.cost))
     assert worst <= TOL[prec] and worst_c <= TOL[prec], (worst, worst_c)
     eng.close()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_cross_locale_move_selections_match_or_are_refused(seed):
+    """the xmove scenario's two cross-locale moves with random source / target locale subsets and groups: either the
+    engine refuses the table (its result would depend on the reference's dictionary order) or the team kernel matches
+    the oracle day by day"""
+    from epipolicy_rl_b200 import lib
+    from epipolicy_rl_b200.desc import OP_MOVE
+    rng = np.random.default_rng(700 + seed)
+    d, z = load("COVID_C_xmove")
+    a = d.arrays
+    off, data = list(a["list_off"]), list(a["list_data"])
+
+    def newlist(n, k=None):
+        data.extend(int(x) for x in sorted(rng.choice(n, size=k or rng.integers(1, n + 1), replace=False)))
+        off.append(len(data))
+        return len(off) - 2
+
+    arg = a["op_arg"].copy().reshape(-1, 8)
+    for o in np.where(a["op_kind"] == OP_MOVE)[0][-2:]:  # the schedule program's two cross-locale moves
+        g = newlist(d.G)
+        arg[o, 1], arg[o, 4], arg[o, 2], arg[o, 5] = newlist(d.L), newlist(d.L), g, g
+    a["list_off"], a["list_data"], a["op_arg"] = np.array(off, np.int32), np.array(data, np.int32), arg.reshape(-1)
+    d.finalize()
+    try:
+        eng = EmuEngine(d, 2, "fp64")
+    except lib.EpiError as e:
+        assert e.code == -2
+        return
+    T = 15
+    oracles = [Oracle(d) for _ in range(2)]
+    cpv = np.repeat(z["sched_plan_cpv"][:T, None, :], 2, 1).astype(np.float32)
+    act = np.repeat(z["sched_plan_active"][:T, None, :], 2, 1).astype(np.uint8)
+    free = np.where(d.cp_min != d.cp_max)[0]
+    cpv[:, 1, free] = rng.uniform(d.cp_min[free], d.cp_max[free], (T, len(free))).astype(np.float32)
+    for t in range(T):
+        eng.step_plan(cpv[t], act[t], True, 1)
+        for e, o in enumerate(oracles):
+            o.day_step(cpv[t, e], act[t, e], init_programs=True)
+            assert x_err(eng.get_state("X")[e], o.X, d) <= 1e-9, (t, e)
+            assert cost_err(eng.get_state("cost")[e], o.cost) <= 1e-9, (t, e)
+    eng.close()
