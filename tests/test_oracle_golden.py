@@ -237,3 +237,22 @@ def test_intervention_code_arithmetic_beyond_the_shipped_shapes():
     for day in range(len(z["sched_X"])):
         o.day_step(z["sched_plan_cpv"][day], z["sched_plan_active"][day], init_programs=True)
         assert x_err(o.X, z["sched_X"][day], d) <= 1e-11 and cost_err(o.cost, z["sched_cost"][day]) <= 1e-11, day
+
+
+def test_schedule_on_single_locales_several_locale_classes():
+    """interventions scheduled on single locales (tools/gen_reporter_lc_golden.py): the oracle against the unmodified
+    reference, float32 tables of the first ten days bit-exact"""
+    d, z = load("COVID_C_lc")
+    o = Oracle(d)
+    nfev = []
+    for day in range(len(z["sched_X"])):
+        o.day_step(z["sched_plan_cpv"][day], z["sched_plan_active"][day], init_programs=True)
+        assert x_err(o.X, z["sched_X"][day], d) <= 1e-11 and cost_err(o.cost, z["sched_cost"][day]) <= 1e-11, day
+        if day < 10:
+            p = o.params(0)
+            for k in ("mp", "ft", "fi", "mob"):
+                assert np.array_equal(p[k], z[f"sched_p_{k}"][day].reshape(p[k].shape)), (day, k)
+        nfev.append(o.trace["nfev"])
+    assert np.array_equal(np.array(nfev), z["sched_nfev"])
+    mp = z["sched_p_mp"][0]
+    assert not np.array_equal(mp[:, 0], mp[:, 1])  # the locales' parameters differ: masks in one, screening in another
