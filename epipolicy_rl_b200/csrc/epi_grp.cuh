@@ -1082,6 +1082,11 @@ __device__ __forceinline__ void step_group(const DevPlan& P, const DevState& S, 
       }
       mc = (mc + EPI_GRP_CHUNK - 1) / EPI_GRP_CHUNK * EPI_GRP_CHUNK;
       mr = (mr + EPI_GRP_CHUNK - 1) / EPI_GRP_CHUNK * EPI_GRP_CHUNK;
+#ifdef EPI_HOST_EMU
+      // the host emulation's __syncwarp is a CTA-wide barrier: every warp has to walk the same number of chunks (the
+      // CTA's padded row length; the padding gathers the own locale with weight 0, so the sums do not change)
+      mc = spec::grp_nqc; mr = spec::grp_nqr;
+#endif
       b.nq_w = mc | (mr << 16);
     }
     // selects / MOVE ops covering this thread's cell, and each select's compartment mask and mode

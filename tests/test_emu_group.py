@@ -108,3 +108,20 @@ def test_group_kernel_run_plan_one_launch(monkeypatch):
         assert np.allclose(one.acc_days[t], daily.acc(), rtol=1e-4, atol=1e-3), t
     assert x_err(one.get_state("X"), daily.get_state("X"), d) <= 1e-5
     one.close(); daily.close()
+
+
+@pytest.mark.parametrize("S", [1, 2, 3])
+def test_group_kernel_awkward_dimensions_vs_reference(S, monkeypatch):
+    """13 locales x 5 groups x 3 facilities (tools/gen_syn_odd.py): a locale's groups straddle warp boundaries, G is neither
+    16 nor a multiple of 4 and F is odd, so the mixing pass takes its scalar path and the warps of a CTA have gather rows
+    of different lengths - against the unmodified reference's per-day trajectory"""
+    d, z = load("syn_odd")
+    grp = _group_engine(d, 2, S, monkeypatch)
+    day = 0
+    for a in z["rnd_actions"]:
+        for _ in range(7):
+            grp.step(np.repeat(a[None], 2, 0), 1)
+            assert x_err(grp.get_state("X")[1], z["rnd_X"][day], d) <= TOL, day
+            assert cost_err(grp.get_state("cost")[1], z["rnd_cost"][day]) <= TOL, day
+            day += 1
+    grp.close()

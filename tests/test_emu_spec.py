@@ -84,3 +84,24 @@ def test_specialised_cell_kernel_with_mobility_multipliers(prec):
         if prec == "fp64":
             assert int(eng.get_state("trace")[0, 0]) == int(z["sched_nfev"][day])
     eng.close()
+
+
+@pytest.mark.parametrize("prec,spec", [("fp64", False), ("fp64", True), ("fp32", True)], ids=["interpreted", "specialised", "specialised-fp32"])
+def test_env_kernel_awkward_dimensions_vs_reference(prec, spec, monkeypatch):
+    """13 locales x 5 groups x 3 facilities through the env kernel against the unmodified reference (tools/gen_syn_odd.py)"""
+    monkeypatch.setenv("EPI_GRP", "0")
+    d, z = load("syn_odd")
+    eng = EmuEngine(d, 2, prec)
+    if spec:
+        eng.attach_spec()
+    assert eng.info.team_kind == 3
+    day = 0
+    for a in z["rnd_actions"]:
+        for _ in range(7):
+            eng.step(np.repeat(a[None], 2, 0), 1)
+            assert x_err(eng.get_state("X")[1], z["rnd_X"][day], d) <= TOL[prec], day
+            assert cost_err(eng.get_state("cost")[1], z["rnd_cost"][day]) <= TOL[prec], day
+            if prec == "fp64":
+                assert int(eng.get_state("trace")[0, 0]) == int(z["rnd_nfev"][day])
+            day += 1
+    eng.close()

@@ -256,3 +256,18 @@ def test_schedule_on_single_locales_several_locale_classes():
     assert np.array_equal(np.array(nfev), z["sched_nfev"])
     mp = z["sched_p_mp"][0]
     assert not np.array_equal(mp[:, 0], mp[:, 1])  # the locales' parameters differ: masks in one, screening in another
+
+
+def test_synthetic_scenario_with_awkward_dimensions():
+    """13 locales x 5 groups x 3 facilities (tools/gen_syn_odd.py): the oracle against the unmodified reference"""
+    d, z = load("syn_odd")
+    assert (d.L, d.G, d.F) == (13, 5, 3)
+    o = Oracle(d)
+    day, nfev = 0, []
+    for a in z["rnd_actions"]:
+        for _ in range(7):
+            o.step(a, 1)
+            assert x_err(o.X, z["rnd_X"][day], d) <= 1e-11 and cost_err(o.cost, z["rnd_cost"][day]) <= 1e-11, day
+            nfev.append(o.trace["nfev"])
+            day += 1
+    assert np.array_equal(np.array(nfev), z["rnd_nfev"])

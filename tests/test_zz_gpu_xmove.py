@@ -69,3 +69,24 @@ def test_non_conserving_model_vs_reference_on_device(prec):
     ref = z["rnd_flat_last"]
     assert np.max(np.abs(eng.get_state("flat")[n - 1] - ref) / (np.abs(ref) + 1e-3)) <= tol
     eng.close()
+
+
+@pytest.mark.parametrize("prec,knob", [("fp64", "0"), ("fp32", "0"), ("fp32", "")], ids=["env-fp64", "env-fp32", "env-group-fp32"])
+def test_awkward_dimensions_vs_reference_on_device(prec, knob, monkeypatch):
+    """13 locales x 5 groups x 3 facilities (tools/gen_syn_odd.py) on the GPU: the env kernel in both precisions and the
+    env-group kernel (locales straddling warps, scalar mixing path, per-warp gather row lengths - the last of which the
+    host emulation cannot reproduce, its __syncwarp being CTA-wide) against the unmodified reference's weekly observations"""
+    from epipolicy_rl_b200.engine import BatchedEpidemic
+    if knob:
+        monkeypatch.setenv("EPI_GRP", knob)
+    d, z = load("syn_odd")
+    n = 6
+    eng = BatchedEpidemic(d, n, device=0, precision=prec)
+    tol = 1e-9 if prec == "fp64" else 1e-4
+    for w, a in enumerate(z["rnd_actions"]):
+        obs, rew, _ = eng.step(torch.from_numpy(np.repeat(a[None], n, 0)).cuda(), 7)
+        o = obs.double().cpu().numpy()
+        for e in (0, n - 1):
+            assert x_err(o[e], z["rnd_obs_weekly"][w], d) <= tol, (w, e)
+            assert abs(float(rew[e]) - z["rnd_rewards"][w]) <= tol * abs(z["rnd_rewards"][w]), (w, e)
+    eng.close()
