@@ -105,3 +105,26 @@ def test_env_kernel_awkward_dimensions_vs_reference(prec, spec, monkeypatch):
                 assert int(eng.get_state("trace")[0, 0]) == int(z["rnd_nfev"][day])
             day += 1
     eng.close()
+
+
+@pytest.mark.parametrize("prec,spec", [("fp64", False), ("fp64", True), ("fp32", True)], ids=["interpreted", "specialised", "specialised-fp32"])
+def test_cell_kernel_with_more_than_four_locales_vs_reference(prec, spec):
+    """5 locales x 3 groups x 3 facilities (tools/gen_syn_odd.py): the cell kernel's sparse CSC / CSR mobility gathers (its
+    dense-register form covers L <= 4, i.e. every shipped scenario) with two envs per warp, four envs = two warps,
+    against the unmodified reference"""
+    d, z = load("syn_cell")
+    eng = EmuEngine(d, 4, prec)
+    if spec:
+        eng.attach_spec()
+    assert eng.info.team_kind == 2 and eng.info.envs_per_cta == 2
+    day = 0
+    for a in z["rnd_actions"]:
+        for _ in range(7):
+            eng.step(np.repeat(a[None], 4, 0), 1)
+            for e in (0, 3):
+                assert x_err(eng.get_state("X")[e], z["rnd_X"][day], d) <= TOL[prec], (day, e)
+                assert cost_err(eng.get_state("cost")[e], z["rnd_cost"][day]) <= TOL[prec], (day, e)
+            if prec == "fp64":
+                assert int(eng.get_state("trace")[3, 0]) == int(z["rnd_nfev"][day])
+            day += 1
+    eng.close()

@@ -271,3 +271,18 @@ def test_synthetic_scenario_with_awkward_dimensions():
             nfev.append(o.trace["nfev"])
             day += 1
     assert np.array_equal(np.array(nfev), z["rnd_nfev"])
+
+
+def test_synthetic_scenario_in_the_cell_kernels_shape_space():
+    """5 locales x 3 groups x 3 facilities (tools/gen_syn_odd.py): L*G <= 32 with more than four locales"""
+    d, z = load("syn_cell")
+    assert (d.L, d.G, d.F) == (5, 3, 3)
+    o = Oracle(d)
+    day, nfev = 0, []
+    for a in z["rnd_actions"]:
+        for _ in range(7):
+            o.step(a, 1)
+            assert x_err(o.X, z["rnd_X"][day], d) <= 1e-11 and cost_err(o.cost, z["rnd_cost"][day]) <= 1e-11, day
+            nfev.append(o.trace["nfev"])
+            day += 1
+    assert np.array_equal(np.array(nfev), z["rnd_nfev"])

@@ -90,3 +90,22 @@ def test_awkward_dimensions_vs_reference_on_device(prec, knob, monkeypatch):
             assert x_err(o[e], z["rnd_obs_weekly"][w], d) <= tol, (w, e)
             assert abs(float(rew[e]) - z["rnd_rewards"][w]) <= tol * abs(z["rnd_rewards"][w]), (w, e)
     eng.close()
+
+
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+def test_cell_kernel_with_more_than_four_locales_on_device(prec):
+    """5 locales x 3 groups x 3 facilities (tools/gen_syn_odd.py): the specialised cell kernel with sparse mobility gathers
+    (L > 4) and two envs per warp on the GPU against the unmodified reference's weekly observations and rewards"""
+    from epipolicy_rl_b200.engine import BatchedEpidemic
+    d, z = load("syn_cell")
+    n = 7
+    eng = BatchedEpidemic(d, n, device=0, precision=prec)
+    assert eng.info.team_kind == 2 and eng.info.specialized == 1
+    tol = 1e-9 if prec == "fp64" else 1e-4
+    for w, a in enumerate(z["rnd_actions"]):
+        obs, rew, _ = eng.step(torch.from_numpy(np.repeat(a[None], n, 0)).cuda(), 7)
+        o = obs.double().cpu().numpy()
+        for e in (0, n - 1):
+            assert x_err(o[e], z["rnd_obs_weekly"][w], d) <= tol, (w, e)
+            assert abs(float(rew[e]) - z["rnd_rewards"][w]) <= tol * abs(z["rnd_rewards"][w]), (w, e)
+    eng.close()

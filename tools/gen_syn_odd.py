@@ -4,7 +4,8 @@ are 20x4x8, 100x8x8 and 1000x16x8, so the kernels' vectorised paths for G % 4 ==
 they exercise).
 
   PYTHONDONTWRITEBYTECODE=1 PYTHONPATH=tools/gym_shim:/root/reference:tools:. python tools/gen_syn_odd.py
--> tests/golden/desc_syn_odd.npz, tests/golden/traj_syn_odd.npz
+-> tests/golden/desc_syn_odd.npz, traj_syn_odd.npz; desc_syn_cell.npz, traj_syn_cell.npz (5 x 3 x 3: the cell kernel with
+   more than four locales and two envs per warp)
 """
 import json
 import os
@@ -18,9 +19,9 @@ from epipolicy_rl_b200 import synth  # noqa: E402
 from epipolicy_rl_b200.export import export_static  # noqa: E402
 
 
-def main():
+def main(name="syn_odd", dims=(13, 5, 3)):
     t0 = time.time()
-    name, (L, G, F) = "syn_odd", (13, 5, 3)
+    L, G, F = dims
     base = json.load(open(os.path.join(gg.REF, "jsons", "COVID_C.json")))
     env = EpiEnv(synth.make_session(base, L, G, F, seed=20260202))
     d = export_static(env.epi)
@@ -35,3 +36,6 @@ def main():
 
 if __name__ == "__main__":
     main()
+    # the cell kernel's shape space: L*G <= 32 with more than 4 locales (its dense-register mobility covers L <= 4 only;
+    # every shipped scenario has L <= 3) and two envs per warp
+    main("syn_cell", (5, 3, 3))
