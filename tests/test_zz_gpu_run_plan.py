@@ -10,7 +10,7 @@ import pytest
 from helpers import cost_err, load, x_err  # noqa: F401
 
 torch = pytest.importorskip("torch")
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600, method="thread")]  # a hung kernel must not hang the GPU tier
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 

@@ -6,7 +6,7 @@ import pytest
 from helpers import cost_err, load, x_err
 
 torch = pytest.importorskip("torch")
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600, method="thread")]  # a hung kernel must not hang the GPU tier
 
 
 @pytest.mark.parametrize("prec", ["fp64", "fp32"])
