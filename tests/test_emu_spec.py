@@ -128,3 +128,22 @@ def test_cell_kernel_with_more_than_four_locales_vs_reference(prec, spec):
                 assert int(eng.get_state("trace")[3, 0]) == int(z["rnd_nfev"][day])
             day += 1
     eng.close()
+
+
+@pytest.mark.parametrize("prec,spec", [("fp64", False), ("fp64", True), ("fp32", True)], ids=["interpreted", "specialised", "specialised-fp32"])
+def test_cell_kernel_with_a_full_warp_per_env_vs_reference(prec, spec):
+    """2 locales x 16 groups x 3 facilities: L*G == 32, the largest scenario of the cell kernel (one env per warp, no idle
+    lanes), against the unmodified reference (tools/gen_syn_odd.py)"""
+    d, z = load("syn_lg32")
+    eng = EmuEngine(d, 2, prec)
+    if spec:
+        eng.attach_spec()
+    assert eng.info.team_kind == 2 and eng.info.envs_per_cta == 1
+    day = 0
+    for a in z["rnd_actions"]:
+        for _ in range(7):
+            eng.step(np.repeat(a[None], 2, 0), 1)
+            assert x_err(eng.get_state("X")[1], z["rnd_X"][day], d) <= TOL[prec], day
+            assert cost_err(eng.get_state("cost")[1], z["rnd_cost"][day]) <= TOL[prec], day
+            day += 1
+    eng.close()

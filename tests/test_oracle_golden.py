@@ -273,10 +273,12 @@ def test_synthetic_scenario_with_awkward_dimensions():
     assert np.array_equal(np.array(nfev), z["rnd_nfev"])
 
 
-def test_synthetic_scenario_in_the_cell_kernels_shape_space():
-    """5 locales x 3 groups x 3 facilities (tools/gen_syn_odd.py): L*G <= 32 with more than four locales"""
-    d, z = load("syn_cell")
-    assert (d.L, d.G, d.F) == (5, 3, 3)
+@pytest.mark.parametrize("name,dims", [("syn_cell", (5, 3, 3)), ("syn_lg32", (2, 16, 3))])
+def test_synthetic_scenario_in_the_cell_kernels_shape_space(name, dims):
+    """5 x 3 x 3 (L*G <= 32 with more than four locales) and 2 x 16 x 3 (L*G == 32: a full warp per env, the boundary of
+    the cell kernel) through the unmodified reference (tools/gen_syn_odd.py)"""
+    d, z = load(name)
+    assert (d.L, d.G, d.F) == dims
     o = Oracle(d)
     day, nfev = 0, []
     for a in z["rnd_actions"]:

@@ -91,12 +91,14 @@ def test_awkward_dimensions_vs_reference_on_device(prec):
     eng.close()
 
 
+@pytest.mark.parametrize("name", ["syn_cell", "syn_lg32"])
 @pytest.mark.parametrize("prec", ["fp64", "fp32"])
-def test_cell_kernel_with_more_than_four_locales_on_device(prec):
-    """5 locales x 3 groups x 3 facilities (tools/gen_syn_odd.py): the specialised cell kernel with sparse mobility gathers
-    (L > 4) and two envs per warp on the GPU against the unmodified reference's weekly observations and rewards"""
+def test_cell_kernel_shape_space_on_device(prec, name):
+    """5 x 3 x 3 (sparse mobility gathers, L > 4, two envs per warp) and 2 x 16 x 3 (L*G == 32, a full warp per env)
+    (tools/gen_syn_odd.py): the specialised cell kernel on the GPU against the unmodified reference's weekly observations
+    and rewards"""
     from epipolicy_rl_b200.engine import BatchedEpidemic
-    d, z = load("syn_cell")
+    d, z = load(name)
     n = 7
     eng = BatchedEpidemic(d, n, device=0, precision=prec)
     assert eng.info.team_kind == 2 and eng.info.specialized == 1

@@ -39,3 +39,4 @@ if __name__ == "__main__":
     # the cell kernel's shape space: L*G <= 32 with more than 4 locales (its dense-register mobility covers L <= 4 only;
     # every shipped scenario has L <= 3) and two envs per warp
     main("syn_cell", (5, 3, 3))
+    main("syn_lg32", (2, 16, 3))  # L*G == 32: a full warp per env, the largest scenario of the cell kernel
